@@ -1,0 +1,131 @@
+/*
+ * paramol_b200.h -- C ABI of the B200-native objective-evaluation path (libparamol_b200.so).
+ *
+ * The reference (JMorado/ParaMol, /root/reference) is pure Python and has no FFI of its own: the
+ * hot path sits behind duck-typed Python seams that end in calls into the third-party OpenMM library.
+ * Each entry point below names the reference interface it replaces (file:line under /root/reference).
+ * INTEGRATION.md shows the ctypes stub a ParaMol maintainer would add to bind them.
+ *
+ * Conventions
+ * -----------
+ *  - every function returns 0 on success, non-zero on error; pm_last_error() gives the message
+ *    (thread-local).  There is NO CPU fallback: without a CUDA device every compute call fails.
+ *  - "dev" pointers are CUDA device pointers owned by the caller (the Python host layer allocates
+ *    them as torch tensors); "host" pointers are ordinary host memory.  No torch types cross the ABI.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All launches are
+ *    asynchronous on that stream unless the function name ends in _host.
+ *  - units are OpenMM's: nm, kJ/mol, rad, elementary charge.
+ *  - one handle per (topology, device); handles are not thread-safe, distinct handles are independent.
+ *
+ * Parameter "slots" (the physical MM parameter table; what an OpenMM Context holds after
+ * OpenMMEngine.set_bonded_parameters / set_nonbonded_parameters, ParaMol/MM_engines/openmm.py:590-756),
+ * one row of `pm_n_slots()` doubles per parameter vector:
+ *    [ (r0, k)            x n_bonds      ]   HarmonicBondForce
+ *    [ (theta0, k)        x n_angles     ]   HarmonicAngleForce
+ *    [ (phase, k)         x n_torsions   ]   PeriodicTorsionForce (periodicity is topology)
+ *    [ (q, sigma, eps)    x n_atoms      ]   NonbondedForce particles
+ *    [ (qq, sigma, eps)   x n_exceptions ]   NonbondedForce exceptions
+ *
+ * Conformation "tiles": conformations are kept resident in HBM as tiles of PM_TILE=32 conformations,
+ * tile t = doubles [3*n_atoms][32] with the conformation index fastest (a warp reads one row as one
+ * coalesced 256-byte line and a whole tile is one contiguous TMA bulk copy).  pm_pack_tiles converts
+ * from the reference's [S][N][3] C-order arrays (ParaMolSystem.ref_coordinates / ref_forces,
+ * ParaMol/System/system.py:85-123).
+ */
+#ifndef PARAMOL_B200_H
+#define PARAMOL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_TILE 32
+#define PM_NPARTIAL 8 /* doubles per (parameter vector) row written by pm_reduce_objective */
+
+typedef struct pm_handle_s *pm_handle;
+
+/* Topology: what app.AmberPrmtopFile(...).createSystem(...) hands to ParaMol
+ * (ParaMol/MM_engines/openmm.py:161-254) minus the parameter values.  All arrays are host int32. */
+typedef struct pm_topology {
+    int n_atoms;
+    int n_bonds;      const int *bond_idx;       /* [n_bonds][2]      */
+    int n_angles;     const int *angle_idx;      /* [n_angles][3]     */
+    int n_torsions;   const int *torsion_idx;    /* [n_torsions][4]   */
+                      const int *torsion_per;    /* [n_torsions]      */
+    int n_exceptions; const int *exception_idx;  /* [n_exceptions][2] */
+                      const int *exception_active; /* [n_exceptions] 1: interacts with its own (qq,sigma,eps)
+                                                      (scaled 1-4 pair); 0: pure exclusion            */
+    int nonbonded_method;   /* 0 NoCutoff ; 1 CutoffNonPeriodic with reaction field (openmm.py:114) */
+    double cutoff;          /* nm, method 1 only */
+    double rf_dielectric;   /* method 1 only     */
+    double one_4pi_eps0;    /* Coulomb constant, 138.935456 for the OpenMM 7.x the reference pins */
+} pm_topology;
+
+const char *pm_last_error(void);
+int pm_version(void);
+/* number of CUDA devices visible (0 = none; compute calls will fail) */
+int pm_device_count(void);
+
+/* ---- handle ------------------------------------------------------------------------------------ */
+/* Replaces OpenMMEngine.init_openmm / Context creation (ParaMol/MM_engines/openmm.py:161-254). */
+int pm_create(const pm_topology *topo, int device, pm_handle *out);
+int pm_destroy(pm_handle h);
+int pm_n_slots(pm_handle h);          /* doubles per parameter vector (layout above)           */
+int pm_n_derived(pm_handle h);        /* doubles per parameter vector of the derived table      */
+int pm_n_pairs(pm_handle h);          /* interacting pairs (plain pairs + active exceptions)    */
+long pm_n_tiles(long n_conf);         /* ceil(n_conf / PM_TILE)                                  */
+long pm_tile_doubles(pm_handle h);    /* 3 * n_atoms * PM_TILE                                   */
+/* interacting pair list, bit-exact indexing contract: out [n_pairs][3] = (i, j, exception index or -1) */
+int pm_get_pairs(pm_handle h, int *out_host);
+/* launch geometry chosen for the E+F kernel (for the roofline bookkeeping in bench.py) */
+int pm_launch_info(pm_handle h, int with_forces, int *grid, int *block, int *smem_bytes, int *warps_per_cta);
+
+/* Per-atom 3x3 force metric M_j used by the force residual  sum_j dF_j^T M_j dF_j :
+ * inverse covariance of the QM forces ("components", ParaMol/Objective_function/Properties/force_property.py:85-101,126-173)
+ * or I / var_j ("norm", :102-117,175-202).  host [n_atoms][9]. */
+int pm_set_force_metric(pm_handle h, const double *metric_host);
+
+/* ---- conformations ---------------------------------------------------------------------------- */
+/* [S][N][3] (dev, C order) -> tiles (dev, pm_n_tiles(S) * pm_tile_doubles doubles); the last tile is
+ * padded by repeating the last conformation.  Replaces the per-conformation context.setPositions of
+ * ParaMol/System/system.py:333-338,349-354: coordinates are staged once and stay resident. */
+int pm_pack_tiles(pm_handle h, const double *src_dev, long n_conf, double *tiles_dev, void *stream);
+int pm_unpack_tiles(pm_handle h, const double *tiles_dev, long n_conf, double *dst_dev, void *stream);
+
+/* ---- parameters -------------------------------------------------------------------------------- */
+/* slots [P][pm_n_slots] (dev) -> derived [P][pm_n_derived] (dev): combining rules, c12/c6/Coulomb products
+ * per interacting pair, cos/sin of torsion phases.  Replaces force.set*Parameters +
+ * updateParametersInContext (ParaMol/MM_engines/openmm.py:507-588, 661-756). */
+int pm_prepare_params(pm_handle h, const double *slots_dev, int n_vec, double *derived_dev, void *stream);
+
+/* ---- evaluation -------------------------------------------------------------------------------- */
+/* E (+F) of every conformation for every parameter vector.
+ *   emm_dev   [P][S]            MM energies                 (ParaMolSystem.get_energies_ensemble, system.py:340-354)
+ *   fres_dev  [P][S] or NULL    sum_j dF^T M_j dF per conformation with dF = F_mm - F_ref
+ *                               (ForceProperty.calculate_property inner loops, force_property.py:85-117)
+ *   fmm_tiles_dev [P][tiles] or NULL  MM forces in tile layout (get_forces_ensemble, system.py:324-338)
+ * fref_tiles_dev may be NULL when fres_dev is NULL.  with_forces=0 runs the energy-only kernel. */
+int pm_eval(pm_handle h, const double *derived_dev, int n_vec,
+            const double *coord_tiles_dev, const double *fref_tiles_dev, long n_conf,
+            int with_forces, double *emm_dev, double *fres_dev, double *fmm_tiles_dev, void *stream);
+
+/* Weighted residual partial sums of this rank's conformations, one row of PM_NPARTIAL doubles per vector:
+ *   [0] sum d'          d' = (E_ref - E_mm) - d_shift       (energy_property.py:99-108)
+ *   [1] sum w d'   [2] sum w d'^2   [3] sum w   [4] sum w * fres   [5] count   [6],[7] reserved (0)
+ * weights_dev NULL = w_s = 1.  Rows from different ranks add (one allreduce), then
+ *   ENERGY = ([2] - 2 m [1] + m^2 [3]) / var(E_ref),  m = [0]/[5];   FORCE = [4] / (3 N).
+ * scratch_dev: at least pm_reduce_scratch_doubles(P) doubles. */
+long pm_reduce_scratch_doubles(int n_vec);
+int pm_reduce_objective(const double *emm_dev, const double *fres_dev, const double *eref_dev,
+                        const double *weights_dev, double d_shift, int n_vec, long n_conf,
+                        double *partials_dev, double *scratch_dev, void *stream);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* Measured FMA-pipe peak of the current device: runs a register-only FMA kernel and returns FLOP/s
+ * (2 flop per FMA) in *flops and the kernel time in *ms.  fp64 = 1: DFMA, 0: FFMA. */
+int pm_measure_fma_peak(int device, int fp64, int iters, double *flops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAMOL_B200_H */

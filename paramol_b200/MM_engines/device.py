@@ -1,0 +1,272 @@
+# -*- coding: utf-8 -*-
+"""
+Description
+-----------
+Thin Python layer over the C ABI (``include/paramol_b200.h``): :obj:`DeviceTopology` owns one ``pm_handle``
+and :obj:`DeviceEnsemble` keeps the conformations of one ParaMol system resident in HBM (tile layout) and
+launches the evaluation / reduction kernels on them.  PyTorch is used only for device memory and streams.
+
+This is the layer that replaces the ``context.setPositions -> context.getState`` loops of
+``ParaMol/System/system.py:324-354`` and ``ParaMol/Objective_function/cpu_objective_function.py:67-108``.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from .._lib import B200Error, PmTopology, c_int_p, c_double_p
+
+NPARTIAL = 8
+TILE = 32
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _stream_ptr(device):
+    torch = _torch()
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceTopology:
+    """
+    One ``pm_handle``: the topology "program" of a molecule on one GPU.
+
+    Parameters
+    ----------
+    mm_system : :obj:`paramol_b200.MM_engines.mm_system.MMSystem`
+        Term lists in OpenMM-System order.  Exceptions whose initial chargeProd and epsilon are both zero are
+        pure exclusions (OpenMM decides this once, when the Context is created; see the note in
+        ``ParaMol/MM_engines/openmm.py:622-626``); every other exception is a scaled 1-4 interaction.
+    device : int or None
+        CUDA device index (default: current device).
+    """
+
+    def __init__(self, mm_system, device=None):
+        torch = _torch()
+        L = _lib.lib()
+        if not torch.cuda.is_available() or L.pm_device_count() < 1:
+            raise B200Error("no CUDA device is visible: the B200 path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        s = mm_system
+        self.n_atoms = int(s.n_atoms)
+        self._keep = dict(
+            bond=np.ascontiguousarray(s.bond_idx, dtype=np.int32).reshape(-1, 2),
+            angle=np.ascontiguousarray(s.angle_idx, dtype=np.int32).reshape(-1, 3),
+            tors=np.ascontiguousarray(s.torsion_idx, dtype=np.int32).reshape(-1, 4),
+            tper=np.ascontiguousarray(s.torsion_per, dtype=np.int32).reshape(-1),
+            exc=np.ascontiguousarray(s.exception_idx, dtype=np.int32).reshape(-1, 2),
+        )
+        par = np.asarray(s.exception_par, dtype=np.float64).reshape(-1, 3)
+        self.exception_active = np.ascontiguousarray(((par[:, 0] != 0.0) | (par[:, 2] != 0.0)).astype(np.int32))
+        self._keep["act"] = self.exception_active
+        k = self._keep
+        topo = PmTopology(self.n_atoms,
+                          len(k["bond"]), _iptr(k["bond"]),
+                          len(k["angle"]), _iptr(k["angle"]),
+                          len(k["tors"]), _iptr(k["tors"]), _iptr(k["tper"]),
+                          len(k["exc"]), _iptr(k["exc"]), _iptr(k["act"]),
+                          0 if s.nonbonded_method == "NoCutoff" else 1,
+                          float(s.cutoff), float(s.rf_dielectric), float(s.one_4pi_eps0))
+        h = ctypes.c_void_p()
+        _lib.check(L.pm_create(ctypes.byref(topo), self.device, ctypes.byref(h)), "pm_create")
+        self._h = h
+        self._L = L
+        self.n_bonds, self.n_angles, self.n_torsions, self.n_exceptions = (len(k["bond"]), len(k["angle"]),
+                                                                           len(k["tors"]), len(k["exc"]))
+        self.n_slots = int(L.pm_n_slots(h))
+        self.n_derived = int(L.pm_n_derived(h))
+        self.n_pairs = int(L.pm_n_pairs(h))
+        self.tile_doubles = int(L.pm_tile_doubles(h))
+        # slot offsets (include/paramol_b200.h)
+        self.off_bond = 0
+        self.off_angle = self.off_bond + 2 * self.n_bonds
+        self.off_torsion = self.off_angle + 2 * self.n_angles
+        self.off_particle = self.off_torsion + 2 * self.n_torsions
+        self.off_exception = self.off_particle + 3 * self.n_atoms
+        assert self.off_exception + 3 * self.n_exceptions == self.n_slots
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.pm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def slots_from_system(self, mm_system):
+        """Flatten the physical parameter table of ``mm_system`` into one slots row (float64 [n_slots])."""
+        s = mm_system
+        return np.concatenate([np.asarray(s.bond_par, dtype=np.float64).ravel(),
+                               np.asarray(s.angle_par, dtype=np.float64).ravel(),
+                               np.asarray(s.torsion_par, dtype=np.float64).ravel(),
+                               np.asarray(s.particle_par, dtype=np.float64).ravel(),
+                               np.asarray(s.exception_par, dtype=np.float64).ravel()])
+
+    def pairs(self):
+        """Interacting pair list as the kernel enumerates it: int32 [n_pairs, 3] = (i, j, exception or -1)."""
+        out = np.zeros((self.n_pairs, 3), dtype=np.int32)
+        _lib.check(self._L.pm_get_pairs(self._h, _iptr(out)), "pm_get_pairs")
+        return out
+
+    def launch_info(self, with_forces=True):
+        g, b, s, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._L.pm_launch_info(self._h, int(with_forces), ctypes.byref(g), ctypes.byref(b), ctypes.byref(s),
+                                          ctypes.byref(w)), "pm_launch_info")
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, warps_per_cta=w.value)
+
+    def set_force_metric(self, metric):
+        m = np.ascontiguousarray(metric, dtype=np.float64).reshape(self.n_atoms, 9)
+        _lib.check(self._L.pm_set_force_metric(self._h, m.ctypes.data_as(c_double_p)), "pm_set_force_metric")
+
+    def n_tiles(self, n_conf):
+        return (int(n_conf) + TILE - 1) // TILE
+
+    # ---- raw launches on torch tensors ---------------------------------------------------------
+    def pack(self, src, n_conf):
+        """[S,N,3] float64 CUDA tensor -> tile tensor."""
+        torch = _torch()
+        assert src.is_cuda and src.dtype == torch.float64 and src.is_contiguous()
+        tiles = torch.empty(self.n_tiles(n_conf) * self.tile_doubles, dtype=torch.float64, device=src.device)
+        _lib.check(self._L.pm_pack_tiles(self._h, src.data_ptr(), n_conf, tiles.data_ptr(), _stream_ptr(src.device)),
+                   "pm_pack_tiles")
+        return tiles
+
+    def unpack(self, tiles, n_conf):
+        torch = _torch()
+        dst = torch.empty((n_conf, self.n_atoms, 3), dtype=torch.float64, device=tiles.device)
+        _lib.check(self._L.pm_unpack_tiles(self._h, tiles.data_ptr(), n_conf, dst.data_ptr(), _stream_ptr(tiles.device)),
+                   "pm_unpack_tiles")
+        return dst
+
+    def prepare(self, slots_dev, derived_dev=None):
+        """slots [P, n_slots] CUDA float64 -> derived [P, n_derived]."""
+        torch = _torch()
+        assert slots_dev.is_cuda and slots_dev.dtype == torch.float64 and slots_dev.is_contiguous()
+        assert slots_dev.dim() == 2 and slots_dev.shape[1] == self.n_slots
+        n_vec = slots_dev.shape[0]
+        if derived_dev is None:
+            derived_dev = torch.empty((n_vec, self.n_derived), dtype=torch.float64, device=slots_dev.device)
+        _lib.check(self._L.pm_prepare_params(self._h, slots_dev.data_ptr(), n_vec, derived_dev.data_ptr(),
+                                             _stream_ptr(slots_dev.device)), "pm_prepare_params")
+        return derived_dev
+
+
+class DeviceEnsemble:
+    """
+    The conformations of one system, resident on one GPU in tile layout, plus their QM reference data.
+
+    Parameters
+    ----------
+    topology : :obj:`DeviceTopology`
+    coordinates : array [S,N,3] (nm), host numpy or CUDA tensor
+    ref_forces : array [S,N,3] (kJ/mol/nm) or None
+    ref_energies : array [S] (kJ/mol) or None
+    """
+
+    def __init__(self, topology, coordinates, ref_forces=None, ref_energies=None, pinned=False):
+        torch = _torch()
+        self.topology = topology
+        self.device = torch.device("cuda", topology.device)
+        self.h2d_bytes = 0
+        x = self._to_device(coordinates, pinned)
+        if x.dim() != 3 or x.shape[1] != topology.n_atoms or x.shape[2] != 3:
+            raise ValueError("coordinates must have shape [S, %d, 3]" % topology.n_atoms)
+        self.n_conf = int(x.shape[0])
+        if self.n_conf < 1:
+            raise ValueError("no conformations")
+        self.coord_tiles = topology.pack(x, self.n_conf)
+        del x
+        self.fref_tiles = None
+        self.eref = None
+        if ref_forces is not None:
+            f = self._to_device(ref_forces, pinned)
+            if tuple(f.shape) != (self.n_conf, topology.n_atoms, 3):
+                raise ValueError("ref_forces shape mismatch")
+            self.fref_tiles = topology.pack(f, self.n_conf)
+            del f
+        if ref_energies is not None:
+            self.eref = self._to_device(ref_energies, pinned).reshape(-1)
+            if self.eref.shape[0] != self.n_conf:
+                raise ValueError("ref_energies shape mismatch")
+        self.weights = None            # CUDA [S] or None (= 1)
+        self._scratch = None
+        self._buffers = {}
+
+    def _to_device(self, a, pinned=False):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float64).contiguous()
+            if not a.is_cuda:
+                self.h2d_bytes += t.numel() * 8
+            return t
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        t = torch.from_numpy(a)
+        if pinned:
+            t = t.pin_memory()
+        self.h2d_bytes += t.numel() * 8
+        return t.to(self.device, non_blocking=pinned)
+
+    def set_weights(self, weights):
+        self.weights = None if weights is None else self._to_device(weights).reshape(-1)
+
+    def _buf(self, name, shape):
+        torch = _torch()
+        b = self._buffers.get(name)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.empty(shape, dtype=torch.float64, device=self.device)
+            self._buffers[name] = b
+        return b
+
+    # ------------------------------------------------------------------------------------------
+    def evaluate(self, derived, with_forces=True, want_fres=True, want_fmm=False):
+        """
+        Launch the E(+F) kernel for ``derived`` [P, n_derived] (CUDA).  Returns (emm [P,S], fres [P,S] or None,
+        fmm_tiles [P, tiles*tile_doubles] or None); outputs are views of reusable device buffers.
+        """
+        topo = self.topology
+        n_vec = int(derived.shape[0])
+        emm = self._buf("emm", (n_vec, self.n_conf))
+        fres = None
+        fmm = None
+        if with_forces and want_fres:
+            if self.fref_tiles is None:
+                raise B200Error("force residual requested but the ensemble holds no reference forces")
+            fres = self._buf("fres", (n_vec, self.n_conf))
+        if with_forces and want_fmm:
+            fmm = self._buf("fmm", (n_vec, topo.n_tiles(self.n_conf) * topo.tile_doubles))
+        _lib.check(topo._L.pm_eval(topo._h, derived.data_ptr(), n_vec, self.coord_tiles.data_ptr(),
+                                   self.fref_tiles.data_ptr() if (fres is not None) else None, self.n_conf,
+                                   int(bool(with_forces)), emm.data_ptr(),
+                                   fres.data_ptr() if fres is not None else None,
+                                   fmm.data_ptr() if fmm is not None else None, _stream_ptr(self.device)), "pm_eval")
+        return emm, fres, fmm
+
+    def reduce(self, emm, fres, d_shift=0.0, weights="own"):
+        """Partial sums [P, 8] (CUDA) of this ensemble; see ``pm_reduce_objective`` in include/paramol_b200.h."""
+        torch = _torch()
+        topo = self.topology
+        n_vec = int(emm.shape[0])
+        need = int(topo._L.pm_reduce_scratch_doubles(n_vec))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float64, device=self.device)
+        partials = self._buf("partials", (n_vec, NPARTIAL))
+        w = self.weights if isinstance(weights, str) else weights
+        _lib.check(topo._L.pm_reduce_objective(emm.data_ptr(), fres.data_ptr() if fres is not None else None,
+                                               self.eref.data_ptr() if self.eref is not None else None,
+                                               w.data_ptr() if w is not None else None, float(d_shift), n_vec, self.n_conf,
+                                               partials.data_ptr(), self._scratch.data_ptr(), _stream_ptr(self.device)),
+                   "pm_reduce_objective")
+        return partials
+
+    def forces_from_tiles(self, fmm_tiles):
+        """[P, tiles] -> torch [P, S, N, 3]."""
+        torch = _torch()
+        return torch.stack([self.topology.unpack(fmm_tiles[p], self.n_conf) for p in range(fmm_tiles.shape[0])])

@@ -1,0 +1,93 @@
+// pm_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+// Everything here is FP64: the reference evaluates on OpenMM's double-precision Reference platform
+// (ParaMol/Objective_function/objective_function.py:81 forces OPENMM_DEFAULT_PLATFORM=Reference) and the
+// parity bar (objective 1e-8 relative on as few as 10 conformations) cannot be met with FP32 terms.
+// B200 issues DFMA at half the FFMA rate, so the design goal is to keep the FP64 pipe saturated and to
+// spend as few FP64 instructions per interaction as possible (no libm sqrt/div/sincos in the hot loops).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PM_TILE 32
+#define PM_IT 4          // atoms of an i-tile kept in registers in the pair loop
+#define PM_MAX_WARPS 16  // warps per CTA (1 persistent CTA per SM)
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void pm_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pm_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void pm_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void pm_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pm_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pm_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(pm_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool pm_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(pm_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void pm_mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!pm_mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 reciprocal square root: MUFU.RSQ64H seed (upper 32 bits, ~2^-20) + ONE cubically convergent
+// correction  y (1 + e/2 + 3 e^2 / 8),  e = 1 - x y^2   ->  relative error ~ (5/16) e^3 < 2^-56.
+// 1 MUFU + 5 FP64 ops instead of the ~25-instruction libm sqrt + division.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pm_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = y * y;
+    const double e = fma(-x, t, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    return fma(y, q, y);
+}
+
+struct pm_d3 {
+    double x, y, z;
+};
+__device__ __forceinline__ pm_d3 pm_sub(const pm_d3 a, const pm_d3 b) { return pm_d3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double pm_dot(const pm_d3 a, const pm_d3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ pm_d3 pm_cross(const pm_d3 a, const pm_d3 b) {
+    return pm_d3{fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))};
+}
+
+// Tile accessors: tile[(3*atom + c) * 32 + lane]  (bank-conflict free: one 256 B row per warp request)
+__device__ __forceinline__ pm_d3 pm_ld3(const double *tile, int atom, int lane) {
+    const double *p = tile + (3 * atom) * PM_TILE + lane;
+    return pm_d3{p[0], p[PM_TILE], p[2 * PM_TILE]};
+}
+__device__ __forceinline__ void pm_add3(double *tile, int atom, int lane, const pm_d3 v) {
+    double *p = tile + (3 * atom) * PM_TILE + lane;
+    p[0] += v.x;
+    p[PM_TILE] += v.y;
+    p[2 * PM_TILE] += v.z;
+}
+__device__ __forceinline__ void pm_sub3(double *tile, int atom, int lane, const pm_d3 v) {
+    double *p = tile + (3 * atom) * PM_TILE + lane;
+    p[0] -= v.x;
+    p[PM_TILE] -= v.y;
+    p[2 * PM_TILE] -= v.z;
+}

@@ -1,0 +1,164 @@
+"""
+GPU parity tests proper (run with ``-m gpu`` on the B200 box): the CUDA path, called through the C ABI
+(``include/paramol_b200.h`` via ``paramol_b200._lib``), against the CPU oracle on the same seeded inputs.
+
+Tolerances are the north-star ones: energies/forces 1e-6 relative with a 1e-4 kJ/mol(/nm) absolute floor,
+residual sums / objective 1e-8 relative, pair and exclusion lists bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL, E_ATOL = 1e-6, 1e-4
+OBJ_RTOL = 1e-8
+
+
+def _close_ef(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return np.all(np.abs(a - b) <= np.maximum(E_RTOL * np.abs(b), E_ATOL))
+
+
+def _system(golden_dir, name):
+    from paramol_b200.Utils.amber import system_from_prmtop, read_inpcrd
+    return (system_from_prmtop(os.path.join(golden_dir, name + ".prmtop")),
+            read_inpcrd(os.path.join(golden_dir, name + ".inpcrd")))
+
+
+def _run(sys_, X, Fref=None, Eref=None, metric=None, slots=None):
+    import torch
+    from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
+    topo = DeviceTopology(sys_)
+    if metric is not None:
+        topo.set_force_metric(metric)
+    ens = DeviceEnsemble(topo, X, Fref, Eref)
+    if slots is None:
+        slots = topo.slots_from_system(sys_)[None, :]
+    slots_dev = torch.from_numpy(np.ascontiguousarray(slots)).cuda()
+    derived = topo.prepare(slots_dev)
+    emm, fres, fmm = ens.evaluate(derived, with_forces=True, want_fres=Fref is not None, want_fmm=True)
+    F = ens.forces_from_tiles(fmm).cpu().numpy()
+    out = dict(emm=emm.cpu().numpy(), fmm=F, fres=None if fres is None else fres.cpu().numpy(), topo=topo, ens=ens,
+               derived=derived)
+    emm_only, _, _ = ens.evaluate(derived, with_forces=False)
+    out["emm_energy_only_kernel"] = emm_only.cpu().numpy()
+    torch.cuda.synchronize()
+    return out
+
+
+def test_pair_list_bit_exact(golden_dir):
+    from paramol_b200.MM_engines.device import DeviceTopology
+    for name in ("aniline", "caffeine", "norfloxacin"):
+        s, _ = _system(golden_dir, name)
+        topo = DeviceTopology(s)
+        pairs = topo.pairs()
+        plain = {tuple(p) for p in s.nonexcluded_pairs().tolist()}
+        active = {(int(min(a, b)), int(max(a, b))): e for e, ((a, b), par) in
+                  enumerate(zip(s.exception_idx, s.exception_par)) if par[0] != 0.0 or par[2] != 0.0}
+        got_plain = {(int(i), int(j)) for i, j, e in pairs if e < 0}
+        got_exc = {(int(i), int(j)): int(e) for i, j, e in pairs if e >= 0}
+        assert got_plain == plain
+        assert got_exc == active
+        assert len(pairs) == len(plain) + len(active)  # no duplicates
+
+
+def test_aniline_goldens_through_cuda(aniline_system, aniline_data, goldens):
+    X, Eq, Fq = aniline_data
+    r = _run(aniline_system, X, Fq, Eq)
+    gold_e = np.asarray(goldens["test_system.py::test_get_energies_ensemble::energies_to_compare"])
+    gold_f = np.asarray(goldens["test_system.py::test_get_forces_ensemble::forces_to_compare"])
+    # the reference's own tolerance is decimal=4 (Tests/System/test_system.py:109-142)
+    assert np.abs(r["emm"][0] - gold_e).max() < 1e-7
+    assert np.abs(r["fmm"][0, 0] - gold_f).max() < 1e-7
+    assert np.abs(r["emm_energy_only_kernel"][0] - gold_e).max() < 1e-7
+
+
+@pytest.mark.parametrize("name,n_conf", [("aniline", 1000), ("caffeine", 257), ("norfloxacin", 96), ("ethane", 33)])
+def test_ef_parity_vs_oracle(golden_dir, name, n_conf):
+    from oracle import oracle as O
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(1234)
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    E, F = O.energies_forces(s, X, n_threads=4)
+    Fref = F + rng.normal(0, 50.0, F.shape)
+    metric = np.tile(np.eye(3).ravel(), (s.n_atoms, 1)) * rng.uniform(0.5, 2.0, (s.n_atoms, 1))
+    r = _run(s, X, Fref, E + rng.normal(0, 5, E.shape), metric)
+    assert _close_ef(r["emm"][0], E), np.abs(r["emm"][0] - E).max()
+    assert _close_ef(r["fmm"][0], F), np.abs(r["fmm"][0] - F).max()
+    assert _close_ef(r["emm_energy_only_kernel"][0], E)
+    # far tighter than the bar in practice: FP64 evaluation end to end
+    assert np.abs(r["emm"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    assert np.abs(r["fmm"][0] - F).max() < 1e-9 * np.abs(F).max()
+    d = F - Fref
+    res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
+    assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
+
+
+def test_batched_parameter_vectors_and_reduction(golden_dir):
+    import torch
+    from oracle import oracle as O
+    s, x0 = _system(golden_dir, "aniline")
+    rng = np.random.default_rng(7)
+    n_conf, n_vec = 333, 5
+    X = x0[None] + rng.normal(0, 0.004, (n_conf,) + x0.shape)
+    E0, F0 = O.energies_forces(s, X)
+    Eref = E0 + rng.normal(0, 5, n_conf) - 43000.0
+    Fref = F0 + rng.normal(0, 50, F0.shape)
+    w = rng.uniform(0.1, 1.0, n_conf)
+    w /= w.sum()
+    from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
+    topo = DeviceTopology(s)
+    base = topo.slots_from_system(s)
+    slots = np.stack([base * (1.0 + 0.02 * rng.uniform(-1, 1, base.shape)) for _ in range(n_vec)])
+    slots[0] = base
+    ens = DeviceEnsemble(topo, X, Fref, Eref)
+    ens.set_weights(w)
+    derived = topo.prepare(torch.from_numpy(slots).cuda())
+    emm, fres, _ = ens.evaluate(derived)
+    d_shift = float(np.mean(Eref))
+    partials = ens.reduce(emm, fres, d_shift=d_shift).cpu().numpy()
+    for p in range(n_vec):
+        sp = s.copy()
+        o = 0
+        for arr in (sp.bond_par, sp.angle_par, sp.torsion_par, sp.particle_par, sp.exception_par):
+            arr[...] = slots[p, o:o + arr.size].reshape(arr.shape)
+            o += arr.size
+        E, F = O.energies_forces(sp, X)
+        assert _close_ef(emm[p].cpu().numpy(), E)
+        d = (Eref - E) - d_shift
+        res = np.sum((F - Fref) ** 2, axis=(1, 2))
+        want = np.array([d.sum(), (w * d).sum(), (w * d * d).sum(), w.sum(), (w * res).sum(), n_conf, 0, 0])
+        assert np.all(np.abs(partials[p] - want) <= 1e-10 * np.maximum(1.0, np.abs(want))), (partials[p], want)
+        # objective assembled from the partial sums == oracle property values (1e-8 relative)
+        m = partials[p, 0] / partials[p, 5]
+        energy_obj = (partials[p, 2] - 2 * m * partials[p, 1] + m * m * partials[p, 3]) / np.var(Eref)
+        assert abs(energy_obj - O.energy_property(Eref, E, w)) <= OBJ_RTOL * abs(energy_obj)
+        force_obj = partials[p, 4] / (3 * s.n_atoms)
+        var1 = np.ones(s.n_atoms)
+        want_f = np.sum(w * np.sum(np.sum((F - Fref) ** 2, axis=2) / var1, axis=1)) / (3 * s.n_atoms)
+        assert abs(force_obj - want_f) <= OBJ_RTOL * abs(want_f)
+
+
+def test_ragged_tail_and_single_conformation(golden_dir):
+    from oracle import oracle as O
+    s, x0 = _system(golden_dir, "aniline")
+    rng = np.random.default_rng(3)
+    for n_conf in (1, 31, 32, 33, 65):
+        X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+        E, F = O.energies_forces(s, X)
+        r = _run(s, X, F, E)
+        assert r["emm"].shape == (1, n_conf) and r["fmm"].shape == (1, n_conf, s.n_atoms, 3)
+        assert np.abs(r["emm"][0] - E).max() < 1e-9 * np.abs(E).max()
+        assert np.abs(r["fres"][0]).max() < 1e-12 * np.abs(F).max() ** 2
+
+
+def test_fma_peak_probe():
+    import ctypes
+    from paramol_b200 import _lib
+    L = _lib.lib()
+    fl, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(L.pm_measure_fma_peak(0, 1, 2000, ctypes.byref(fl), ctypes.byref(ms)))
+    assert fl.value > 1e12  # a B200 sustains tens of TFLOP/s of DFMA
