@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200-native ParaMol objective-evaluation path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload aniline|lig50|lig60|norfloxacin]
+                    [--conformations S]
+
+Workload (BASELINE.json configs[1]): the reference test-suite molecule (aniline, 14 atoms), S = 2^20 synthetic perturbed
+conformations PER GPU (weak scaling: conformations are sharded by rank, the only collective is one allreduce of 8
+doubles per objective call), objective = ENERGY + FORCE("components") + L2 REGULARIZATION with uniform weights.
+A "step" is ONE objective evaluation over all conformations.
+
+Printed JSON line (rank 0):
+  value      conformation E+F evaluations / s, whole job, parameters and conformations resident in HBM
+             (pm_prepare_params + pm_eval + pm_reduce_objective + allreduce per step, CUDA-event timed)
+  e2e        the same metric through the public API ``ObjectiveFunction.f(x)`` with a HOST parameter vector: numpy
+             plumbing, pinned H2D of the slot row, kernels, allreduce, D2H of the partial sums, every step
+  roofline   dominant kernel pm_ef_kernel<true>: algorithmic FP64 flops / CUDA-event kernel time against the DFMA peak
+             measured live on this GPU (the kernel is FP64-pipe bound); ``hbm`` holds the same kernel
+             against the measured copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the FP64 CPU oracle (oracle/oracle.c, OpenMP over conformations, all host cores) on a bounded sample
+``--impl reference`` times that CPU oracle alone (OpenMM, where ParaMol's arithmetic lives, is not installable here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+GOLDEN = os.path.join(REPO, "tests", "golden")
+METRIC = "conformation E+F evals/sec"
+
+
+def flops_per_conformation(topo_counts, term_type):
+    """36/pair + 30/bond + 90/angle + 160/torsion + epilogue (9N+4 norm | 21N+4 components)."""
+    n, nb, na, nt, npair = topo_counts
+    epi = (21 * n + 4) if term_type == "components" else (9 * n + 4)
+    return 36 * npair + 30 * nb + 90 * na + 160 * nt + epi
+
+
+def load_molecule(name):
+    from paramol_b200.Utils.amber import system_from_prmtop, read_inpcrd
+    from paramol_b200.Utils.synthetic import make_ligand
+    if name.startswith("lig"):
+        return make_ligand(int(name[3:]))
+    return (system_from_prmtop(os.path.join(GOLDEN, name + ".prmtop")), read_inpcrd(os.path.join(GOLDEN, name + ".inpcrd")))
+
+
+def base_conformations(name, x0):
+    if name == "aniline":
+        from paramol_b200.Utils.netcdf_lite import read_paramol_data
+        return read_paramol_data(os.path.join(GOLDEN, "aniline_10_struct.nc"))[0]
+    return x0[None]
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                     universal_newlines=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(mm_system, x_base, term_type, target_seconds, threads=None):
+    """conformation E+F(+residual) evaluations / s of the CPU oracle on a bounded sample."""
+    from oracle import oracle as O
+    from paramol_b200.Utils.synthetic import perturbed_conformations
+    threads = threads or O.max_threads()
+    probe = perturbed_conformations(x_base, 2048, seed=99)
+    t0 = time.perf_counter()
+    E, F = O.energies_forces(mm_system, probe, n_threads=threads)
+    dt = time.perf_counter() - t0
+    n = int(min(max(2048, 2048 * target_seconds / max(dt, 1e-6)), 4_000_000))
+    X = perturbed_conformations(x_base, n, seed=100)
+    rng = np.random.default_rng(3)
+    t0 = time.perf_counter()
+    E, F = O.energies_forces(mm_system, X, n_threads=threads)
+    t_ef = time.perf_counter() - t0
+    Eref = E + rng.normal(0, 5, E.shape)
+    Fref = F + rng.normal(0, 50, F.shape)
+    w = O.conformation_weights("uniform", n)
+    t0 = time.perf_counter()
+    O.energy_property(Eref, E, w)
+    if term_type == "norm":
+        O.force_property(Fref, F, w, "norm")
+    else:
+        inv = O.force_inverse_covariance(Fref[:min(n, 4096)])
+        d = F - Fref
+        np.sum(w * np.einsum("sna,nab,snb->s", d, inv, d))
+    t_red = time.perf_counter() - t0
+    return dict(value=n / (t_ef + t_red), unit=METRIC, cores=int(threads), kind="port",
+                sample="%d perturbed conformations of the bench molecule, FP64 C oracle (OpenMP over conformations) "
+                       "+ numpy residual reductions; %.2f s E+F, %.2f s reductions" % (n, t_ef, t_red))
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle (port of the reference's OpenMM Reference-platform path), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    mm, x0 = load_molecule(args.workload)
+    xb = base_conformations(args.workload, x0)
+    threads = O.max_threads()
+    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    for it in range(args.warmup + args.steps):
+        r = cpu_oracle_rate(mm, xb, args.term_type, per_step, threads)
+        if it >= args.warmup:
+            rates.append(r)
+    value = float(np.mean([r["value"] for r in rates]))
+    n_sample = rates[-1]["sample"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "conformations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (args.conformations * max(1, args.gpus)) / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "conformations_per_gpu": args.conformations, "term_type": args.term_type,
+                       "note": "CPU arm: each step is a bounded sample, rate extrapolates linearly in S (the reference is O(S)); "
+                               "ms_per_step is the time this rate implies for the full workload"},
+            "cpu_baseline": {"value": value, "unit": "conformations/s", "cores": threads, "kind": "port", "sample": n_sample},
+            "e2e": {"value": value, "unit": "conformations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return "%s x %d perturbed conformations per GPU, ENERGY+FORCE(%s)+L2 objective, uniform weights" % (
+        args.workload, args.conformations, args.term_type)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from paramol_b200 import _lib
+    from paramol_b200.MM_engines.b200_engine import B200Engine
+    from paramol_b200.System.system import ParaMolSystem
+    from paramol_b200.Parameter_space.parameter_space import ParameterSpace
+    from paramol_b200.Objective_function.objective_function import ObjectiveFunction
+    from paramol_b200.Objective_function.Properties.energy_property import EnergyProperty
+    from paramol_b200.Objective_function.Properties.force_property import ForceProperty
+    from paramol_b200.Objective_function.Properties.regularization import Regularization
+    from paramol_b200.Utils.synthetic import perturbed_conformations
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    mm, x0 = load_molecule(args.workload)
+    xb = base_conformations(args.workload, x0)
+    S = args.conformations
+    engine = B200Engine(system=mm, device=local_rank)
+    system = ParaMolSystem(args.workload, engine, mm.n_atoms)
+    system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True, opt_charges=True, opt_lj=True,
+                                          opt_sc=True)
+    # ---- synthetic data on the HOST (per-rank shard, seeded by rank), labels = MM(x_ref) + noise --------------------------
+    X = perturbed_conformations(xb, S, sigma=0.005, seed=1234 + rank)
+    system.ref_coordinates = X
+    system.n_structures = S
+    rng = np.random.default_rng(4321 + rank)
+    t0 = time.perf_counter()
+    emm0 = system.get_energies_ensemble()
+    fmm0 = system.get_forces_ensemble()
+    system.ref_energies = emm0 + rng.normal(0.0, 5.0, S)
+    system.ref_forces = fmm0 + rng.normal(0.0, 50.0, fmm0.shape)
+    del fmm0
+    torch.cuda.synchronize()
+    # ---- cold start: pinned host -> HBM tiles (reported, not part of the steady-state metric) --------------------------------
+    t0 = time.perf_counter()
+    ens = system.device_ensemble(pinned=True)
+    torch.cuda.synchronize()
+    t_upload = time.perf_counter() - t0
+    upload_bytes = ens.h2d_bytes
+
+    ps = ParameterSpace()
+    _, x_init = ps.get_optimizable_parameters([system])
+    x_init = np.asarray(x_init, dtype=np.float64)
+    e_prop = EnergyProperty([system], weight=1.0)
+    f_prop = ForceProperty([system], term_type=args.term_type, weight=1.0)
+    e_prop.calculate_variance()
+    f_prop.calculate_variance()
+    ps.calculate_prior_widths("default")
+    r_prop = Regularization(x_init.copy(), ps.prior_widths, "L2", weight=1.0, scaling_factor=1.0)
+    of = ObjectiveFunction(None, ps, [e_prop, f_prop, r_prop], [system], platform_name="B200", weighting_method="uniform",
+                           checkpoint_freq=10 ** 12)
+    rng = np.random.default_rng(0)
+    trial = [x_init * (1.0 + 0.01 * rng.uniform(-1, 1, x_init.shape)) for _ in range(args.warmup + args.steps)]
+
+    topo = engine.device_topology()
+    counts = (mm.n_atoms, topo.n_bonds, topo.n_angles, topo.n_torsions, topo.n_pairs)
+    flops_conf = flops_per_conformation(counts, args.term_type)
+    bytes_conf = 48 * mm.n_atoms + 16  # f64 coords + f64 reference forces + reference energy in, energy out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ======================= (1) e2e through the public API, host parameter vectors ===========================================
+    for x in trial[:args.warmup]:
+        of.f(x)
+    barrier()
+    t0 = time.perf_counter()
+    f_vals = [of.f(x) for x in trial[args.warmup:]]
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    h2d_step = topo.n_slots * 8
+    d2h_step = 8 * 8
+
+    # ======================= (2) device-resident: prepare + eval + reduce (+ allreduce) ========================================
+    slots_dev = torch.from_numpy(np.stack([engine.current_slots()])).to(dev)
+    st = of._system_state(0, system)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step(k=None):
+        derived = topo.prepare(slots_dev)
+        if k is not None:
+            ev[k][0].record()
+        emm, fres, _ = ens.evaluate(derived, with_forces=True, want_fres=True)
+        if k is not None:
+            ev[k][1].record()
+        partials = ens.reduce(emm, fres, d_shift=st["d_shift"])
+        if world > 1:
+            dist.all_reduce(partials)
+        return partials
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        e_all0.record()
+        for k in range(args.steps):
+            step(k)
+        e_all1.record()
+        barrier()
+    t_dev = max_over_ranks(e_all0.elapsed_time(e_all1) * 1e-3)
+    t_kernel = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ======================= roofline denominators ================================================================================
+    L = _lib.lib()
+    import ctypes
+    fl, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(L.pm_measure_fma_peak(local_rank, 1, 4000, ctypes.byref(fl), ctypes.byref(ms)))
+    fp64_peak = fl.value / 1e12
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
+            hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        key = "%s:%d" % (args.workload, S)
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved_tf = flops_conf * S / t_kernel / 1e12
+    achieved_gbs = bytes_conf * S / t_kernel / 1e9
+    info = topo.launch_info(True)
+
+    cpu = cpu_oracle_rate(mm, xb, args.term_type, args.cpu_seconds)
+
+    value = world * S * args.steps / t_dev
+    line = {
+        "metric": METRIC, "value": value, "unit": "conformations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "molecule": args.workload, "n_atoms": mm.n_atoms,
+                   "conformations_per_gpu": S, "parameter_vectors_per_step": 1, "term_type": args.term_type,
+                   "l2": "inputs larger than L2 (%.0f MB of tiles per GPU vs 126 MB)" % (2 * S * mm.n_atoms * 24 / 1e6),
+                   "parallelism": "conformation shards, 1 allreduce of 8 doubles per step" if world > 1 else "single GPU"},
+        "e2e": {"value": world * S * args.steps / t_e2e, "unit": "conformations/s", "h2d_bytes_per_step": h2d_step,
+                "d2h_bytes_per_step": d2h_step, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "objective_evals_per_s": args.steps / t_e2e, "api": "ObjectiveFunction.f(x) with host x",
+                "cold_upload": {"seconds": t_upload, "bytes": upload_bytes,
+                                "note": "one-time pinned-host -> HBM staging of the conformation tiles, outside the step"}},
+        "gpu_launches": 4 * args.steps,
+        "objective_evals_per_s": args.steps / t_dev,
+        "roofline": {"bound": "fp64", "kernel": "pm_ef_kernel<true>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                     "peak_source": "DFMA peak measured live by pm_measure_fma_peak on this GPU",
+                     "flops_per_conformation": flops_conf, "kernel_ms": 1e3 * t_kernel,
+                     "kernel_share_of_step": t_kernel * args.steps / t_dev, "launch": info,
+                     "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm_peak, "bytes_per_conformation": bytes_conf, "peak_source": hbm_src}},
+        "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
+        "objective_value_last_step": f_vals[-1] if f_vals else None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="aniline")
+    ap.add_argument("--conformations", type=int, default=1 << 20)
+    ap.add_argument("--term-type", dest="term_type", default="components", choices=["components", "norm"])
+    ap.add_argument("--cpu-seconds", dest="cpu_seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,344 @@
+# -*- coding: utf-8 -*-
+"""
+Description
+-----------
+:obj:`ObjectiveFunction` -- the callable handed to the optimisers; same constructor keywords, attributes and
+methods as the reference class (``ParaMol/Objective_function/objective_function.py:26-361``):
+``f(parameters_values, opt_mode=True)``, ``calculate_objective_function``, ``reset_f_count``, ``get_f_count``,
+``init_parallel``.
+
+What changes underneath ``f``:
+
+* reference: ``update_systems`` (O(#terms) SWIG calls) -> per-conformation OpenMM loops for energies, then
+  again for forces -> numpy/Python property loops;
+* here: ``update_systems`` (numpy gathers) -> ONE host->device copy of the slot rows -> ``pm_prepare_params`` ->
+  ``pm_eval`` (energies, forces and the per-conformation force residual in one pass) -> ``pm_reduce_objective``
+  -> ONE allreduce of 8 doubles per (system, vector) when ``torch.distributed`` is initialised -> ONE
+  device->host copy of those doubles -> scalar assembly.
+
+``f_batch(X)`` evaluates P trial vectors per launch (Monte Carlo / simulated annealing / finite differences,
+``ParaMol/Optimizers/monte_carlo.py:101``, ``gradient_descent.py:106-121``, ``simulated_annealing.py:104``)
+without mutating the parameter space.  ``fused=False`` keeps the reference's structure (ensemble arrays brought
+to the host through ``ParaMolSystem.get_*_ensemble`` and reduced by the numpy property formulas); it exists for
+parity tests of the seam, not for speed.
+"""
+import logging
+import time
+
+import numpy as np
+
+from ..Utils import dist as _dist
+
+NPARTIAL = 8
+
+
+class ObjectiveFunction:
+    """
+    Parameters
+    ----------
+    restart_settings : dict or None
+    parameter_space : :obj:`paramol_b200.Parameter_space.parameter_space.ParameterSpace`
+    properties : list of properties
+    systems : list of :obj:`paramol_b200.System.system.ParaMolSystem`
+    platform_name : str
+        Kept from the reference ("Reference", "CPU", "OpenCL", "CUDA") plus "B200"; evaluation always runs on the
+        B200 path (there is no CPU fallback).
+    parallel : bool
+        Kept for signature compatibility.  Data parallelism here is one process per GPU (``torch.distributed``),
+        each rank holding a shard of the conformations; see ``ParaMolSystem.shard_for_rank``.
+    weighting_method : str
+        "uniform", "boltzmann", "non_boltzmann" or "manual".
+    weighting_temperature : float (K) or quantity with ``_value``
+    checkpoint_freq : int
+    fused : bool
+        True (default): device-side residual reduction.  False: reference-structured seam path.
+    """
+
+    def __init__(self, restart_settings, parameter_space, properties, systems, platform_name="B200", parallel=False,
+                 weighting_method="uniform", weighting_temperature=300.0, checkpoint_freq=1000, fused=True):
+        self.restart_settings = restart_settings
+        self.parameter_space = parameter_space
+        self.properties = properties
+        self.systems = systems
+        self._platform = platform_name
+        self._parallel = parallel
+        self._checkpoint_freq = checkpoint_freq
+        self._weighting_method = weighting_method
+        self._weighting_temperature = weighting_temperature
+        self._f_count = 0
+        self._fused = bool(fused)
+        self._total_n_batches = None
+        self._batch_lims = None
+        self._parallel_function = None
+        self._state = {}
+        self.last_timings = {}
+        if self._parallel:
+            self.init_parallel()
+
+    # ------------------------------------------------------------------------------------------
+    #                                       PUBLIC METHODS
+    # ------------------------------------------------------------------------------------------
+    def reset_f_count(self):
+        self._f_count = 0
+        return self._f_count
+
+    def get_f_count(self):
+        return self._f_count
+
+    def init_parallel(self):
+        """
+        Batch limits with the reference's rule ``batch_size = int(S / n_cpus) + 1`` (reference ``:112-160``).  No worker
+        pool is created: on the B200 path conformations are already evaluated in parallel on the device.
+        """
+        logging.info("Initializing parallel objective function.")
+        self._total_n_batches = 0
+        self._batch_lims = []
+        for system in self.systems:
+            n_structures = len(system.ref_coordinates)
+            self._total_n_batches = self._total_n_batches + system.n_cpus
+            batch_size = int(n_structures / float(system.n_cpus)) + 1
+            self._batch_lims.append([[n * batch_size, (n + 1) * batch_size] for n in range(system.n_cpus)])
+        return self._total_n_batches
+
+    def calculate_objective_function(self, parameters_values, fmm, emm, esp):
+        """Reference-structured assembly from host arrays (reference ``:162-226``)."""
+        objective_function = 0.0
+        for system in self.systems:
+            system.compute_conformations_weights(temperature=self._weighting_temperature, emm=emm,
+                                                 weighting_method=self._weighting_method)
+        for prop in self.properties:
+            if prop.name == "ENERGY":
+                objective_function += prop.weight * np.sum(prop.calculate_property(emm))
+            elif prop.name == "FORCE":
+                objective_function += prop.weight * np.sum(prop.calculate_property(fmm))
+            elif prop.name == "ESP":
+                objective_function += prop.weight * np.sum(prop.calculate_property(esp))
+            elif prop.name == "REGULARIZATION":
+                objective_function += prop.weight * prop.calculate_property(parameters_values)
+        return objective_function
+
+    # ------------------------------------------------------------------------------------------
+    #                                    Objective function
+    # ------------------------------------------------------------------------------------------
+    def f(self, parameters_values, opt_mode=True):
+        """
+        Objective function value for ``parameters_values`` (scaled if the parameter space is preconditioned).
+        Side effects as in the reference: parameters, force fields and engines are updated, ``system.weights`` and
+        ``property.value`` are set, ``_f_count`` is incremented in ``opt_mode``; NaN becomes 1e16.
+        """
+        start_time = time.time()
+        self.parameter_space.update_systems(self.systems, parameters_values)
+        if opt_mode:
+            self._f_count += 1
+        if self._fused and not any(p.name == "ESP" for p in self.properties):
+            slots = [system.engine.current_slots()[None, :] for system in self.systems]
+            objective_function = float(self._evaluate_fused(slots, np.asarray(parameters_values, dtype=np.float64)[None, :],
+                                                           set_values=True)[0])
+        else:
+            fmm, emm, esp = self._run_serial()
+            objective_function = self.calculate_objective_function(parameters_values, fmm, emm, esp)
+        if np.isnan(objective_function):
+            objective_function = 1e16
+        if self._f_count % self._checkpoint_freq == 1:
+            for system in self.systems:
+                system.engine.write_system_xml("{}_checkpoint.xml".format(system.name))
+        if not opt_mode:
+            self._print_table(time.time() - start_time)
+        return objective_function
+
+    def f_batch(self, parameters_matrix):
+        """
+        Objective values, numpy [P], for the rows of ``parameters_matrix`` [P, P_opt] in one set of launches.  Nothing
+        is mutated except ``_f_count`` (+P).  NaN rows become 1e16.
+        """
+        X = np.atleast_2d(np.asarray(parameters_matrix, dtype=np.float64))
+        if any(p.name == "ESP" for p in self.properties):
+            raise NotImplementedError("f_batch does not evaluate the ESP property.")
+        slots = self.parameter_space.update_systems_batch(self.systems, X)
+        values = self._evaluate_fused(slots, X, set_values=False)
+        self._f_count += X.shape[0]
+        values = np.where(np.isnan(values), 1e16, values)
+        return values
+
+    # ------------------------------------------------------------------------------------------
+    #                                       PRIVATE METHODS
+    # ------------------------------------------------------------------------------------------
+    def _run_serial(self):
+        fmm, emm, esp = [], [], []
+        for prop in self.properties:
+            if prop.systems is not None:
+                for system in prop.systems:
+                    if prop.name == "ENERGY":
+                        emm.append(system.get_energies_ensemble())
+                    elif prop.name == "FORCE":
+                        fmm.append(system.get_forces_ensemble())
+                    elif prop.name == "ESP":
+                        esp.append(system.get_esp_ensemble())
+        return fmm, emm, esp
+
+    def _print_table(self, elapsed):
+        print("!=================================================================================!")
+        print("!                           Objective Function Analysis                           !")
+        print("! {:<25s}{:^17s}{:<1s}{:^17s}{:<2s}{:^17s} !".format("PROPERTY", "Value", "x", "Weight", "=", "Contribution"))
+        print("!---------------------------------------------------------------------------------!")
+        obj_fun_total = 0.0
+        for prop in self.properties:
+            print("! {:<25s}{:^17.8f} {:^17.8f} {:^17.8f}  !".format(prop.name, prop.value, prop.weight, prop.value * prop.weight))
+            obj_fun_total = obj_fun_total + prop.value * prop.weight
+        print("! {:<61s}{:^17.8f}  !".format("TOTAL", obj_fun_total))
+        print("!---------------------------------------------------------------------------------!")
+        print("! {:<25s}{:<10}{:<25s}{:<8.3f}{:11s} !".format("Function Evaluations:", self._f_count, "Time (s):", elapsed, " "))
+        print("!=================================================================================!\n")
+
+    def _prop(self, name):
+        for prop in self.properties:
+            if prop.name == name:
+                return prop
+        return None
+
+    def _system_state(self, s_idx, system):
+        """Per-system device state: ensemble, force metric, static weights, energy shift."""
+        import torch
+        e_prop, f_prop = self._prop("ENERGY"), self._prop("FORCE")
+        need_e = e_prop is not None and system in e_prop.systems
+        need_f = f_prop is not None and system in f_prop.systems
+        ens = system.device_ensemble()
+        key = (id(ens), need_e, need_f, None if f_prop is None else f_prop.term_type,
+               None if f_prop is None else id(f_prop.variance), self._weighting_method.upper(), id(system.wham_weights))
+        st = self._state.get(s_idx)
+        if st is not None and st["key"] == key:
+            return st
+        st = dict(key=key, ens=ens, need_e=need_e, need_f=need_f)
+        if need_f:
+            assert f_prop.variance is not None, "ForceProperty.calculate_variance() was not called."
+            ens.topology.set_force_metric(f_prop.metric(f_prop.systems.index(system)))
+        st["n_global"] = system.n_structures_global()
+        st["d_shift"] = 0.0
+        if need_e:
+            assert e_prop.variance is not None, "EnergyProperty.calculate_variance() was not called."
+            k = e_prop.systems.index(system)
+            st["d_shift"] = float(e_prop.mean_ref[k])
+        # static weights (everything except NON_BOLTZMANN, which depends on the MM energies of the call)
+        method = self._weighting_method.upper()
+        st["w_scale"] = 1.0
+        wham = system.wham_weights
+        wham_is_array = np.ndim(wham) > 0
+        if method == "UNIFORM" and not wham_is_array:
+            system.compute_conformations_weights(weighting_method="UNIFORM")
+            ens.set_weights(None)
+            st["w_scale"] = float(wham) / st["n_global"]
+        elif method in ("UNIFORM", "BOLTZMANN", "MANUAL"):
+            system.compute_conformations_weights(temperature=self._weighting_temperature, weighting_method=method)
+            ens.set_weights(np.asarray(system.weights, dtype=np.float64) * np.asarray(wham, dtype=np.float64))
+        elif method == "NON_BOLTZMANN":
+            st["beta"] = system.beta(self._weighting_temperature)
+            st["wham_dev"] = torch.from_numpy(np.asarray(wham, dtype=np.float64) * np.ones(system.n_structures)).to(ens.device) \
+                if wham_is_array else None
+            st["wham_scalar"] = 1.0 if wham_is_array else float(wham)
+        else:
+            raise NotImplementedError("Weighting method {} is not implemented.".format(self._weighting_method))
+        self._state[s_idx] = st
+        return st
+
+    def _non_boltzmann_weights(self, st, system, emm):
+        """w = softmax(-beta (d - mean d)), d = E_mm - E_ref, per parameter vector; [P,S] on the device (global over ranks)."""
+        import torch
+        ens = st["ens"]
+        d = emm - ens.eref[None, :]
+        sums = torch.stack([d.sum(dim=1)], dim=1)
+        _dist.allreduce_sum_tensor_(sums)
+        mean = sums[:, 0] / st["n_global"]
+        w = torch.exp(-st["beta"] * (d - mean[:, None]))
+        z = w.sum(dim=1, keepdim=True)
+        _dist.allreduce_sum_tensor_(z)
+        bad = ~torch.isfinite(z) | (z <= 0)
+        w = torch.where(bad, torch.full_like(w, 1.0 / st["n_global"]), w / z)
+        if emm.shape[0] == 1:
+            system.weights = w[0].cpu().numpy()
+        if st["wham_dev"] is not None:
+            w = w * st["wham_dev"][None, :]
+        else:
+            w = w * st["wham_scalar"]
+        return w.contiguous()
+
+    def _evaluate_fused(self, slots_per_system, X, set_values):
+        """
+        slots_per_system: list over ``self.systems`` of float64 [P, n_slots]; X [P, P_opt] for the regularisation.
+        Returns numpy [P].
+        """
+        import torch
+        n_vec = X.shape[0]
+        e_prop, f_prop, r_prop = self._prop("ENERGY"), self._prop("FORCE"), self._prop("REGULARIZATION")
+        partial_list = []
+        states = []
+        for s_idx, (system, slots) in enumerate(zip(self.systems, slots_per_system)):
+            st = self._system_state(s_idx, system)
+            states.append(st)
+            if not (st["need_e"] or st["need_f"]):
+                partial_list.append(None)
+                continue
+            ens = st["ens"]
+            host = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64))
+            pin = st.get("pin")
+            if pin is None or tuple(pin.shape) != tuple(host.shape):
+                pin = torch.empty(tuple(host.shape), dtype=torch.float64).pin_memory()
+                st["pin"] = pin
+            pin.copy_(host)
+            slots_dev = pin.to(ens.device, non_blocking=True)
+            derived = ens.topology.prepare(slots_dev)
+            emm, fres, _ = ens.evaluate(derived, with_forces=st["need_f"], want_fres=st["need_f"])
+            if self._weighting_method.upper() == "NON_BOLTZMANN":
+                w = self._non_boltzmann_weights(st, system, emm)
+                rows = []
+                for p in range(n_vec):
+                    rows.append(ens.reduce(emm[p:p + 1], None if fres is None else fres[p:p + 1], d_shift=st["d_shift"],
+                                           weights=w[p]).clone())
+                partial_list.append(torch.cat(rows, dim=0))
+            else:
+                partial_list.append(ens.reduce(emm, fres, d_shift=st["d_shift"]))
+        live = [p for p in partial_list if p is not None]
+        values = np.zeros(n_vec)
+        if live:
+            stacked = torch.stack(live, dim=0)           # [n_live, P, 8]
+            _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective
+            host_partials = stacked.cpu().numpy()
+            k = 0
+            per_system = []
+            for p in partial_list:
+                if p is None:
+                    per_system.append(None)
+                else:
+                    per_system.append(host_partials[k] * 1.0)
+                    k += 1
+            # fold the uniform-weight normalisation (device weights were 1)
+            for st, hp in zip(states, per_system):
+                if hp is not None and st["w_scale"] != 1.0:
+                    hp[:, 1:5] *= st["w_scale"]
+            if e_prop is not None:
+                vals = np.zeros(n_vec)
+                for system in e_prop.systems:
+                    s_idx = self.systems.index(system)
+                    hp = per_system[s_idx]
+                    var = e_prop.variance[e_prop.systems.index(system)]
+                    m = hp[:, 0] / hp[:, 5]
+                    vals += (hp[:, 2] - 2.0 * m * hp[:, 1] + m * m * hp[:, 3]) / var
+                if set_values:
+                    e_prop.value = float(vals[0])
+                values += e_prop.weight * vals
+            if f_prop is not None:
+                vals = np.zeros(n_vec)
+                for system in f_prop.systems:
+                    hp = per_system[self.systems.index(system)]
+                    vals += hp[:, 4] / (3 * system.n_atoms)
+                if set_values:
+                    f_prop.value = float(vals[0])
+                values += f_prop.weight * vals
+        if r_prop is not None:
+            if set_values:
+                reg = np.atleast_1d(r_prop.calculate_property(X[0]))
+            else:
+                keep = r_prop.value
+                reg = np.atleast_1d(r_prop.calculate_property(X))
+                r_prop.value = keep
+            values = values + r_prop.weight * reg
+        return values

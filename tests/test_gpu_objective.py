@@ -1,0 +1,173 @@
+"""
+GPU parity of the objective function through the reference-facing API (run with ``-m gpu``).  The first tests
+are the reference's own test bodies (ParaMol/Tests/Objective_function/test_objective_function.py:26-145,
+Tests/System/test_system.py:94-169, Tests/MM_engines/test_openmm_wrapper.py:43-72) with the imports pointed at
+this package; the rest compare the fused device path with the CPU oracle on seeded inputs.
+Tolerances: objective 1e-8 relative (the reference asserts 1e-8 absolute on O(0.1-0.5) values), E/F 1e-6 rel, 1e-4 abs floor.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from paramol_b200.System.system import ParaMolSystem
+from paramol_b200.MM_engines.b200_engine import B200Engine
+from paramol_b200.Force_field.force_field import ForceField
+from paramol_b200.Objective_function.objective_function import ObjectiveFunction
+from paramol_b200.Objective_function.Properties.regularization import Regularization
+from paramol_b200.Objective_function.Properties.force_property import ForceProperty
+from paramol_b200.Objective_function.Properties.energy_property import EnergyProperty
+from paramol_b200.Parameter_space.parameter_space import ParameterSpace
+
+objective_function_settings = {"parallel": False,
+                               "platform_name": "Reference",
+                               "weighting_method": "uniform",
+                               "weighting_temperature": 300.0,
+                               "checkpoint_freq": 100}
+
+
+@pytest.fixture()
+def kwargs_dict(golden_dir):
+    return {"topology_format": "AMBER", "crd_format": "AMBER",
+            "top_file": os.path.join(golden_dir, "aniline.prmtop"), "crd_file": os.path.join(golden_dir, "aniline.inpcrd")}
+
+
+def _aniline(kwargs_dict, golden_dir, **opt):
+    openmm_engine = B200Engine(True, **kwargs_dict)
+    system = ParaMolSystem(name="aniline", engine=openmm_engine, n_atoms=14)
+    assert type(system.force_field) is ForceField
+    flags = dict(opt_bonds=True, opt_angles=True, opt_torsions=True, opt_charges=True, opt_lj=True, opt_sc=True)
+    flags.update(opt)
+    system.force_field.create_force_field(ff_file=None, **flags)
+    system.read_data(os.path.join(golden_dir, "aniline_10_struct.nc"))
+    return system
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_objective_function_and_properties(kwargs_dict, golden_dir, goldens, fused, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)  # the checkpoint XML of f() lands in the cwd, as in the reference
+    system = _aniline(kwargs_dict, golden_dir)
+    parameter_space = ParameterSpace()
+    optimizable_parameters, optimizable_parameters_values = parameter_space.get_optimizable_parameters([system])
+    gold = goldens["test_objective_function.py::test_objective_function_and_properties::optimizable_parameters_values_to_compare"]
+    np.testing.assert_almost_equal(gold, optimizable_parameters_values, decimal=4)
+
+    prop_energy = EnergyProperty([system], **{"weight": 1.0})
+    prop_energy.calculate_variance()
+    objective_function = ObjectiveFunction(restart_settings=None, parameter_space=parameter_space, properties=[prop_energy],
+                                           systems=[system], fused=fused, **objective_function_settings)
+    f_val = objective_function.f(optimizable_parameters_values, opt_mode=False)
+    assert abs(f_val - 0.16587870225911971) < 1e-8
+    assert abs(f_val - 0.16587870225911971) <= 1e-8 * 0.16587870225911971  # north-star bar: 1e-8 relative
+    assert abs(prop_energy.value - f_val) < 1e-15
+
+    prop_forces_components = ForceProperty([system], **{"term_type": "components", "weight": 1.0})
+    prop_forces_components.calculate_variance()
+    objective_function = ObjectiveFunction(restart_settings=None, parameter_space=parameter_space,
+                                           properties=[prop_forces_components], systems=[system], fused=fused,
+                                           **objective_function_settings)
+    f_val = objective_function.f(optimizable_parameters_values, opt_mode=False)
+    assert abs(f_val - 0.3022524295062905) <= 1e-8 * 0.3022524295062905
+
+    prop_forces_norm = ForceProperty([system], **{"term_type": "norm", "weight": 1.0})
+    prop_forces_norm.calculate_variance()
+    objective_function = ObjectiveFunction(restart_settings=None, parameter_space=parameter_space, properties=[prop_forces_norm],
+                                           systems=[system], fused=fused, **objective_function_settings)
+    f_val = objective_function.f(optimizable_parameters_values, opt_mode=False)
+    assert abs(f_val - 0.498237598004599) <= 1e-8 * 0.498237598004599
+
+    parameter_space.calculate_prior_widths("arithmetic")
+    prop_reg = Regularization(initial_parameters_values=parameter_space.optimizable_parameters_values,
+                              prior_widths=parameter_space.prior_widths, **{"method": "L2", "weight": 1.0, "scaling_factor": 1.0})
+    objective_function = ObjectiveFunction(restart_settings=None, parameter_space=parameter_space, properties=[prop_reg],
+                                           systems=[system], fused=fused, **objective_function_settings)
+    f_val = objective_function.f(optimizable_parameters_values, opt_mode=False)
+    assert abs(f_val) < 1e-8
+
+    # all four together, counting calls
+    objective_function = ObjectiveFunction(restart_settings=None, parameter_space=parameter_space,
+                                           properties=[prop_energy, prop_forces_norm, prop_reg], systems=[system], fused=fused,
+                                           **objective_function_settings)
+    f_val = objective_function.f(optimizable_parameters_values)
+    assert abs(f_val - (0.16587870225911971 + 0.498237598004599)) < 1e-8
+    assert objective_function.get_f_count() == 1 and objective_function.reset_f_count() == 0
+
+
+def test_system_ensembles_and_weights(kwargs_dict, golden_dir, goldens):
+    # Tests/System/test_system.py:94-169
+    system = _aniline(kwargs_dict, golden_dir)
+    emm = system.get_energies_ensemble()
+    np.testing.assert_almost_equal(emm, goldens["test_system.py::test_get_energies_ensemble::energies_to_compare"], decimal=4)
+    assert np.abs(emm - np.asarray(goldens["test_system.py::test_get_energies_ensemble::energies_to_compare"])).max() < 1e-7
+    fmm = system.get_forces_ensemble()
+    assert fmm.shape == (10, 14, 3)
+    np.testing.assert_almost_equal(fmm[0], goldens["test_system.py::test_get_forces_ensemble::forces_to_compare"], decimal=4)
+    k = "test_system.py::test_weighting_methods::"
+    w = system.compute_conformations_weights(temperature=300.0, emm=emm, weighting_method="non_boltzmann")
+    np.testing.assert_almost_equal(w, goldens[k + "non_boltzmann_to_compare"], decimal=6)
+    # single-conformation engine calls
+    e = system.engine.get_potential_energy(system.ref_coordinates[3])
+    assert abs(e - emm[3]) < 1e-9
+    f = system.engine.get_forces(system.ref_coordinates[3])
+    assert np.abs(f - fmm[3]).max() < 1e-9
+
+
+def _oracle_objective(system, x_slots_system, weighting, temperature=300.0, term_type="norm"):
+    from oracle import oracle as O
+    total, parts = O.objective(x_slots_system, np.asarray(system.ref_coordinates), np.asarray(system.ref_energies),
+                               np.asarray(system.ref_forces), force_term_type=term_type, weighting_method=weighting,
+                               temperature=temperature)
+    return total, parts
+
+
+@pytest.mark.parametrize("weighting", ["uniform", "boltzmann", "non_boltzmann"])
+@pytest.mark.parametrize("term_type", ["norm", "components"])
+def test_fused_objective_vs_oracle_with_perturbed_parameters(kwargs_dict, golden_dir, weighting, term_type):
+    system = _aniline(kwargs_dict, golden_dir, opt_sc=False)  # branch A: charges/LJ reach the 1-4 exceptions
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    x0 = np.asarray(x0)
+    e_prop, f_prop = EnergyProperty([system], weight=0.7), ForceProperty([system], term_type=term_type, weight=1.3)
+    e_prop.calculate_variance()
+    f_prop.calculate_variance()
+    ps.calculate_prior_widths("arithmetic")
+    r_prop = Regularization(x0.copy(), ps.prior_widths, "L2", weight=0.5, scaling_factor=2.0)
+    settings = dict(objective_function_settings, weighting_method=weighting, checkpoint_freq=10 ** 9)
+    of = ObjectiveFunction(None, ps, [e_prop, f_prop, r_prop], [system], **settings)
+    of_serial = ObjectiveFunction(None, ps, [e_prop, f_prop, r_prop], [system], fused=False, **settings)
+    rng = np.random.default_rng(5)
+    X = np.stack([x0 * (1.0 + 0.01 * rng.uniform(-1, 1, x0.shape)) for _ in range(4)])
+    X[0] = x0
+    # oracle values: push each vector through the (CPU-tested) parameter plumbing, evaluate with the oracle
+    want = []
+    for x in X:
+        ps.update_systems([system], x.copy())
+        total, parts = _oracle_objective(system, system.engine.system, weighting, term_type=term_type)
+        val = 0.7 * parts["ENERGY"] + 1.3 * parts["FORCE"] + 0.5 * 2.0 * np.sum(((x - x0) / ps.prior_widths) ** 2)
+        want.append(val)
+    want = np.asarray(want)
+    ps.update_systems([system], x0.copy())
+    got_batch = of.f_batch(X)
+    assert np.all(np.abs(got_batch - want) <= 1e-8 * np.abs(want)), (got_batch, want)
+    # the batch left the parameter space untouched
+    assert np.array_equal(np.asarray(ps.optimizable_parameters_values), x0)
+    for x, w in zip(X, want):
+        got = of.f(x.copy())
+        assert abs(got - w) <= 1e-8 * abs(w)
+        got_serial = of_serial.f(x.copy())
+        assert abs(got_serial - w) <= 1e-8 * abs(w)
+
+
+def test_nan_objective_becomes_1e16(kwargs_dict, golden_dir):
+    system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False)
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    e_prop = EnergyProperty([system])
+    e_prop.calculate_variance()
+    of = ObjectiveFunction(None, ps, [e_prop], [system], **dict(objective_function_settings, checkpoint_freq=10 ** 9))
+    x = np.asarray(x0).copy()
+    x[1] = np.nan
+    assert of.f(x) == 1e16
+    assert of.f_batch(np.stack([x, np.asarray(x0)]))[0] == 1e16
