@@ -26,9 +26,10 @@
  *    [ (q, sigma, eps)    x n_atoms      ]   NonbondedForce particles
  *    [ (qq, sigma, eps)   x n_exceptions ]   NonbondedForce exceptions
  *
- * Conformation "tiles": conformations are kept resident in HBM as tiles of PM_TILE=32 conformations,
- * tile t = doubles [3*n_atoms][32] with the conformation index fastest (a warp reads one row as one
- * coalesced 256-byte line and a whole tile is one contiguous TMA bulk copy).  pm_pack_tiles converts
+ * Conformation "tiles": conformations are kept resident in HBM as tiles of CPW = pm_conf_per_tile(h) conformations,
+ * tile t = doubles [3*n_atoms][CPW] with the conformation index fastest; a whole tile is one contiguous TMA bulk
+ * copy into the shared memory of the warp that evaluates it.  CPW = 32 / (lanes per conformation) is chosen per
+ * topology so that enough warps fit in shared memory (env PM_CPW overrides).  pm_pack_tiles converts
  * from the reference's [S][N][3] C-order arrays (ParaMolSystem.ref_coordinates / ref_forces,
  * ParaMol/System/system.py:85-123).
  */
@@ -39,7 +40,6 @@
 extern "C" {
 #endif
 
-#define PM_TILE 32
 #define PM_NPARTIAL 8 /* doubles per (parameter vector) row written by pm_reduce_objective */
 
 typedef struct pm_handle_s *pm_handle;
@@ -73,12 +73,19 @@ int pm_destroy(pm_handle h);
 int pm_n_slots(pm_handle h);          /* doubles per parameter vector (layout above)           */
 int pm_n_derived(pm_handle h);        /* doubles per parameter vector of the derived table      */
 int pm_n_pairs(pm_handle h);          /* interacting pairs (plain pairs + active exceptions)    */
-long pm_n_tiles(long n_conf);         /* ceil(n_conf / PM_TILE)                                  */
-long pm_tile_doubles(pm_handle h);    /* 3 * n_atoms * PM_TILE                                   */
+int pm_conf_per_tile(pm_handle h);    /* CPW: conformations per tile (32, 16, 8 or 4; chosen per topology) */
+long pm_n_tiles(pm_handle h, long n_conf); /* ceil(n_conf / CPW)                                 */
+long pm_tile_doubles(pm_handle h);    /* 3 * n_atoms * CPW                                       */
 /* interacting pair list, bit-exact indexing contract: out [n_pairs][3] = (i, j, exception index or -1) */
 int pm_get_pairs(pm_handle h, int *out_host);
 /* launch geometry chosen for the E+F kernel (for the roofline bookkeeping in bench.py) */
 int pm_launch_info(pm_handle h, int with_forces, int *grid, int *block, int *smem_bytes, int *warps_per_cta);
+/* topology program statistics: out[10] = {CPW, lanes per conformation, stars, star steps, axes, axis steps,
+ * pair segments, pair entries, pair entry slots (incl. padding), program ints} */
+int pm_program_info(pm_handle h, int *out10);
+/* host-only (no CUDA call): build the program for a given CPW and check its invariants -- every bond, angle, torsion
+ * and interacting pair executed exactly once, records of one step atom-disjoint.  0 = valid. */
+int pm_program_check(const pm_topology *topo, int cpw, int *stats10);
 
 /* Per-atom 3x3 force metric M_j used by the force residual  sum_j dF_j^T M_j dF_j :
  * inverse covariance of the QM forces ("components", ParaMol/Objective_function/Properties/force_property.py:85-101,126-173)
@@ -86,7 +93,7 @@ int pm_launch_info(pm_handle h, int with_forces, int *grid, int *block, int *sme
 int pm_set_force_metric(pm_handle h, const double *metric_host);
 
 /* ---- conformations ---------------------------------------------------------------------------- */
-/* [S][N][3] (dev, C order) -> tiles (dev, pm_n_tiles(S) * pm_tile_doubles doubles); the last tile is
+/* [S][N][3] (dev, C order) -> tiles (dev, pm_n_tiles(h, S) * pm_tile_doubles(h) doubles); the last tile is
  * padded by repeating the last conformation.  Replaces the per-conformation context.setPositions of
  * ParaMol/System/system.py:333-338,349-354: coordinates are staged once and stay resident. */
 int pm_pack_tiles(pm_handle h, const double *src_dev, long n_conf, double *tiles_dev, void *stream);

@@ -17,7 +17,6 @@ from .. import _lib
 from .._lib import B200Error, PmTopology, c_int_p, c_double_p
 
 NPARTIAL = 8
-TILE = 32
 
 
 def _torch():
@@ -84,6 +83,7 @@ class DeviceTopology:
         self.n_derived = int(L.pm_n_derived(h))
         self.n_pairs = int(L.pm_n_pairs(h))
         self.tile_doubles = int(L.pm_tile_doubles(h))
+        self.conf_per_tile = int(L.pm_conf_per_tile(h))
         # slot offsets (include/paramol_b200.h)
         self.off_bond = 0
         self.off_angle = self.off_bond + 2 * self.n_bonds
@@ -127,7 +127,14 @@ class DeviceTopology:
         _lib.check(self._L.pm_set_force_metric(self._h, m.ctypes.data_as(c_double_p)), "pm_set_force_metric")
 
     def n_tiles(self, n_conf):
-        return (int(n_conf) + TILE - 1) // TILE
+        return (int(n_conf) + self.conf_per_tile - 1) // self.conf_per_tile
+
+    def program_info(self):
+        out = np.zeros(10, dtype=np.int32)
+        _lib.check(self._L.pm_program_info(self._h, _iptr(out)), "pm_program_info")
+        keys = ("conf_per_tile", "lanes_per_conformation", "stars", "star_steps", "axes", "axis_steps", "pair_segments",
+                "pair_entries", "pair_entry_slots", "program_ints")
+        return dict(zip(keys, (int(v) for v in out)))
 
     # ---- raw launches on torch tensors ---------------------------------------------------------
     def pack(self, src, n_conf):

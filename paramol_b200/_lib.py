@@ -43,7 +43,10 @@ SIGNATURES = {
     "pm_n_slots": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_n_derived": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_n_pairs": (ctypes.c_int, [ctypes.c_void_p]),
-    "pm_n_tiles": (ctypes.c_long, [ctypes.c_long]),
+    "pm_conf_per_tile": (ctypes.c_int, [ctypes.c_void_p]),
+    "pm_n_tiles": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_long]),
+    "pm_program_info": (ctypes.c_int, [ctypes.c_void_p, c_int_p]),
+    "pm_program_check": (ctypes.c_int, [ctypes.POINTER(PmTopology), ctypes.c_int, c_int_p]),
     "pm_tile_doubles": (ctypes.c_long, [ctypes.c_void_p]),
     "pm_get_pairs": (ctypes.c_int, [ctypes.c_void_p, c_int_p]),
     "pm_launch_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_int_p, c_int_p, c_int_p, c_int_p]),

@@ -4,14 +4,15 @@
 // (ParaMol/Objective_function/objective_function.py:81 forces OPENMM_DEFAULT_PLATFORM=Reference) and the
 // parity bar (objective 1e-8 relative on as few as 10 conformations) cannot be met with FP32 terms.
 // B200 issues DFMA at half the FFMA rate, so the design goal is to keep the FP64 pipe saturated and to
-// spend as few FP64 instructions per interaction as possible (no libm sqrt/div/sincos in the hot loops).
+// spend as few FP64 instructions per interaction as possible (no libm sqrt / div / acos / sincos in the hot loops).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define PM_TILE 32
 #define PM_IT 4          // atoms of an i-tile kept in registers in the pair loop
 #define PM_MAX_WARPS 16  // warps per CTA (1 persistent CTA per SM)
+#define PM_ACOS_N 256    // intervals of the (cos, sin) table behind pm_acos_cs
+#define PM_PI 3.14159265358979323846
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
@@ -31,6 +32,10 @@ __device__ __forceinline__ void pm_bulk_g2s(void *dst_smem, const void *src_gmem
                      pm_smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(pm_smem_u32(bar))
                  : "memory");
+}
+// L2 prefetch of a contiguous block (one instruction): next tile's coordinates / this tile's reference forces
+__device__ __forceinline__ void pm_bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool pm_mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -60,9 +65,32 @@ __device__ __forceinline__ double pm_rsqrt(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double t = y * y;
     const double e = fma(-x, t, 1.0);
+    const double h = y * e;               // h and p are independent: dependency depth 4, not 5
     const double p = fma(0.375, e, 0.5);
-    const double q = e * p;
-    return fma(y, q, y);
+    return fma(h, p, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// theta in [0, pi] from BOTH c = cos(theta) and s = sin(theta) >= 0 (the angle code has both: the dot product and the
+// norm of the cross product).  An FP32 acosf picks the nearest of PM_ACOS_N+1 tabulated angles theta_q; then
+// sin(theta - theta_q) = s cos(theta_q) - c sin(theta_q) is exact to FP64 rounding and well conditioned for every theta
+// (unlike acos(c) alone near 0 and pi), and theta - theta_q = asin(.) needs a 5-term odd series since |.| < 0.02.
+// 9 FP64 ops + ~15 FP32/integer ops (idle pipes here) instead of ~50 FP64 ops for libm acos.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pm_acos_cs(double c, double s, const double2 *__restrict__ tab) {
+    float cf = __double2float_rn(c);
+    cf = fminf(1.0f, fmaxf(-1.0f, cf));
+    const float th = acosf(cf);
+    int q = __float2int_rn(th * (float)(PM_ACOS_N / PM_PI));
+    q = min(max(q, 0), PM_ACOS_N);
+    const double2 t = tab[q];
+    const double sd = fma(s, t.x, -(c * t.y));
+    const double z = sd * sd;
+    double p = fma(z, 35.0 / 1152.0, 15.0 / 336.0);
+    p = fma(z, p, 3.0 / 40.0);
+    p = fma(z, p, 1.0 / 6.0);
+    const double delta = fma(sd * z, p, sd);
+    return fma((double)q, PM_PI / PM_ACOS_N, delta);
 }
 
 struct pm_d3 {
@@ -73,21 +101,30 @@ __device__ __forceinline__ double pm_dot(const pm_d3 a, const pm_d3 b) { return 
 __device__ __forceinline__ pm_d3 pm_cross(const pm_d3 a, const pm_d3 b) {
     return pm_d3{fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))};
 }
+// a += s * v
+__device__ __forceinline__ void pm_axpy(pm_d3 &a, const double s, const pm_d3 v) {
+    a.x = fma(s, v.x, a.x);
+    a.y = fma(s, v.y, a.y);
+    a.z = fma(s, v.z, a.z);
+}
 
-// Tile accessors: tile[(3*atom + c) * 32 + lane]  (bank-conflict free: one 256 B row per warp request)
-__device__ __forceinline__ pm_d3 pm_ld3(const double *tile, int atom, int lane) {
-    const double *p = tile + (3 * atom) * PM_TILE + lane;
-    return pm_d3{p[0], p[PM_TILE], p[2 * PM_TILE]};
+// Tile accessors: tile[(3*atom + c) * CPW + column]; CPW = conformations per warp (row = CPW doubles)
+template <int CPW>
+__device__ __forceinline__ pm_d3 pm_ld3(const double *tile, int atom, int col) {
+    const double *p = tile + (3 * atom) * CPW + col;
+    return pm_d3{p[0], p[CPW], p[2 * CPW]};
 }
-__device__ __forceinline__ void pm_add3(double *tile, int atom, int lane, const pm_d3 v) {
-    double *p = tile + (3 * atom) * PM_TILE + lane;
+template <int CPW>
+__device__ __forceinline__ void pm_add3(double *tile, int atom, int col, const pm_d3 v) {
+    double *p = tile + (3 * atom) * CPW + col;
     p[0] += v.x;
-    p[PM_TILE] += v.y;
-    p[2 * PM_TILE] += v.z;
+    p[CPW] += v.y;
+    p[2 * CPW] += v.z;
 }
-__device__ __forceinline__ void pm_sub3(double *tile, int atom, int lane, const pm_d3 v) {
-    double *p = tile + (3 * atom) * PM_TILE + lane;
+template <int CPW>
+__device__ __forceinline__ void pm_sub3(double *tile, int atom, int col, const pm_d3 v) {
+    double *p = tile + (3 * atom) * CPW + col;
     p[0] -= v.x;
-    p[PM_TILE] -= v.y;
-    p[2 * PM_TILE] -= v.z;
+    p[CPW] -= v.y;
+    p[2 * CPW] -= v.z;
 }

@@ -9,16 +9,16 @@
 //   * force.set*Parameters + updateParametersInContext
 //       ParaMol/MM_engines/openmm.py:507-588, 661-756
 //
-// Mapping: ONE LANE = ONE CONFORMATION.  A warp owns a tile of 32 conformations whose
-// coordinates [3N][32] are pulled into shared memory with one TMA bulk copy; the topology "program"
-// and the derived parameter table are staged once per CTA and read as warp-uniform broadcasts, so the
-// term loops have no divergence, no shuffles and no atomics: forces accumulate in a lane-private
-// column of a shared [3N][32] tile.  The O(N^2) pair loop keeps PM_IT atoms (coordinates + force
-// accumulators) in registers so that shared-memory traffic per pair stays below the FP64-pipe time.
+// Mapping: every conformation gets a TEAM of L = 32/CPW lanes; a warp owns a tile of CPW conformations
+// whose coordinates [3N][CPW] arrive in shared memory by one TMA bulk copy.  The topology "program" (pm_program.hpp) and
+// the derived parameter table are staged once per CTA.  All lanes run the same step loops; in a step the L lanes of a
+// team execute records that touch disjoint atoms, so forces accumulate in the team's column of a shared [3N][CPW] tile
+// without atomics.  With L = 1 (small molecules) every index/parameter read is a warp-uniform broadcast.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -26,25 +26,27 @@
 
 #include "../../include/paramol_b200.h"
 #include "pm_device.cuh"
+#include "pm_program.hpp"
 
 // =============================================================================================
 // Device-visible description of one topology
 // =============================================================================================
 struct PmProg {
-    int n_atoms, n_bonds, n_angles, n_torsions;
-    int n_itiles, n_entries, n_pairs;
-    int n_int;       // ints in the blob
-    int n_derived;   // doubles per parameter vector in the derived table
-    // int offsets into the blob
-    int off_bond, off_angle, off_tors, off_tper, off_itile, off_entry;
-    // double offsets into a derived row
+    int n_atoms, n_bonds, n_angles, n_torsions, n_pairs;
+    int cpw, L;
+    int n_star_steps, n_axis_steps, n_segs;
+    int n_int;      // ints in the blob
+    int n_derived;  // doubles per parameter vector in the derived table
+    int off_star_tab, off_star_hdr, off_star_rec, off_axis_tab, off_axis_hdr, off_axis_rec, off_axis_terms, off_seg_hdr, off_seg_tile,
+        off_entries, off_tper;
     int doff_bond, doff_angle, doff_tors, doff_pair;
     int n_slots;
     int soff_bond, soff_angle, soff_tors, soff_part, soff_exc;
     double k_coul;
-    const int *ints;        // device blob
-    const double *metric;   // device [9N]
-    const int *pair_map;    // device [n_pairs][3] = (i, j, exception or -1)
+    const int *ints;         // device blob
+    const double *metric;    // device [9N]
+    const int *pair_map;     // device [n_pairs][3] = (i, j, exception or -1)
+    const double2 *acos_tab; // device [PM_ACOS_N + 1] = (cos, sin)(q pi / PM_ACOS_N)
 };
 
 // =============================================================================================
@@ -101,37 +103,50 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     const double u3 = u * u * u;
     const double c12 = pp[0], c6 = pp[1], cq = pp[2];
     const double a = c12 * u3;
-    const double elj = (a - c6) * u3;
+    const double b = a - c6;
     const double ec = cq * rinv;
-    e_nb += elj;
+    e_nb = fma(b, u3, e_nb);
     e_nb += ec;
     if (WITH_F) {
-        // -(dE/dr)/r = (12 c12 u^6 - 6 c6 u^3 + cq rinv) u = (6 (elj + a u3) + ec) u
-        const double g = fma(6.0, fma(a, u3, elj), ec) * u;
-        fi.x = fma(g, d.x, fi.x);
-        fi.y = fma(g, d.y, fi.y);
-        fi.z = fma(g, d.z, fi.z);
-        fj.x = fma(g, d.x, fj.x);
-        fj.y = fma(g, d.y, fj.y);
-        fj.z = fma(g, d.z, fj.z);
+        // -(dE/dr)/r = (12 c12 u^6 - 6 c6 u^3 + cq rinv) u = (6 (2a - c6) u3 + ec) u
+        const double g = fma(6.0 * u3, a + b, ec) * u;
+        pm_axpy(fi, g, d);
+        pm_axpy(fj, g, d);
     }
 }
 
-template <bool WITH_F>
+// Force write-back of one step.  One lane per conformation (L == 1): plain.  Teams: the records of a step that share a
+// colour touch disjoint atoms (pm_program.hpp), colours are serialised with __syncwarp between them.
+#define PM_ORDERED(n_col, colour, cond, ...)           \
+    if (L == 1) {                                      \
+        if (cond) __VA_ARGS__                          \
+    } else {                                           \
+        for (int _c = 0; _c < (n_col); ++_c) {         \
+            if ((cond) && (colour) == _c) __VA_ARGS__  \
+            __syncwarp();                              \
+        }                                              \
+    }
+
+template <int CPW, bool WITH_F>
 __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
     pm_ef_kernel(PmProg g, const double *__restrict__ derived, int n_vec, const double *__restrict__ xt,
                  const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm,
                  double *__restrict__ fres, double *__restrict__ fmm_t) {
+    constexpr int L = 32 / CPW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int col = lane % CPW;  // conformation inside the tile
+    const int tl = lane / CPW;   // team lane
     const int N = g.n_atoms;
-    const int tile_d = 3 * N * PM_TILE;
+    const int tile_d = 3 * N * CPW;
 
     // ---- shared memory carve-up -----------------------------------------------------------------
     int *s_int = reinterpret_cast<int *>(smem_raw);
     size_t off = ((size_t)g.n_int * sizeof(int) + 15) & ~(size_t)15;
+    double2 *s_acos = reinterpret_cast<double2 *>(smem_raw + off);
+    off += (size_t)(PM_ACOS_N + 1) * sizeof(double2);
     double *s_metric = reinterpret_cast<double *>(smem_raw + off);
-    off += (size_t)9 * N * sizeof(double);
+    off += ((size_t)9 * N * sizeof(double) + 15) & ~(size_t)15;  // keep the derived table 16-byte aligned (double2 reads)
     double *s_der = reinterpret_cast<double *>(smem_raw + off);
     off += (size_t)g.n_derived * sizeof(double);
     off = (off + 127) & ~(size_t)127;
@@ -142,6 +157,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
     double *fs = xs + tile_d;  // only touched when WITH_F
 
     for (int i = threadIdx.x; i < g.n_int; i += blockDim.x) s_int[i] = g.ints[i];
+    for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = g.acos_tab[i];
     for (int i = threadIdx.x; i < 9 * N; i += blockDim.x) s_metric[i] = g.metric[i];
     if (lane == 0) {
         pm_mbar_init(bar, 1);
@@ -149,12 +165,16 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
     }
     uint32_t parity = 0;
 
-    const int *s_bond = s_int + g.off_bond;
-    const int *s_angle = s_int + g.off_angle;
-    const int *s_tors = s_int + g.off_tors;
-    const int *s_tper = s_int + g.off_tper;
-    const int *s_itile = s_int + g.off_itile;
-    const int2 *s_entry = reinterpret_cast<const int2 *>(s_int + g.off_entry);
+    const int2 *s_star_tab = reinterpret_cast<const int2 *>(s_int + g.off_star_tab);
+    const int *s_star_hdr = s_int + g.off_star_hdr;
+    const int4 *s_star_rec = reinterpret_cast<const int4 *>(s_int + g.off_star_rec);
+    const int2 *s_axis_tab = reinterpret_cast<const int2 *>(s_int + g.off_axis_tab);
+    const int *s_axis_hdr = s_int + g.off_axis_hdr;
+    const int *s_axis_rec = s_int + g.off_axis_rec;
+    const int2 *s_axis_terms = reinterpret_cast<const int2 *>(s_int + g.off_axis_terms);
+    const int2 *s_seg_hdr = reinterpret_cast<const int2 *>(s_int + g.off_seg_hdr);
+    const int4 *s_seg_tile = reinterpret_cast<const int4 *>(s_int + g.off_seg_tile);
+    const int2 *s_entries = reinterpret_cast<const int2 *>(s_int + g.off_entries);
 
     const long warp_stride = (long)gridDim.x * n_warps;
     const long first_tile = (long)blockIdx.x * n_warps + warp;
@@ -166,182 +186,332 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
             for (int i = threadIdx.x; i < g.n_derived; i += blockDim.x) s_der[i] = dsrc[i];
         }
         __syncthreads();
-        const double *s_pbond = s_der + g.doff_bond;
-        const double *s_pangle = s_der + g.doff_angle;
-        const double *s_ptors = s_der + g.doff_tors;
+        const double2 *s_pbond = reinterpret_cast<const double2 *>(s_der + g.doff_bond);
+        const double2 *s_pangle = reinterpret_cast<const double2 *>(s_der + g.doff_angle);
+        const double2 *s_ptors = reinterpret_cast<const double2 *>(s_der + g.doff_tors);
         const double *s_ppair = s_der + g.doff_pair;
 
         for (long tile = first_tile; tile < n_tiles; tile += warp_stride) {
-            // ---- coordinates of 32 conformations: one TMA bulk copy into this warp's tile ---------
+            // ---- coordinates of CPW conformations: one TMA bulk copy into this warp's tile ---------
             if (lane == 0) {
                 pm_fence_proxy_async();
                 pm_mbar_expect_tx(bar, (uint32_t)(tile_d * sizeof(double)));
                 pm_bulk_g2s(xs, xt + (size_t)tile * tile_d, (uint32_t)(tile_d * sizeof(double)), bar);
+                // hide HBM latency of what comes next: this tile's reference forces (read in the epilogue) and the
+                // coordinates of the next tile of this warp
+                if (WITH_F && fres != nullptr)
+                    pm_bulk_prefetch_l2(fref_t + (size_t)tile * tile_d, (uint32_t)(tile_d * sizeof(double)));
+                if (tile + warp_stride < n_tiles)
+                    pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * tile_d, (uint32_t)(tile_d * sizeof(double)));
             }
             if (WITH_F) {
-                for (int k = 0; k < 3 * N; ++k) fs[k * PM_TILE + lane] = 0.0;
+                for (int k = lane; k < tile_d; k += 32) fs[k] = 0.0;
             }
             pm_mbar_wait(bar, parity);
             parity ^= 1;
+            __syncwarp();
 
             double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
 
-            // ---- HarmonicBondForce ---------------------------------------------------------------
-            for (int b = 0; b < g.n_bonds; ++b) {
-                const int ia = s_bond[2 * b], ib = s_bond[2 * b + 1];
-                const double r0 = s_pbond[2 * b], k = s_pbond[2 * b + 1];
-                const pm_d3 d = pm_sub(pm_ld3(xs, ib, lane), pm_ld3(xs, ia, lane));
-                const double r2 = pm_dot(d, d);
-                const double rinv = pm_rsqrt(r2);
-                const double di = fma(r2, rinv, -r0);
-                const double kd = k * di;
-                e_bond = fma(0.5 * kd, di, e_bond);
+            // ================= stars: bonds and angles around a centre atom ==========================
+            for (int step = 0; step < g.n_star_steps; ++step) {
+                const int2 te = s_star_tab[step * L + tl];  // (record, colour)
+                const int rec = te.x;
+                const int n_col = L > 1 ? s_star_hdr[step] : 1;
+                int center = 0, m = 0;
+                int nb[4] = {0, 0, 0, 0};
+                pm_d3 f[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[k] = pm_d3{0.0, 0.0, 0.0};
+                if (rec >= 0) {
+                    const int4 h0 = s_star_rec[4 * rec], h1 = s_star_rec[4 * rec + 1], h2 = s_star_rec[4 * rec + 2],
+                               h3 = s_star_rec[4 * rec + 3];
+                    center = h0.x;
+                    m = h0.y;
+                    nb[0] = h0.z;
+                    nb[1] = h0.w;
+                    nb[2] = h1.x;
+                    nb[3] = h1.y;
+                    const int bp[4] = {h1.z, h1.w, h2.x, h2.y};
+                    const int ap[6] = {h2.z, h2.w, h3.x, h3.y, h3.z, h3.w};
+                    const pm_d3 xc = pm_ld3<CPW>(xs, center, col);
+                    pm_d3 d[4];
+                    double r2[4], ri[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        d[k] = pm_d3{1.0, 0.0, 0.0};
+                        r2[k] = 1.0;
+                        ri[k] = 1.0;
+                        if (k < m) {
+                            d[k] = pm_sub(xc, pm_ld3<CPW>(xs, nb[k], col));
+                            r2[k] = pm_dot(d[k], d[k]);
+                            ri[k] = pm_rsqrt(r2[k]);
+                            if (bp[k] >= 0) {
+                                const double2 pb = s_pbond[bp[k]];  // (r0, k)
+                                const double di = fma(r2[k], ri[k], -pb.x);
+                                const double kd = pb.y * di;
+                                e_bond = fma(0.5 * kd, di, e_bond);
+                                if (WITH_F) pm_axpy(f[k], kd * ri[k], d[k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        constexpr int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
+                        if (ap[q] >= 0) {
+                            const int a = PA[q], b = PB[q];
+                            const double2 pa = s_pangle[ap[q]];  // (theta0, k)
+                            const double dot = pm_dot(d[a], d[b]);
+                            const double rr = ri[a] * ri[b];
+                            double cosine = dot * rr;
+                            cosine = fmin(1.0, fmax(-1.0, cosine));
+                            // |d_a x d_b|^2 (Lagrange identity)
+                            const double rp2 = fmax(fma(-dot, dot, r2[a] * r2[b]), 0.0);
+                            const bool tiny = rp2 <= 1.0e-12;  // the reference clamps |p| at 1e-6
+                            const double rpinv = tiny ? 1.0e6 : pm_rsqrt(rp2);
+                            const double sine = tiny ? sqrt(rp2) * rr : rp2 * rpinv * rr;
+                            const double theta = pm_acos_cs(cosine, sine, s_acos);
+                            const double di = theta - pa.x;
+                            const double kd = pa.y * di;
+                            e_angle = fma(0.5 * kd, di, e_angle);
+                            if (WITH_F) {
+                                // f_a = termA d_a x p, f_b = termC d_b x p with p = d_a x d_b, expanded with the
+                                // triple-product rule:  f_a = alpha d_a - w d_b ;  f_b = beta d_b - w d_a
+                                const double w = kd * rpinv;
+                                const double wd = w * dot;
+                                const double alpha = wd * (ri[a] * ri[a]), beta = wd * (ri[b] * ri[b]);
+                                pm_axpy(f[a], alpha, d[a]);
+                                pm_axpy(f[a], -w, d[b]);
+                                pm_axpy(f[b], beta, d[b]);
+                                pm_axpy(f[b], -w, d[a]);
+                            }
+                        }
+                    }
+                }
                 if (WITH_F) {
-                    const double s = kd * rinv;
-                    const pm_d3 f{s * d.x, s * d.y, s * d.z};
-                    pm_add3(fs, ia, lane, f);
-                    pm_sub3(fs, ib, lane, f);
+                    // write-back: records of one colour touch disjoint atoms; colours are serialised
+                    PM_ORDERED(n_col, te.y, rec >= 0, {
+                        pm_d3 fc{0.0, 0.0, 0.0};
+                        _Pragma("unroll") for (int k = 0; k < 4; ++k) {
+                            if (k < m) {
+                                pm_add3<CPW>(fs, nb[k], col, f[k]);
+                                fc.x -= f[k].x;
+                                fc.y -= f[k].y;
+                                fc.z -= f[k].z;
+                            }
+                        }
+                        pm_add3<CPW>(fs, center, col, fc);
+                    })
                 }
             }
 
-            // ---- HarmonicAngleForce --------------------------------------------------------------
-            for (int a = 0; a < g.n_angles; ++a) {
-                const int ia = s_angle[3 * a], ib = s_angle[3 * a + 1], ic = s_angle[3 * a + 2];
-                const double t0 = s_pangle[2 * a], k = s_pangle[2 * a + 1];
-                const pm_d3 xb = pm_ld3(xs, ib, lane);
-                const pm_d3 d0 = pm_sub(xb, pm_ld3(xs, ia, lane));
-                const pm_d3 d1 = pm_sub(xb, pm_ld3(xs, ic, lane));
-                const double r20 = pm_dot(d0, d0), r21 = pm_dot(d1, d1);
-                const double dot = pm_dot(d0, d1);
-                const double inv01 = pm_rsqrt(r20 * r21);
-                double cosine = dot * inv01;
-                cosine = fmin(1.0, fmax(-1.0, cosine));
-                const double theta = acos(cosine);
-                const double di = theta - t0;
-                const double kd = k * di;
-                e_angle = fma(0.5 * kd, di, e_angle);
+            // ================= axes: every torsion around a rotation axis j-k (trig-free) ================
+            for (int step = 0; step < g.n_axis_steps; ++step) {
+                const int2 te = s_axis_tab[step * L + tl];  // (record, colour)
+                const int rec = te.x;
+                const bool live = rec >= 0;
+                const int hdr = L > 1 ? s_axis_hdr[step] : 1;
+                const int n_col = hdr & 0xff;
+                int aj = 0, ak = 0, nI = 0, nL = 0;
+                int Ia[3] = {0, 0, 0}, La[3] = {0, 0, 0};
+                int ts[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                pm_d3 xj{0.0, 0.0, 0.0}, d1{1.0, 0.0, 0.0};
+                double rb = 1.0, ib2 = 1.0;
+                pm_d3 c2[3];
+                double s2[3], g2[3], B[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    c2[q] = pm_d3{1.0, 0.0, 0.0};
+                    s2[q] = 1.0;
+                    g2[q] = 0.0;
+                    B[q] = 0.0;
+                }
+                if (live) {
+                    const int4 *r4 = reinterpret_cast<const int4 *>(s_axis_rec + 20 * rec);
+                    const int4 h0 = r4[0], h1 = r4[1], h2 = r4[2], h3 = r4[3], h4 = r4[4];
+                    aj = h0.x;
+                    ak = h0.y;
+                    nI = h0.z;
+                    nL = h0.w;
+                    Ia[0] = h1.x;
+                    Ia[1] = h1.y;
+                    Ia[2] = h1.z;
+                    La[0] = h1.w;
+                    La[1] = h2.x;
+                    La[2] = h2.y;
+                    ts[0] = h2.z;
+                    ts[1] = h2.w;
+                    ts[2] = h3.x;
+                    ts[3] = h3.y;
+                    ts[4] = h3.z;
+                    ts[5] = h3.w;
+                    ts[6] = h4.x;
+                    ts[7] = h4.y;
+                    ts[8] = h4.z;
+                    ts[9] = h4.w;
+                    xj = pm_ld3<CPW>(xs, aj, col);
+                    const pm_d3 xk = pm_ld3<CPW>(xs, ak, col);
+                    d1 = pm_sub(xk, xj);
+                    const double nb2 = pm_dot(d1, d1);
+                    const double rbi = pm_rsqrt(nb2);
+                    rb = nb2 * rbi;
+                    ib2 = rbi * rbi;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (q < nL) {
+                            const pm_d3 d2 = pm_sub(xk, pm_ld3<CPW>(xs, La[q], col));
+                            c2[q] = pm_cross(d1, d2);
+                            s2[q] = pm_rsqrt(pm_dot(c2[q], c2[q]));
+                            g2[q] = pm_dot(d2, d1) * ib2;
+                        }
+                    }
+                }
+                pm_d3 Fj{0.0, 0.0, 0.0}, Fk{0.0, 0.0, 0.0};
+                const int ni_loop = L > 1 ? (hdr >> 8) : nI;
+                for (int pi = 0; pi < ni_loop; ++pi) {
+                    const bool act = live && pi < nI;
+                    int ai = 0;
+                    pm_d3 fi{0.0, 0.0, 0.0};
+                    if (act) {
+                        ai = pi == 0 ? Ia[0] : (pi == 1 ? Ia[1] : Ia[2]);
+                        const pm_d3 d0 = pm_sub(pm_ld3<CPW>(xs, ai, col), xj);
+                        const pm_d3 c1 = pm_cross(d0, d1);
+                        const double s1 = pm_rsqrt(pm_dot(c1, c1));
+                        double A = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int t0 = pi == 0 ? ts[q] : (pi == 1 ? ts[3 + q] : ts[6 + q]);
+                            const int t1 = pi == 0 ? ts[q + 1] : (pi == 1 ? ts[4 + q] : ts[7 + q]);
+                            if (t1 > t0) {
+                                const double inv12 = s1 * s2[q];
+                                const double cphi = pm_dot(c1, c2[q]) * inv12;
+                                const double sphi = rb * pm_dot(d0, c2[q]) * inv12;
+                                double dE = 0.0;
+                                for (int t = t0; t < t1; ++t) {
+                                    const int2 term = s_axis_terms[t];  // (torsion index, periodicity)
+                                    const double2 kk = s_ptors[2 * term.x], cs = s_ptors[2 * term.x + 1];  // (k, k n), (cos, sin) delta
+                                    double cn = 1.0, sn = 0.0;
+                                    for (int mm = 0; mm < term.y; ++mm) {
+                                        const double c_new = fma(cn, cphi, -(sn * sphi));
+                                        sn = fma(sn, cphi, cn * sphi);
+                                        cn = c_new;
+                                    }
+                                    const double cda = fma(cn, cs.x, sn * cs.y);  // cos(n phi - delta)
+                                    e_tors = fma(kk.x, cda, e_tors + kk.x);
+                                    if (WITH_F) dE = fma(-kk.y, fma(sn, cs.x, -(cn * cs.y)), dE);  // -k n sin(n phi - delta)
+                                }
+                                if (WITH_F) {
+                                    const double w = dE * rb;
+                                    A = fma(-w, s1 * s1, A);
+                                    B[q] = fma(w, s2[q] * s2[q], B[q]);
+                                }
+                            }
+                        }
+                        if (WITH_F) {
+                            const double g1 = pm_dot(d0, d1) * ib2;
+                            const double Ag = A * g1;
+                            fi = pm_d3{A * c1.x, A * c1.y, A * c1.z};
+                            pm_axpy(Fj, Ag - A, c1);  // F_j -= A (1 - g1) c1
+                            pm_axpy(Fk, -Ag, c1);     // F_k -= g1 A c1
+                        }
+                    }
+                    if (WITH_F) {
+                        PM_ORDERED(n_col, te.y, act, { pm_add3<CPW>(fs, ai, col, fi); })
+                    }
+                }
                 if (WITH_F) {
-                    const pm_d3 pv = pm_cross(d0, d1);
-                    const double rp2 = pm_dot(pv, pv);
-                    // 1/max(|p|, 1e-6)
-                    const double rpinv = rp2 > 1.0e-12 ? pm_rsqrt(rp2) : 1.0e6;
-                    // termA = kd / (r20 rp) ; termC = -kd / (r21 rp) ; 1/r20 = inv01^2 r21
-                    const double w = kd * rpinv * inv01 * inv01;
-                    const double termA = w * r21, termC = -w * r20;
-                    const pm_d3 c0 = pm_cross(d0, pv), c2 = pm_cross(d1, pv);
-                    const pm_d3 fa{termA * c0.x, termA * c0.y, termA * c0.z};
-                    const pm_d3 fc{termC * c2.x, termC * c2.y, termC * c2.z};
-                    pm_add3(fs, ia, lane, fa);
-                    pm_sub3(fs, ib, lane, pm_d3{fa.x + fc.x, fa.y + fc.y, fa.z + fc.z});
-                    pm_add3(fs, ic, lane, fc);
+                    if (live) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            if (q < nL) {
+                                const double Bg = B[q] * g2[q];
+                                pm_axpy(Fj, -Bg, c2[q]);        // F_j -= g2 B c2
+                                pm_axpy(Fk, Bg - B[q], c2[q]);  // F_k -= B (1 - g2) c2
+                            }
+                        }
+                    }
+                    PM_ORDERED(n_col, te.y, live, {
+                        _Pragma("unroll") for (int q = 0; q < 3; ++q) {
+                            if (q < nL) pm_add3<CPW>(fs, La[q], col, pm_d3{B[q] * c2[q].x, B[q] * c2[q].y, B[q] * c2[q].z});
+                        }
+                        pm_add3<CPW>(fs, aj, col, Fj);
+                        pm_add3<CPW>(fs, ak, col, Fk);
+                    })
                 }
             }
 
-            // ---- PeriodicTorsionForce (trig-free: cos/sin(phi) from the cross products) ------------
-            for (int t = 0; t < g.n_torsions; ++t) {
-                const int i0 = s_tors[4 * t], i1 = s_tors[4 * t + 1], i2 = s_tors[4 * t + 2], i3 = s_tors[4 * t + 3];
-                const int n = s_tper[t];
-                const double k = s_ptors[4 * t], kn = s_ptors[4 * t + 1], cd = s_ptors[4 * t + 2], sd = s_ptors[4 * t + 3];
-                const pm_d3 xb = pm_ld3(xs, i1, lane), xc = pm_ld3(xs, i2, lane);
-                const pm_d3 d0 = pm_sub(pm_ld3(xs, i0, lane), xb);
-                const pm_d3 d1 = pm_sub(xc, xb);
-                const pm_d3 d2 = pm_sub(xc, pm_ld3(xs, i3, lane));
-                const pm_d3 c1 = pm_cross(d0, d1), c2 = pm_cross(d1, d2);
-                const double nc1 = pm_dot(c1, c1), nc2 = pm_dot(c2, c2), nb2 = pm_dot(d1, d1);
-                const double inv12 = pm_rsqrt(nc1 * nc2);
-                const double rb_inv = pm_rsqrt(nb2);
-                const double rb = nb2 * rb_inv;
-                const double cphi = pm_dot(c1, c2) * inv12;
-                const double sphi = rb * pm_dot(d0, c2) * inv12;
-                double cn = 1.0, sn = 0.0;
-                for (int m = 0; m < n; ++m) {
-                    const double c_new = fma(cn, cphi, -(sn * sphi));
-                    sn = fma(sn, cphi, cn * sphi);
-                    cn = c_new;
-                }
-                // cos(n phi - delta), sin(n phi - delta)
-                const double cda = fma(cn, cd, sn * sd);
-                const double sda = fma(sn, cd, -(cn * sd));
-                e_tors = fma(k, cda, e_tors + k);
-                if (WITH_F) {
-                    const double dEdA = -kn * sda;
-                    const double i2_12 = inv12 * inv12;
-                    const double ff0 = -dEdA * rb * (i2_12 * nc2);  // / nc1
-                    const double ff3 = dEdA * rb * (i2_12 * nc1);   // / nc2
-                    const double ib2 = rb_inv * rb_inv;
-                    const double ff1 = pm_dot(d0, d1) * ib2;
-                    const double ff2 = pm_dot(d2, d1) * ib2;
-                    const pm_d3 f0{ff0 * c1.x, ff0 * c1.y, ff0 * c1.z};
-                    const pm_d3 f3{ff3 * c2.x, ff3 * c2.y, ff3 * c2.z};
-                    const pm_d3 sv{fma(ff1, f0.x, -(ff2 * f3.x)), fma(ff1, f0.y, -(ff2 * f3.y)), fma(ff1, f0.z, -(ff2 * f3.z))};
-                    pm_add3(fs, i0, lane, f0);
-                    pm_sub3(fs, i1, lane, pm_d3{f0.x - sv.x, f0.y - sv.y, f0.z - sv.z});
-                    pm_sub3(fs, i2, lane, pm_d3{f3.x + sv.x, f3.y + sv.y, f3.z + sv.z});
-                    pm_add3(fs, i3, lane, f3);
-                }
-            }
-
-            // ---- NonbondedForce: plain pairs and scaled 1-4 exceptions, register-tiled over i -------
-            for (int it = 0; it < g.n_itiles; ++it) {
-                const int *tl = s_itile + it * (PM_IT + 2);
+            // ================= nonbonded: plain pairs and scaled 1-4 exceptions, register-tiled over i ========
+            for (int seg = 0; seg < g.n_segs; ++seg) {
+                const int2 hdr = s_seg_hdr[seg];
+                const int4 ta4 = s_seg_tile[seg * L + tl];
+                const int ta[PM_IT] = {ta4.x, ta4.y, ta4.z, ta4.w};
                 pm_d3 xi[PM_IT], acc[PM_IT];
 #pragma unroll
                 for (int k = 0; k < PM_IT; ++k) {
-                    const int a = tl[k];
-                    xi[k] = pm_ld3(xs, a < 0 ? 0 : a, lane);
+                    xi[k] = pm_ld3<CPW>(xs, ta[k] < 0 ? 0 : ta[k], col);
                     acc[k] = pm_d3{0.0, 0.0, 0.0};
                 }
-                const int e_begin = tl[PM_IT], e_end = tl[PM_IT + 1];
-                for (int e = e_begin; e < e_end; ++e) {
-                    const int2 en = s_entry[e];
-                    const int j = en.x & 0xffff;
+                const int2 *ent = s_entries + hdr.y + tl;
+                for (int e = 0; e < hdr.x; ++e) {
+                    const int2 en = ent[e * L];
                     const int mask = en.x >> 16;
-                    const double *pp = s_ppair + 3 * en.y;
-                    const pm_d3 xj = pm_ld3(xs, j, lane);
-                    pm_d3 fj{0.0, 0.0, 0.0};
+                    if (mask) {
+                        const int j = en.x & 0xffff;
+                        const double *pp = s_ppair + 3 * en.y;
+                        const pm_d3 xj = pm_ld3<CPW>(xs, j, col);
+                        pm_d3 fj{0.0, 0.0, 0.0};
 #pragma unroll
-                    for (int k = 0; k < PM_IT; ++k) {
-                        if (mask & (1 << k)) {
-                            pm_pair<WITH_F>(xi[k], xj, pp, e_nb, acc[k], fj);
-                            pp += 3;
+                        for (int k = 0; k < PM_IT; ++k) {
+                            if (mask & (1 << k)) {
+                                pm_pair<WITH_F>(xi[k], xj, pp, e_nb, acc[k], fj);
+                                pp += 3;
+                            }
                         }
+                        if (WITH_F) pm_sub3<CPW>(fs, j, col, fj);
                     }
-                    if (WITH_F) pm_sub3(fs, j, lane, fj);
+                    if (L > 1) __syncwarp();
                 }
                 if (WITH_F) {
 #pragma unroll
                     for (int k = 0; k < PM_IT; ++k) {
-                        const int a = tl[k];
-                        if (a >= 0) pm_add3(fs, a, lane, acc[k]);
+                        if (ta[k] >= 0) pm_add3<CPW>(fs, ta[k], col, acc[k]);
                     }
+                    if (L > 1) __syncwarp();
                 }
             }
 
-            // ---- epilogue: per-conformation energy and force residual ------------------------------
-            const long sconf = tile * PM_TILE + lane;
-            const double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
-            if (sconf < n_conf) emm[(size_t)p * n_conf + sconf] = e_total;
-            if (WITH_F) {
-                if (fres != nullptr) {
-                    const double *fr = fref_t + (size_t)tile * tile_d + lane;
-                    double res = 0.0;
-                    for (int a = 0; a < N; ++a) {
-                        const double dx = fs[(3 * a) * PM_TILE + lane] - fr[(3 * a) * PM_TILE];
-                        const double dy = fs[(3 * a + 1) * PM_TILE + lane] - fr[(3 * a + 1) * PM_TILE];
-                        const double dz = fs[(3 * a + 2) * PM_TILE + lane] - fr[(3 * a + 2) * PM_TILE];
-                        const double *m = s_metric + 9 * a;
-                        // (d^T M) d as in np.matmul(np.matmul(d, M), d), force_property.py:93-94
-                        const double t0 = fma(dz, m[6], fma(dy, m[3], dx * m[0]));
-                        const double t1 = fma(dz, m[7], fma(dy, m[4], dx * m[1]));
-                        const double t2 = fma(dz, m[8], fma(dy, m[5], dx * m[2]));
-                        res += fma(t2, dz, fma(t1, dy, t0 * dx));
-                    }
-                    if (sconf < n_conf) fres[(size_t)p * n_conf + sconf] = res;
+            // ================= epilogue: per-conformation energy and force residual ==========================
+            const long sconf = tile * CPW + col;
+            double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
+            double res = 0.0;
+            if (WITH_F && fres != nullptr) {
+                const double *fr = fref_t + (size_t)tile * tile_d + col;
+                for (int a = tl; a < N; a += L) {
+                    const double dx = fs[(3 * a) * CPW + col] - fr[(3 * a) * CPW];
+                    const double dy = fs[(3 * a + 1) * CPW + col] - fr[(3 * a + 1) * CPW];
+                    const double dz = fs[(3 * a + 2) * CPW + col] - fr[(3 * a + 2) * CPW];
+                    const double *m = s_metric + 9 * a;
+                    // (d^T M) d as in np.matmul(np.matmul(d, M), d), force_property.py:93-94
+                    const double t0 = fma(dz, m[6], fma(dy, m[3], dx * m[0]));
+                    const double t1 = fma(dz, m[7], fma(dy, m[4], dx * m[1]));
+                    const double t2 = fma(dz, m[8], fma(dy, m[5], dx * m[2]));
+                    res += fma(t2, dz, fma(t1, dy, t0 * dx));
                 }
-                if (fmm_t != nullptr) {
-                    double *fo = fmm_t + ((size_t)p * n_tiles + tile) * tile_d + lane;
-                    for (int k = 0; k < 3 * N; ++k) fo[k * PM_TILE] = fs[k * PM_TILE + lane];
+            }
+            if (L > 1) {
+#pragma unroll
+                for (int o = CPW; o < 32; o <<= 1) {
+                    e_total += __shfl_xor_sync(0xffffffffu, e_total, o);
+                    res += __shfl_xor_sync(0xffffffffu, res, o);
                 }
+            }
+            if (tl == 0 && sconf < n_conf) {
+                emm[(size_t)p * n_conf + sconf] = e_total;
+                if (WITH_F && fres != nullptr) fres[(size_t)p * n_conf + sconf] = res;
+            }
+            if (WITH_F && fmm_t != nullptr) {
+                double *fo = fmm_t + ((size_t)p * n_tiles + tile) * tile_d;
+                for (int k = lane; k < tile_d; k += 32) fo[k] = fs[k];
             }
             __syncwarp();
         }
@@ -349,13 +519,13 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
 }
 
 // =============================================================================================
-// [S][N][3] <-> tiles
+// [S][N][3] <-> tiles of CPW conformations
 // =============================================================================================
-__global__ void pm_pack_kernel(const double *__restrict__ src, long n_conf, int row /* 3N */, double *__restrict__ tiles) {
-    extern __shared__ double s_buf[];  // [32][row + 1]
+__global__ void pm_pack_kernel(const double *__restrict__ src, long n_conf, int row /* 3N */, int cpw, double *__restrict__ tiles) {
+    extern __shared__ double s_buf[];  // [cpw][row + 1]
     const long tile = blockIdx.x;
-    const long s0 = tile * PM_TILE;
-    const int total = PM_TILE * row;
+    const long s0 = tile * cpw;
+    const int total = cpw * row;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int c = i / row, k = i - c * row;
         long s = s0 + c;
@@ -365,19 +535,19 @@ __global__ void pm_pack_kernel(const double *__restrict__ src, long n_conf, int 
     __syncthreads();
     double *dst = tiles + (size_t)tile * total;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i >> 5, c = i & 31;
+        const int k = i / cpw, c = i - k * cpw;
         dst[i] = s_buf[c * (row + 1) + k];
     }
 }
 
-__global__ void pm_unpack_kernel(const double *__restrict__ tiles, long n_conf, int row, double *__restrict__ dst) {
+__global__ void pm_unpack_kernel(const double *__restrict__ tiles, long n_conf, int row, int cpw, double *__restrict__ dst) {
     extern __shared__ double s_buf[];
     const long tile = blockIdx.x;
-    const long s0 = tile * PM_TILE;
-    const int total = PM_TILE * row;
+    const long s0 = tile * cpw;
+    const int total = cpw * row;
     const double *src = tiles + (size_t)tile * total;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int k = i >> 5, c = i & 31;
+        const int k = i / cpw, c = i - k * cpw;
         s_buf[c * (row + 1) + k] = src[i];
     }
     __syncthreads();
@@ -479,17 +649,17 @@ __global__ void pm_fma_peak_kernel(T *out, int iters, T b, T c) {
 }
 
 // =============================================================================================
-// Host side: handle, topology program builder, C ABI
+// Host side: handle, C ABI
 // =============================================================================================
 static thread_local std::string g_err;
 static int pm_fail(const std::string &msg) {
     g_err = msg;
     return 1;
 }
-#define PM_CUDA(call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t _e = (call);                                                                        \
-        if (_e != cudaSuccess) return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e));      \
+#define PM_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
 struct pm_handle_s {
@@ -497,17 +667,29 @@ struct pm_handle_s {
     int n_sm;
     int max_smem;
     PmProg prog;
-    std::vector<int> pairs;  // host copy of pair_map
+    PmHostProgram host;
     int *d_ints;
     double *d_metric;
     int *d_pair_map;
-    size_t shared_bytes[2];  // CTA-shared part, [with_forces]
-    int warps[2];
+    double2 *d_acos;
+    int warps[2];  // [with_forces]
     size_t smem_total[2];
 };
 
+typedef void (*pm_ef_fn)(PmProg, const double *, int, const double *, const double *, long, long, double *, double *, double *);
+
+static pm_ef_fn pm_pick_kernel(int cpw, int wf) {
+    switch (cpw) {
+        case 32: return wf ? pm_ef_kernel<32, true> : pm_ef_kernel<32, false>;
+        case 16: return wf ? pm_ef_kernel<16, true> : pm_ef_kernel<16, false>;
+        case 8: return wf ? pm_ef_kernel<8, true> : pm_ef_kernel<8, false>;
+        case 4: return wf ? pm_ef_kernel<4, true> : pm_ef_kernel<4, false>;
+        default: return nullptr;
+    }
+}
+
 extern "C" const char *pm_last_error(void) { return g_err.c_str(); }
-extern "C" int pm_version(void) { return 100; }
+extern "C" int pm_version(void) { return 200; }
 extern "C" int pm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -516,41 +698,27 @@ extern "C" int pm_device_count(void) {
     }
     return n;
 }
-extern "C" long pm_n_tiles(long n_conf) { return (n_conf + PM_TILE - 1) / PM_TILE; }
 
-static void pm_plan_launch(pm_handle_s *h) {
-    const PmProg &g = h->prog;
-    for (int wf = 0; wf < 2; ++wf) {
-        size_t off = ((size_t)g.n_int * sizeof(int) + 15) & ~(size_t)15;
-        off += (size_t)9 * g.n_atoms * sizeof(double);
-        off += (size_t)g.n_derived * sizeof(double);
-        off = (off + 127) & ~(size_t)127;
-        const size_t per_warp = 128 + (size_t)3 * g.n_atoms * PM_TILE * sizeof(double) * (wf ? 2 : 1);
-        long w = ((long)h->max_smem - (long)off) / (long)per_warp;
-        if (w > PM_MAX_WARPS) w = PM_MAX_WARPS;
-        h->shared_bytes[wf] = off;
-        h->warps[wf] = (int)w;
-        h->smem_total[wf] = w > 0 ? off + per_warp * (size_t)w : 0;
-    }
+// shared-memory plan for a given CPW: bytes shared by the CTA, per-warp bytes, warps that fit
+static void pm_plan(int n_int, int n_derived, int N, int cpw, int max_smem, int wf, size_t *shared, size_t *per_warp, int *warps) {
+    size_t off = ((size_t)n_int * sizeof(int) + 15) & ~(size_t)15;
+    off += (size_t)(PM_ACOS_N + 1) * sizeof(double2);
+    off += ((size_t)9 * N * sizeof(double) + 15) & ~(size_t)15;
+    off += (size_t)n_derived * sizeof(double);
+    off = (off + 127) & ~(size_t)127;
+    const size_t pw = 128 + (size_t)3 * N * cpw * sizeof(double) * (wf ? 2 : 1);
+    long w = ((long)max_smem - (long)off) / (long)pw;
+    if (w > PM_MAX_WARPS) w = PM_MAX_WARPS;
+    if (w < 0) w = 0;
+    *shared = off;
+    *per_warp = pw;
+    *warps = (int)w;
 }
 
-extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
-    if (!t || !out) return pm_fail("pm_create: null argument");
-    if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_create: n_atoms out of range");
-    if (t->nonbonded_method != 0) return pm_fail("pm_create: only NoCutoff is implemented on the device path");
-    int n_dev = 0;
-    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
-        cudaGetLastError();
-        return pm_fail("pm_create: no CUDA device (this path has no CPU fallback)");
-    }
-    if (device < 0 || device >= n_dev) return pm_fail("pm_create: bad device index");
-    PM_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    PM_CUDA(cudaGetDeviceProperties(&prop, device));
-
+// pair classes (0 plain, 1 excluded, 2 + e active exception e) + index validation; returns 0 or sets the error
+static int pm_classify(const pm_topology *t, std::vector<int> &cls) {
     const int N = t->n_atoms;
-    // ---- classify atom pairs: 0 plain, 1 excluded, 2 + e : active exception e -----------------------
-    std::vector<int> cls((size_t)N * N, 0);
+    cls.assign((size_t)N * N, 0);
     for (int e = 0; e < t->n_exceptions; ++e) {
         const int i = t->exception_idx[2 * e], j = t->exception_idx[2 * e + 1];
         if (i < 0 || j < 0 || i >= N || j >= N || i == j) return pm_fail("pm_create: bad exception indices");
@@ -571,73 +739,116 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
         return 1;
     for (int k = 0; k < t->n_torsions; ++k)
         if (t->torsion_per[k] < 0 || t->torsion_per[k] > 64) return pm_fail("pm_create: torsion periodicity out of range");
+    return 0;
+}
 
-    // ---- i-tiles and their j entries -------------------------------------------------------------
-    const int n_itiles = (N + PM_IT - 1) / PM_IT;
-    std::vector<int> itile((size_t)n_itiles * (PM_IT + 2));
-    std::vector<int> entries;  // int2
-    std::vector<int> pair_map; // (i, j, e)
-    for (int it = 0; it < n_itiles; ++it) {
-        int atoms[PM_IT];
-        for (int k = 0; k < PM_IT; ++k) {
-            const int a = it * PM_IT + k;
-            atoms[k] = a < N ? a : -1;
-            itile[(size_t)it * (PM_IT + 2) + k] = atoms[k];
-        }
-        itile[(size_t)it * (PM_IT + 2) + PM_IT] = (int)(entries.size() / 2);
-        for (int j = atoms[0] + 1; j < N; ++j) {
-            int mask = 0;
-            const int base = (int)(pair_map.size() / 3);
-            for (int k = 0; k < PM_IT; ++k) {
-                const int a = atoms[k];
-                if (a < 0 || a >= j) continue;
-                const int c = cls[(size_t)a * N + j];
-                if (c == 1) continue;
-                mask |= 1 << k;
-                pair_map.push_back(a);
-                pair_map.push_back(j);
-                pair_map.push_back(c == 0 ? -1 : c - 2);
-            }
-            if (mask) {
-                entries.push_back(j | (mask << 16));
-                entries.push_back(base);
-            }
-        }
-        itile[(size_t)it * (PM_IT + 2) + PM_IT + 1] = (int)(entries.size() / 2);
+// Host-only: build the topology program for a given CPW and validate its invariants (no CUDA call).
+// stats10 as pm_program_info.  Returns 0 when the program is valid.
+extern "C" int pm_program_check(const pm_topology *t, int cpw, int *stats10) {
+    if (!t) return pm_fail("pm_program_check: null argument");
+    if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_program_check: cpw must be 32, 16, 8 or 4");
+    if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_program_check: n_atoms out of range");
+    std::vector<int> cls;
+    if (pm_classify(t, cls)) return 1;
+    PmHostProgram p;
+    if (!pm_build_program(t->n_atoms, 32 / cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+                          t->torsion_per, cls, p))
+        return pm_fail("pm_program_check: degenerate bonded term (repeated atom)");
+    const int rc = pm_validate_program(p, t->n_atoms, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions,
+                                       t->torsion_idx, cls);
+    if (stats10) {
+        const int v[10] = {cpw, 32 / cpw, p.n_stars, p.n_star_steps, p.n_axes, p.n_axis_steps, p.n_segs, p.n_entries,
+                           p.n_entry_slots, (int)p.blob.size()};
+        memcpy(stats10, v, sizeof(v));
     }
+    if (rc) return pm_fail("pm_program_check: invariant " + std::to_string(rc) + " violated");
+    return 0;
+}
+
+extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
+    if (!t || !out) return pm_fail("pm_create: null argument");
+    if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_create: n_atoms out of range");
+    if (t->nonbonded_method != 0) return pm_fail("pm_create: only NoCutoff is implemented on the device path");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return pm_fail("pm_create: no CUDA device (this path has no CPU fallback)");
+    }
+    if (device < 0 || device >= n_dev) return pm_fail("pm_create: bad device index");
+    PM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PM_CUDA(cudaGetDeviceProperties(&prop, device));
+
+    const int N = t->n_atoms;
+    std::vector<int> cls;
+    if (pm_classify(t, cls)) return 1;
+
+    // ---- choose CPW (conformations per warp; L = 32 / CPW lanes per conformation) ---------------------------
+    // The derived-table size does not depend on L, the program size only weakly: plan with the L = 1 program.
+    const int max_smem = (int)prop.sharedMemPerBlockOptin;
+    int cpw = 0;
+    const char *env = getenv("PM_CPW");
+    if (env && *env) {
+        cpw = atoi(env);
+        if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: PM_CPW must be 32, 16, 8 or 4");
+    }
+    PmHostProgram host;
+    const int n_derived_est = 2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * (N * (N - 1) / 2) + 2;
+    if (!cpw) {
+        // fewest lanes per conformation that still gives >= 12 warps per SM; else the CPW with most warps
+        int best_w = -1;
+        for (int c = 32; c >= 4; c >>= 1) {
+            size_t sh, pw;
+            int w;
+            pm_plan(4096 + 40 * N * (32 / c), n_derived_est, N, c, max_smem, 1, &sh, &pw, &w);
+            if (w >= 12) {
+                cpw = c;
+                break;
+            }
+            if (w > best_w) {
+                best_w = w;
+                cpw = c;
+            }
+        }
+    }
+    if (!pm_build_program(N, 32 / cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+                          t->torsion_per, cls, host))
+        return pm_fail("pm_create: degenerate bonded term (repeated atom)");
 
     pm_handle_s *h = new pm_handle_s();
     memset(&h->prog, 0, sizeof(PmProg));
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
-    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->max_smem = max_smem;
     h->d_ints = nullptr;
     h->d_metric = nullptr;
     h->d_pair_map = nullptr;
+    h->d_acos = nullptr;
+    h->host = host;
     PmProg &g = h->prog;
     g.n_atoms = N;
     g.n_bonds = t->n_bonds;
     g.n_angles = t->n_angles;
     g.n_torsions = t->n_torsions;
-    g.n_itiles = n_itiles;
-    g.n_entries = (int)(entries.size() / 2);
-    g.n_pairs = (int)(pair_map.size() / 3);
+    g.n_pairs = host.n_pairs;
+    g.cpw = cpw;
+    g.L = 32 / cpw;
+    g.n_star_steps = host.n_star_steps;
+    g.n_axis_steps = host.n_axis_steps;
+    g.n_segs = host.n_segs;
+    g.n_int = (int)host.blob.size();
+    g.off_star_tab = host.off_star_tab;
+    g.off_star_hdr = host.off_star_hdr;
+    g.off_star_rec = host.off_star_rec;
+    g.off_axis_tab = host.off_axis_tab;
+    g.off_axis_hdr = host.off_axis_hdr;
+    g.off_axis_rec = host.off_axis_rec;
+    g.off_axis_terms = host.off_axis_terms;
+    g.off_seg_hdr = host.off_seg_hdr;
+    g.off_seg_tile = host.off_seg_tile;
+    g.off_entries = host.off_entries;
+    g.off_tper = host.off_tper;
     g.k_coul = t->one_4pi_eps0;
-
-    std::vector<int> blob;
-    auto append = [&](const int *p, size_t n) {
-        int o = (int)blob.size();
-        blob.insert(blob.end(), p, p + n);
-        return o;
-    };
-    g.off_bond = append(t->bond_idx, (size_t)2 * t->n_bonds);
-    g.off_angle = append(t->angle_idx, (size_t)3 * t->n_angles);
-    g.off_tors = append(t->torsion_idx, (size_t)4 * t->n_torsions);
-    g.off_tper = append(t->torsion_per, (size_t)t->n_torsions);
-    g.off_itile = append(itile.data(), itile.size());
-    if (blob.size() & 1) blob.push_back(0);  // int2 alignment of the entry table
-    g.off_entry = append(entries.data(), entries.size());
-    g.n_int = (int)blob.size();
 
     g.doff_bond = 0;
     g.doff_angle = g.doff_bond + 2 * g.n_bonds;
@@ -653,41 +864,58 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     g.soff_exc = g.soff_part + 3 * N;
     g.n_slots = g.soff_exc + 3 * t->n_exceptions;
 
-    h->pairs = pair_map;
     auto cleanup = [&]() {
         if (h->d_ints) cudaFree(h->d_ints);
         if (h->d_metric) cudaFree(h->d_metric);
         if (h->d_pair_map) cudaFree(h->d_pair_map);
+        if (h->d_acos) cudaFree(h->d_acos);
         delete h;
     };
-#define PM_CUDA_H(call)                                                          \
-    do {                                                                         \
-        cudaError_t _e = (call);                                                 \
-        if (_e != cudaSuccess) {                                                 \
-            cleanup();                                                           \
-            return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e));  \
-        }                                                                        \
+#define PM_CUDA_H(call)                                                         \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) {                                                \
+            cleanup();                                                          \
+            return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+        }                                                                       \
     } while (0)
-    PM_CUDA_H(cudaMalloc(&h->d_ints, sizeof(int) * (blob.size() + 2)));
-    PM_CUDA_H(cudaMemcpy(h->d_ints, blob.data(), sizeof(int) * blob.size(), cudaMemcpyHostToDevice));
-    PM_CUDA_H(cudaMalloc(&h->d_pair_map, sizeof(int) * (pair_map.size() + 3)));
-    if (!pair_map.empty())
-        PM_CUDA_H(cudaMemcpy(h->d_pair_map, pair_map.data(), sizeof(int) * pair_map.size(), cudaMemcpyHostToDevice));
+    PM_CUDA_H(cudaMalloc(&h->d_ints, sizeof(int) * (host.blob.size() + 4)));
+    PM_CUDA_H(cudaMemcpy(h->d_ints, host.blob.data(), sizeof(int) * host.blob.size(), cudaMemcpyHostToDevice));
+    PM_CUDA_H(cudaMalloc(&h->d_pair_map, sizeof(int) * (host.pair_map.size() + 3)));
+    if (!host.pair_map.empty())
+        PM_CUDA_H(cudaMemcpy(h->d_pair_map, host.pair_map.data(), sizeof(int) * host.pair_map.size(), cudaMemcpyHostToDevice));
     std::vector<double> ident((size_t)9 * N, 0.0);
     for (int a = 0; a < N; ++a) ident[9 * a] = ident[9 * a + 4] = ident[9 * a + 8] = 1.0;
     PM_CUDA_H(cudaMalloc(&h->d_metric, sizeof(double) * 9 * N));
     PM_CUDA_H(cudaMemcpy(h->d_metric, ident.data(), sizeof(double) * 9 * N, cudaMemcpyHostToDevice));
+    std::vector<double> tab(2 * (PM_ACOS_N + 1));
+    for (int q = 0; q <= PM_ACOS_N; ++q) {
+        const double th = (double)q * (PM_PI / PM_ACOS_N);
+        tab[2 * q] = cos(th);
+        tab[2 * q + 1] = sin(th);
+    }
+    PM_CUDA_H(cudaMalloc(&h->d_acos, sizeof(double) * tab.size()));
+    PM_CUDA_H(cudaMemcpy(h->d_acos, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     g.ints = h->d_ints;
     g.metric = h->d_metric;
     g.pair_map = h->d_pair_map;
+    g.acos_tab = h->d_acos;
 
-    pm_plan_launch(h);
+    for (int wf = 0; wf < 2; ++wf) {
+        size_t sh, pw;
+        int w;
+        pm_plan(g.n_int, g.n_derived, N, cpw, max_smem, wf, &sh, &pw, &w);
+        const char *envw = getenv("PM_WARPS");
+        if (envw && *envw && atoi(envw) > 0 && atoi(envw) < w) w = atoi(envw);
+        h->warps[wf] = w;
+        h->smem_total[wf] = w > 0 ? sh + pw * (size_t)w : 0;
+    }
     if (h->warps[1] < 1 || h->warps[0] < 1) {
         cleanup();
-        return pm_fail("pm_create: molecule too large for the shared-memory tile of this kernel generation");
+        return pm_fail("pm_create: molecule too large for the shared-memory tiles of this kernel generation");
     }
-    PM_CUDA_H(cudaFuncSetAttribute(pm_ef_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
-    PM_CUDA_H(cudaFuncSetAttribute(pm_ef_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
     *out = h;
     return 0;
 }
@@ -698,6 +926,7 @@ extern "C" int pm_destroy(pm_handle h) {
     cudaFree(h->d_ints);
     cudaFree(h->d_metric);
     cudaFree(h->d_pair_map);
+    cudaFree(h->d_acos);
     delete h;
     return 0;
 }
@@ -705,10 +934,12 @@ extern "C" int pm_destroy(pm_handle h) {
 extern "C" int pm_n_slots(pm_handle h) { return h ? h->prog.n_slots : -1; }
 extern "C" int pm_n_derived(pm_handle h) { return h ? h->prog.n_derived : -1; }
 extern "C" int pm_n_pairs(pm_handle h) { return h ? h->prog.n_pairs : -1; }
-extern "C" long pm_tile_doubles(pm_handle h) { return h ? (long)3 * h->prog.n_atoms * PM_TILE : -1; }
+extern "C" int pm_conf_per_tile(pm_handle h) { return h ? h->prog.cpw : -1; }
+extern "C" long pm_n_tiles(pm_handle h, long n_conf) { return h ? (n_conf + h->prog.cpw - 1) / h->prog.cpw : -1; }
+extern "C" long pm_tile_doubles(pm_handle h) { return h ? (long)3 * h->prog.n_atoms * h->prog.cpw : -1; }
 extern "C" int pm_get_pairs(pm_handle h, int *out_host) {
     if (!h || !out_host) return pm_fail("pm_get_pairs: null argument");
-    memcpy(out_host, h->pairs.data(), sizeof(int) * h->pairs.size());
+    memcpy(out_host, h->host.pair_map.data(), sizeof(int) * h->host.pair_map.size());
     return 0;
 }
 extern "C" int pm_launch_info(pm_handle h, int with_forces, int *grid, int *block, int *smem_bytes, int *warps_per_cta) {
@@ -718,6 +949,14 @@ extern "C" int pm_launch_info(pm_handle h, int with_forces, int *grid, int *bloc
     if (block) *block = h->warps[wf] * 32;
     if (smem_bytes) *smem_bytes = (int)h->smem_total[wf];
     if (warps_per_cta) *warps_per_cta = h->warps[wf];
+    return 0;
+}
+extern "C" int pm_program_info(pm_handle h, int *out10) {
+    if (!h || !out10) return pm_fail("pm_program_info: null argument");
+    const PmHostProgram &p = h->host;
+    const int v[10] = {h->prog.cpw, h->prog.L, p.n_stars, p.n_star_steps, p.n_axes, p.n_axis_steps, p.n_segs, p.n_entries,
+                       p.n_entry_slots, (int)p.blob.size()};
+    memcpy(out10, v, sizeof(v));
     return 0;
 }
 
@@ -732,10 +971,10 @@ extern "C" int pm_pack_tiles(pm_handle h, const double *src_dev, long n_conf, do
     if (!h || !src_dev || !tiles_dev) return pm_fail("pm_pack_tiles: null argument");
     if (n_conf < 1) return pm_fail("pm_pack_tiles: no conformations");
     PM_CUDA(cudaSetDevice(h->device));
-    const int row = 3 * h->prog.n_atoms;
-    const size_t smem = sizeof(double) * PM_TILE * (row + 1);
+    const int row = 3 * h->prog.n_atoms, cpw = h->prog.cpw;
+    const size_t smem = sizeof(double) * cpw * (row + 1);
     if (smem > 48 * 1024) PM_CUDA(cudaFuncSetAttribute(pm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pm_pack_kernel<<<(unsigned)pm_n_tiles(n_conf), 256, smem, (cudaStream_t)stream>>>(src_dev, n_conf, row, tiles_dev);
+    pm_pack_kernel<<<(unsigned)pm_n_tiles(h, n_conf), 256, smem, (cudaStream_t)stream>>>(src_dev, n_conf, row, cpw, tiles_dev);
     PM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -744,10 +983,10 @@ extern "C" int pm_unpack_tiles(pm_handle h, const double *tiles_dev, long n_conf
     if (!h || !dst_dev || !tiles_dev) return pm_fail("pm_unpack_tiles: null argument");
     if (n_conf < 1) return pm_fail("pm_unpack_tiles: no conformations");
     PM_CUDA(cudaSetDevice(h->device));
-    const int row = 3 * h->prog.n_atoms;
-    const size_t smem = sizeof(double) * PM_TILE * (row + 1);
+    const int row = 3 * h->prog.n_atoms, cpw = h->prog.cpw;
+    const size_t smem = sizeof(double) * cpw * (row + 1);
     if (smem > 48 * 1024) PM_CUDA(cudaFuncSetAttribute(pm_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pm_unpack_kernel<<<(unsigned)pm_n_tiles(n_conf), 256, smem, (cudaStream_t)stream>>>(tiles_dev, n_conf, row, dst_dev);
+    pm_unpack_kernel<<<(unsigned)pm_n_tiles(h, n_conf), 256, smem, (cudaStream_t)stream>>>(tiles_dev, n_conf, row, cpw, dst_dev);
     PM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -770,21 +1009,17 @@ extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const 
     if (!with_forces && (fres_dev || fmm_tiles_dev)) return pm_fail("pm_eval: force outputs requested with with_forces=0");
     PM_CUDA(cudaSetDevice(h->device));
     const int wf = with_forces ? 1 : 0;
-    const long n_tiles = pm_n_tiles(n_conf);
-    int warps = h->warps[wf];
-    // do not launch more warps than tiles
-    long grid = h->n_sm;
+    const long n_tiles = pm_n_tiles(h, n_conf);
+    const int warps = h->warps[wf];
+    long grid = h->n_sm;  // persistent: one CTA per SM; never more warps than tiles
     if ((long)grid * warps > n_tiles) {
         grid = (n_tiles + warps - 1) / warps;
         if (grid < 1) grid = 1;
     }
-    const size_t smem = h->smem_total[wf];
-    if (wf)
-        pm_ef_kernel<true><<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
-            h->prog, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, n_tiles, emm_dev, fres_dev, fmm_tiles_dev);
-    else
-        pm_ef_kernel<false><<<(unsigned)grid, warps * 32, smem, (cudaStream_t)stream>>>(
-            h->prog, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, n_tiles, emm_dev, nullptr, nullptr);
+    pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf);
+    fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(h->prog, derived_dev, n_vec, coord_tiles_dev,
+                                                                                fref_tiles_dev, n_conf, n_tiles, emm_dev,
+                                                                                wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr);
     PM_CUDA(cudaGetLastError());
     return 0;
 }
