@@ -108,7 +108,28 @@ __device__ __forceinline__ void pm_axpy(pm_d3 &a, const double s, const pm_d3 v)
     a.z = fma(s, v.z, a.z);
 }
 
-// Tile accessors: tile[(3*atom + c) * CPW + column]; CPW = conformations per warp (row = CPW doubles)
+// Tile accessors.  Tile = doubles [3N][CPW] (row = CPW doubles).  The topology program stores atoms as BYTE offsets of
+// their first row (atom * 3 * CPW * 8), and `base` already points at this lane's column: address = base + offset.
+template <int CPW>
+__device__ __forceinline__ pm_d3 pm_ldo(const double *base, int boff) {
+    const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + boff);
+    return pm_d3{p[0], p[CPW], p[2 * CPW]};
+}
+template <int CPW>
+__device__ __forceinline__ void pm_addo(double *base, int boff, const pm_d3 v) {
+    double *p = reinterpret_cast<double *>(reinterpret_cast<char *>(base) + boff);
+    p[0] += v.x;
+    p[CPW] += v.y;
+    p[2 * CPW] += v.z;
+}
+template <int CPW>
+__device__ __forceinline__ void pm_subo(double *base, int boff, const pm_d3 v) {
+    double *p = reinterpret_cast<double *>(reinterpret_cast<char *>(base) + boff);
+    p[0] -= v.x;
+    p[CPW] -= v.y;
+    p[2 * CPW] -= v.z;
+}
+// Index-based variants: tile[(3*atom + c) * CPW + column]
 template <int CPW>
 __device__ __forceinline__ pm_d3 pm_ld3(const double *tile, int atom, int col) {
     const double *p = tile + (3 * atom) * CPW + col;

@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
             __syncwarp();
 
             double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
+            const double *xc_base = xs + col;  // this lane's column of the coordinate / force tiles
+            double *fc_base = fs + col;
 
             // ================= stars: bonds and angles around a centre atom ==========================
             for (int step = 0; step < g.n_star_steps; ++step) {
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                     nb[3] = h1.y;
                     const int bp[4] = {h1.z, h1.w, h2.x, h2.y};
                     const int ap[6] = {h2.z, h2.w, h3.x, h3.y, h3.z, h3.w};
-                    const pm_d3 xc = pm_ld3<CPW>(xs, center, col);
+                    const pm_d3 xc = pm_ldo<CPW>(xc_base, center);
                     pm_d3 d[4];
                     double r2[4], ri[4];
 #pragma unroll
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                         r2[k] = 1.0;
                         ri[k] = 1.0;
                         if (k < m) {
-                            d[k] = pm_sub(xc, pm_ld3<CPW>(xs, nb[k], col));
+                            d[k] = pm_sub(xc, pm_ldo<CPW>(xc_base, nb[k]));
                             r2[k] = pm_dot(d[k], d[k]);
                             ri[k] = pm_rsqrt(r2[k]);
                             if (bp[k] >= 0) {
@@ -294,13 +296,13 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                         pm_d3 fc{0.0, 0.0, 0.0};
                         _Pragma("unroll") for (int k = 0; k < 4; ++k) {
                             if (k < m) {
-                                pm_add3<CPW>(fs, nb[k], col, f[k]);
+                                pm_addo<CPW>(fc_base, nb[k], f[k]);
                                 fc.x -= f[k].x;
                                 fc.y -= f[k].y;
                                 fc.z -= f[k].z;
                             }
                         }
-                        pm_add3<CPW>(fs, center, col, fc);
+                        pm_addo<CPW>(fc_base, center, fc);
                     })
                 }
             }
@@ -349,8 +351,8 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                     ts[7] = h4.y;
                     ts[8] = h4.z;
                     ts[9] = h4.w;
-                    xj = pm_ld3<CPW>(xs, aj, col);
-                    const pm_d3 xk = pm_ld3<CPW>(xs, ak, col);
+                    xj = pm_ldo<CPW>(xc_base, aj);
+                    const pm_d3 xk = pm_ldo<CPW>(xc_base, ak);
                     d1 = pm_sub(xk, xj);
                     const double nb2 = pm_dot(d1, d1);
                     const double rbi = pm_rsqrt(nb2);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         if (q < nL) {
-                            const pm_d3 d2 = pm_sub(xk, pm_ld3<CPW>(xs, La[q], col));
+                            const pm_d3 d2 = pm_sub(xk, pm_ldo<CPW>(xc_base, La[q]));
                             c2[q] = pm_cross(d1, d2);
                             s2[q] = pm_rsqrt(pm_dot(c2[q], c2[q]));
                             g2[q] = pm_dot(d2, d1) * ib2;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                     pm_d3 fi{0.0, 0.0, 0.0};
                     if (act) {
                         ai = pi == 0 ? Ia[0] : (pi == 1 ? Ia[1] : Ia[2]);
-                        const pm_d3 d0 = pm_sub(pm_ld3<CPW>(xs, ai, col), xj);
+                        const pm_d3 d0 = pm_sub(pm_ldo<CPW>(xc_base, ai), xj);
                         const pm_d3 c1 = pm_cross(d0, d1);
                         const double s1 = pm_rsqrt(pm_dot(c1, c1));
                         double A = 0.0;
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                         }
                     }
                     if (WITH_F) {
-                        PM_ORDERED(n_col, te.y, act, { pm_add3<CPW>(fs, ai, col, fi); })
+                        PM_ORDERED(n_col, te.y, act, { pm_addo<CPW>(fc_base, ai, fi); })
                     }
                 }
                 if (WITH_F) {
@@ -432,10 +434,10 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                     }
                     PM_ORDERED(n_col, te.y, live, {
                         _Pragma("unroll") for (int q = 0; q < 3; ++q) {
-                            if (q < nL) pm_add3<CPW>(fs, La[q], col, pm_d3{B[q] * c2[q].x, B[q] * c2[q].y, B[q] * c2[q].z});
+                            if (q < nL) pm_addo<CPW>(fc_base, La[q], pm_d3{B[q] * c2[q].x, B[q] * c2[q].y, B[q] * c2[q].z});
                         }
-                        pm_add3<CPW>(fs, aj, col, Fj);
-                        pm_add3<CPW>(fs, ak, col, Fk);
+                        pm_addo<CPW>(fc_base, aj, Fj);
+                        pm_addo<CPW>(fc_base, ak, Fk);
                     })
                 }
             }
@@ -448,33 +450,39 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                 pm_d3 xi[PM_IT], acc[PM_IT];
 #pragma unroll
                 for (int k = 0; k < PM_IT; ++k) {
-                    xi[k] = pm_ld3<CPW>(xs, ta[k] < 0 ? 0 : ta[k], col);
+                    xi[k] = pm_ldo<CPW>(xc_base, ta[k] < 0 ? 0 : ta[k]);
                     acc[k] = pm_d3{0.0, 0.0, 0.0};
                 }
                 const int2 *ent = s_entries + hdr.y + tl;
                 for (int e = 0; e < hdr.x; ++e) {
                     const int2 en = ent[e * L];
-                    const int mask = en.x >> 16;
+                    const int mask = (en.x >> 28) & 15;
                     if (mask) {
-                        const int j = en.x & 0xffff;
+                        const int j = en.x & 0x0fffffff;  // byte offset of atom j
                         const double *pp = s_ppair + 3 * en.y;
-                        const pm_d3 xj = pm_ld3<CPW>(xs, j, col);
+                        const pm_d3 xj = pm_ldo<CPW>(xc_base, j);
                         pm_d3 fj{0.0, 0.0, 0.0};
+                        if (mask == 15) {
+                            // all four pairs interact: one branch-free block, four independent dependency chains
 #pragma unroll
-                        for (int k = 0; k < PM_IT; ++k) {
-                            if (mask & (1 << k)) {
-                                pm_pair<WITH_F>(xi[k], xj, pp, e_nb, acc[k], fj);
-                                pp += 3;
+                            for (int k = 0; k < PM_IT; ++k) pm_pair<WITH_F>(xi[k], xj, pp + 3 * k, e_nb, acc[k], fj);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < PM_IT; ++k) {
+                                if (mask & (1 << k)) {
+                                    pm_pair<WITH_F>(xi[k], xj, pp, e_nb, acc[k], fj);
+                                    pp += 3;
+                                }
                             }
                         }
-                        if (WITH_F) pm_sub3<CPW>(fs, j, col, fj);
+                        if (WITH_F) pm_subo<CPW>(fc_base, j, fj);
                     }
                     if (L > 1) __syncwarp();
                 }
                 if (WITH_F) {
 #pragma unroll
                     for (int k = 0; k < PM_IT; ++k) {
-                        if (ta[k] >= 0) pm_add3<CPW>(fs, ta[k], col, acc[k]);
+                        if (ta[k] >= 0) pm_addo<CPW>(fc_base, ta[k], acc[k]);
                     }
                     if (L > 1) __syncwarp();
                 }
@@ -751,7 +759,7 @@ extern "C" int pm_program_check(const pm_topology *t, int cpw, int *stats10) {
     std::vector<int> cls;
     if (pm_classify(t, cls)) return 1;
     PmHostProgram p;
-    if (!pm_build_program(t->n_atoms, 32 / cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+    if (!pm_build_program(t->n_atoms, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
                           t->torsion_per, cls, p))
         return pm_fail("pm_program_check: degenerate bonded term (repeated atom)");
     const int rc = pm_validate_program(p, t->n_atoms, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions,
@@ -811,7 +819,7 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
             }
         }
     }
-    if (!pm_build_program(N, 32 / cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+    if (!pm_build_program(N, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
                           t->torsion_per, cls, host))
         return pm_fail("pm_create: degenerate bonded term (repeated atom)");
 

@@ -29,7 +29,7 @@
 #define PMH_IT 4
 
 struct PmHostProgram {
-    int n_atoms = 0, L = 1;
+    int n_atoms = 0, L = 1, cpw = 32;
     std::vector<int> blob;      // everything the kernel stages into shared memory
     std::vector<int> pair_map;  // (i, j, exception or -1) per interacting pair, kernel order
     int n_pairs = 0;
@@ -121,11 +121,15 @@ inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_s
 }  // namespace pmh
 
 // cls[i*N+j]: 0 plain pair, 1 excluded, 2+e active exception e
-inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int n_angles, const int *angle_idx, int n_torsions,
+inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, int n_angles, const int *angle_idx, int n_torsions,
                              const int *tors_idx, const int *tors_per, const std::vector<int> &cls, PmHostProgram &out) {
     out = PmHostProgram();
+    const int L = 32 / cpw;
     out.n_atoms = N;
     out.L = L;
+    out.cpw = cpw;
+    // atoms are stored as BYTE offsets of their first row inside a [3N][cpw] tile of doubles
+    const int AO = 3 * cpw * 8;
 
     // ------------------------------------------------------------------ stars -------------------------------------
     // neighbour sets from the angle list (centre = middle atom), chunked to 4
@@ -243,9 +247,9 @@ inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int
         it.cost = 13 * (int)st.n.size() + 8 * nb + 45 * na;
         it.rec = (int)star_items.size();
         star_items.push_back(it);
-        star_rec.push_back(st.c);
+        star_rec.push_back(st.c * AO);
         star_rec.push_back((int)st.n.size());
-        for (int k = 0; k < 4; ++k) star_rec.push_back(k < (int)st.n.size() ? st.n[k] : st.c);
+        for (int k = 0; k < 4; ++k) star_rec.push_back((k < (int)st.n.size() ? st.n[k] : st.c) * AO);
         for (int k = 0; k < 4; ++k) star_rec.push_back(st.bond[k]);
         for (int k = 0; k < 6; ++k) star_rec.push_back(st.angle[k]);
     }
@@ -320,12 +324,12 @@ inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int
         it.cost = 14 + 34 * (int)(ax.I.size() + ax.Lst.size()) + 30 * nterms;
         it.rec = (int)axis_items.size();
         axis_items.push_back(it);
-        axis_rec.push_back(ax.j);
-        axis_rec.push_back(ax.k);
+        axis_rec.push_back(ax.j * AO);
+        axis_rec.push_back(ax.k * AO);
         axis_rec.push_back((int)ax.I.size());
         axis_rec.push_back((int)ax.Lst.size());
-        for (int q = 0; q < 3; ++q) axis_rec.push_back(q < (int)ax.I.size() ? ax.I[q] : ax.j);
-        for (int q = 0; q < 3; ++q) axis_rec.push_back(q < (int)ax.Lst.size() ? ax.Lst[q] : ax.k);
+        for (int q = 0; q < 3; ++q) axis_rec.push_back((q < (int)ax.I.size() ? ax.I[q] : ax.j) * AO);
+        for (int q = 0; q < 3; ++q) axis_rec.push_back((q < (int)ax.Lst.size() ? ax.Lst[q] : ax.k) * AO);
         for (int q = 0; q < 9; ++q) {
             axis_rec.push_back((int)axis_terms.size() / 2);
             for (int t : ax.cell[q]) {
@@ -450,7 +454,7 @@ inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int
                     a = units[seg[l]].tile * PMH_IT + k;
                     if (a >= N) a = -1;
                 }
-                seg_tile.push_back(a);
+                seg_tile.push_back(a < 0 ? -1 : a * AO);
             }
         int n_e = 0;
         while (true) {
@@ -472,7 +476,7 @@ inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int
                     const Entry e = lists[l][pick];
                     lists[l].erase(lists[l].begin() + pick);
                     used.insert(e.j);
-                    entries.push_back(e.j | (e.mask << 16));
+                    entries.push_back((e.j * AO) | (e.mask << 28));
                     entries.push_back(e.base);
                 }
                 ++slots;
@@ -528,6 +532,7 @@ inline bool pm_build_program(int N, int L, int n_bonds, const int *bond_idx, int
 inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const int *bond_idx, int n_angles, const int *angle_idx,
                                int n_torsions, const int *tors_idx, const std::vector<int> &cls) {
     const int L = p.L;
+    const int AO = 3 * p.cpw * 8;
     const int *b = p.blob.data();
     std::vector<int> seen_b(n_bonds, 0), seen_a(n_angles, 0), seen_t(n_torsions, 0);
     static const int PA[6] = {0, 0, 0, 1, 1, 2}, PB[6] = {1, 2, 3, 2, 3, 3};
@@ -541,12 +546,12 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
             if (colour < 0 || colour >= n_col) return 17;
             std::set<int> &used = used_by_colour[colour];
             const int *r = b + p.off_star_rec + 16 * rec;
-            const int c = r[0], m = r[1];
-            if (m < 1 || m > 4) return 10;
+            const int c = r[0] / AO, m = r[1];
+            if (m < 1 || m > 4 || r[0] % AO) return 10;
             std::set<int> mine;
             mine.insert(c);
             for (int k = 0; k < m; ++k)
-                if (!mine.insert(r[2 + k]).second) return 11;
+                if (!mine.insert(r[2 + k] / AO).second) return 11;
             for (int a : mine)
                 if (!used.insert(a).second) return 12;  // cross-lane conflict
             for (int k = 0; k < 4; ++k) {
@@ -554,7 +559,7 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
                 if (bi < 0) continue;
                 if (k >= m || bi >= n_bonds) return 13;
                 const int x = bond_idx[2 * bi], y = bond_idx[2 * bi + 1];
-                if (!((x == c && y == r[2 + k]) || (y == c && x == r[2 + k]))) return 14;
+                if (!((x == c && y == r[2 + k] / AO) || (y == c && x == r[2 + k] / AO))) return 14;
                 seen_b[bi]++;
             }
             for (int q = 0; q < 6; ++q) {
@@ -562,7 +567,7 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
                 if (ai < 0) continue;
                 if (PB[q] >= m || ai >= n_angles) return 15;
                 const int x = angle_idx[3 * ai], cc = angle_idx[3 * ai + 1], y = angle_idx[3 * ai + 2];
-                const int na = r[2 + PA[q]], nb = r[2 + PB[q]];
+                const int na = r[2 + PA[q]] / AO, nb = r[2 + PB[q]] / AO;
                 if (cc != c || !((x == na && y == nb) || (x == nb && y == na))) return 16;
                 seen_a[ai]++;
             }
@@ -578,13 +583,13 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
             if (colour < 0 || colour >= n_col) return 27;
             std::set<int> &used = used_by_colour[colour];
             const int *r = b + p.off_axis_rec + 20 * rec;
-            const int j = r[0], k = r[1], nI = r[2], nL = r[3];
+            const int j = r[0] / AO, k = r[1] / AO, nI = r[2], nL = r[3];
             if (nI < 1 || nI > 3 || nL < 1 || nL > 3 || nI > max_ni) return 20;
             std::set<int> mine;
             mine.insert(j);
             mine.insert(k);
-            for (int q = 0; q < nI; ++q) mine.insert(r[4 + q]);
-            for (int q = 0; q < nL; ++q) mine.insert(r[7 + q]);
+            for (int q = 0; q < nI; ++q) mine.insert(r[4 + q] / AO);
+            for (int q = 0; q < nL; ++q) mine.insert(r[7 + q] / AO);
             for (int a : mine)
                 if (!used.insert(a).second) return 21;
             for (int cell = 0; cell < 9; ++cell) {
@@ -596,8 +601,8 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
                     const int ti = b[p.off_axis_terms + 2 * t], per = b[p.off_axis_terms + 2 * t + 1];
                     if (ti < 0 || ti >= n_torsions) return 24;
                     const int *x = tors_idx + 4 * ti;
-                    const bool fwd = x[0] == r[4 + pi] && x[1] == j && x[2] == k && x[3] == r[7 + pl];
-                    const bool rev = x[3] == r[4 + pi] && x[2] == j && x[1] == k && x[0] == r[7 + pl];
+                    const bool fwd = x[0] == r[4 + pi] / AO && x[1] == j && x[2] == k && x[3] == r[7 + pl] / AO;
+                    const bool rev = x[3] == r[4 + pi] / AO && x[2] == j && x[1] == k && x[0] == r[7 + pl] / AO;
                     if (!fwd && !rev) return 25;
                     if (per != b[p.off_tper + ti]) return 26;
                     seen_t[ti]++;
@@ -624,13 +629,14 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
             std::set<int> js;
             for (int l = 0; l < L; ++l) {
                 const int w0 = b[p.off_entries + 2 * (eoff + e * L + l)], base = b[p.off_entries + 2 * (eoff + e * L + l) + 1];
-                const int mask = w0 >> 16, j = w0 & 0xffff;
+                const int mask = (w0 >> 28) & 15, j = (w0 & 0x0fffffff) / AO;
                 if (!mask) continue;
                 if (!js.insert(j).second) return 41;  // two lanes updating the same j in one step
                 int q = base;
                 for (int k = 0; k < PMH_IT; ++k) {
                     if (!(mask & (1 << k))) continue;
-                    const int a = b[p.off_seg_tile + (s * L + l) * 4 + k];
+                    const int ao = b[p.off_seg_tile + (s * L + l) * 4 + k];
+                    const int a = ao < 0 ? -1 : ao / AO;
                     if (a < 0 || q >= p.n_pairs) return 42;
                     if (p.pair_map[3 * q] != a || p.pair_map[3 * q + 1] != j) return 43;
                     seen_p[q]++;
