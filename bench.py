@@ -60,39 +60,53 @@ def base_conformations(name, x0):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    """Streams nvidia-smi clocks / throttle reasons of one GPU (`-lms 20`) while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                     universal_newlines=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
 
     def __enter__(self):
-        self._thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, universal_newlines=True)
+            self._thread = threading.Thread(target=self._read, daemon=True)
+            self._thread.start()
+            time.sleep(0.15)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark(self):
+        """Only samples taken after this call count (start of the timed region)."""
+        self.t_start = time.perf_counter()
+
     def __exit__(self, *a):
-        self._stop.set()
-        self._thread.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = getattr(self, "t_start", 0.0)
+        for t, r in self.rows:
+            if t < t0 or len(r) < 7:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -107,36 +121,58 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(mm_system, x_base, term_type, target_seconds, threads=None):
-    """conformation E+F(+residual) evaluations / s of the CPU oracle on a bounded sample."""
-    from oracle import oracle as O
-    from paramol_b200.Utils.synthetic import perturbed_conformations
-    threads = threads or O.max_threads()
-    probe = perturbed_conformations(x_base, 2048, seed=99)
-    t0 = time.perf_counter()
-    E, F = O.energies_forces(mm_system, probe, n_threads=threads)
-    dt = time.perf_counter() - t0
-    n = int(min(max(2048, 2048 * target_seconds / max(dt, 1e-6)), 4_000_000))
-    X = perturbed_conformations(x_base, n, seed=100)
-    rng = np.random.default_rng(3)
-    t0 = time.perf_counter()
-    E, F = O.energies_forces(mm_system, X, n_threads=threads)
-    t_ef = time.perf_counter() - t0
-    Eref = E + rng.normal(0, 5, E.shape)
-    Fref = F + rng.normal(0, 50, F.shape)
-    w = O.conformation_weights("uniform", n)
-    t0 = time.perf_counter()
-    O.energy_property(Eref, E, w)
-    if term_type == "norm":
-        O.force_property(Fref, F, w, "norm")
-    else:
-        inv = O.force_inverse_covariance(Fref[:min(n, 4096)])
-        d = F - Fref
-        np.sum(w * np.einsum("sna,nab,snb->s", d, inv, d))
-    t_red = time.perf_counter() - t0
-    return dict(value=n / (t_ef + t_red), unit=METRIC, cores=int(threads), kind="port",
-                sample="%d perturbed conformations of the bench molecule, FP64 C oracle (OpenMP over conformations) "
-                       "+ numpy residual reductions; %.2f s E+F, %.2f s reductions" % (n, t_ef, t_red))
+class CpuOracleWorkload:
+    """
+    The CPU arm: the FP64 oracle port of the reference path (oracle/oracle.c: E+F of every conformation, OpenMP over
+    conformations = the analogue of the reference's fork pool; per-conformation force residual in C; the scalar
+    reductions of EnergyProperty / ForceProperty in numpy) on a bounded sample of the bench workload.
+    """
+
+    def __init__(self, mm_system, x_base, term_type, seconds_per_step, threads=None):
+        from oracle import oracle as O
+        from paramol_b200.Utils.synthetic import perturbed_conformations
+        self.O = O
+        self.mm = mm_system
+        self.threads = threads or O.max_threads()
+        probe = perturbed_conformations(x_base, 4096, seed=99)
+        O.energies_forces(mm_system, probe[:64], n_threads=self.threads)  # spin up the OpenMP team
+        t0 = time.perf_counter()
+        O.energies_forces(mm_system, probe, n_threads=self.threads)
+        dt = time.perf_counter() - t0
+        self.n = int(min(max(4096, 4096 * seconds_per_step / max(dt, 1e-6)), 2_000_000))
+        self.X = perturbed_conformations(x_base, self.n, seed=100)
+        rng = np.random.default_rng(3)
+        E, F = O.energies_forces(mm_system, self.X, n_threads=self.threads)
+        self.Eref = E + rng.normal(0, 5, E.shape)
+        self.Fref = F + rng.normal(0, 50, F.shape)
+        self.w = O.conformation_weights("uniform", self.n)
+        if term_type == "norm":
+            self.metric = np.eye(3)[None] / O.force_variance(self.Fref)[:, None, None]
+        else:
+            self.metric = O.force_inverse_covariance(self.Fref[:min(self.n, 2048)])
+        self.var_e = np.var(self.Eref)
+
+    def step(self):
+        """One objective evaluation over the sample; returns seconds."""
+        O = self.O
+        t0 = time.perf_counter()
+        E, F = O.energies_forces(self.mm, self.X, n_threads=self.threads)
+        res = O.force_residuals(F, self.Fref, self.metric, n_threads=self.threads)
+        d = self.Eref - E
+        value = np.sum(self.w * (d - np.mean(d)) ** 2) / self.var_e + np.sum(self.w * res) / (3 * self.mm.n_atoms)
+        self.last_value = float(value)
+        return time.perf_counter() - t0
+
+    def describe(self):
+        return ("%d perturbed conformations of the bench molecule per step; FP64 C oracle, OpenMP over conformations, %d threads"
+                % (self.n, self.threads))
+
+
+def cpu_oracle_rate(mm_system, x_base, term_type, target_seconds):
+    wl = CpuOracleWorkload(mm_system, x_base, term_type, max(1.0, target_seconds / 3.0))
+    wl.step()
+    times = [wl.step() for _ in range(2)]
+    return dict(value=wl.n / float(np.mean(times)), unit="conformations/s", cores=int(wl.threads), kind="port", sample=wl.describe())
 
 
 def run_reference(args):
@@ -144,26 +180,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
     mm, x0 = load_molecule(args.workload)
     xb = base_conformations(args.workload, x0)
-    threads = O.max_threads()
-    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    rates = []
-    for it in range(args.warmup + args.steps):
-        r = cpu_oracle_rate(mm, xb, args.term_type, per_step, threads)
-        if it >= args.warmup:
-            rates.append(r)
-    value = float(np.mean([r["value"] for r in rates]))
-    n_sample = rates[-1]["sample"]
+    n_steps = max(1, args.steps + args.warmup)
+    wl = CpuOracleWorkload(mm, xb, args.term_type, min(10.0, max(0.05, 100.0 / n_steps)))
+    for _ in range(args.warmup):
+        wl.step()
+    times = [wl.step() for _ in range(args.steps)]
+    value = wl.n * len(times) / float(np.sum(times))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "conformations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * (args.conformations * max(1, args.gpus)) / value, "higher_is_better": True,
+            "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "conformations_per_gpu": args.conformations, "term_type": args.term_type,
-                       "note": "CPU arm: each step is a bounded sample, rate extrapolates linearly in S (the reference is O(S)); "
-                               "ms_per_step is the time this rate implies for the full workload"},
-            "cpu_baseline": {"value": value, "unit": "conformations/s", "cores": threads, "kind": "port", "sample": n_sample},
+                       "conformations_per_cpu_step": wl.n,
+                       "note": "CPU arm: each step is one objective evaluation over a bounded sample of the workload; the "
+                               "reference is O(S), so conformations/s is size independent"},
+            "cpu_baseline": {"value": value, "unit": "conformations/s", "cores": int(wl.threads), "kind": "port",
+                             "sample": wl.describe()},
             "e2e": {"value": value, "unit": "conformations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -287,6 +321,7 @@ def run_ours(args):
         step()
     barrier()
     with ClockSampler(local_rank) as clocks:
+        clocks.mark()
         e_all0.record()
         for k in range(args.steps):
             step(k)
@@ -361,8 +396,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="aniline")
     ap.add_argument("--conformations", type=int, default=1 << 20)

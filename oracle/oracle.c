@@ -369,3 +369,31 @@ int pmo_resp_sums(int n_atoms, const double *x /*[N][3]*/, long n_grid, const do
     if (!inv_r) free(r);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-conformation force residual  r_s = sum_j dF_sj^T M_j dF_sj ,  dF = F_mm - F_ref
+ * (inner loops of ForceProperty.calculate_property, ParaMol/Objective_function/Properties/force_property.py:85-117;
+ *  M_j = inverse covariance of the QM forces for "components", I / var_j for "norm").  OpenMP over conformations.
+ * ---------------------------------------------------------------------------------------------- */
+int pmo_force_residuals(int n_atoms, long n_conf, const double *fmm, const double *fref, const double *metric /*[N][9]*/,
+                        double *out, int n_threads) {
+    const size_t stride = (size_t)3 * n_atoms;
+#ifdef _OPENMP
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+#endif
+    for (long s = 0; s < n_conf; ++s) {
+        const double *a = fmm + stride * s, *b = fref + stride * s;
+        double acc = 0.0;
+        for (int j = 0; j < n_atoms; ++j) {
+            const double d[3] = {a[3 * j] - b[3 * j], a[3 * j + 1] - b[3 * j + 1], a[3 * j + 2] - b[3 * j + 2]};
+            const double *m = metric + 9 * j;
+            double t[3];
+            for (int c = 0; c < 3; ++c) t[c] = d[0] * m[c] + d[1] * m[3 + c] + d[2] * m[6 + c];
+            acc += t[0] * d[0] + t[1] * d[1] + t[2] * d[2];
+        }
+        out[s] = acc;
+    }
+    (void)n_threads;
+    return 0;
+}

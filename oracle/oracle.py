@@ -64,6 +64,8 @@ def lib():
         L.pmo_max_threads.restype = ctypes.c_int
         L.pmo_internal_coordinates.restype = ctypes.c_int
         L.pmo_internal_coordinates.argtypes = [ctypes.c_int, ctypes.c_long, dp, ctypes.c_int, ip, ip, dp]
+        L.pmo_force_residuals.restype = ctypes.c_int
+        L.pmo_force_residuals.argtypes = [ctypes.c_int, ctypes.c_long, dp, dp, dp, dp, ctypes.c_int]
         L.pmo_resp_sums.restype = ctypes.c_int
         L.pmo_resp_sums.argtypes = [ctypes.c_int, dp, ctypes.c_long, dp, dp, dp, dp, dp]
         _LIB = L
@@ -269,6 +271,17 @@ def force_property(ref_forces, fmm, weights, term_type="components", wham_weight
         obj = np.sum(weights * wham_weights * obj)
         return obj / (3 * N)
     raise NotImplementedError(term_type)
+
+
+def force_residuals(fmm, ref_forces, metric, n_threads=1):
+    """r_s = sum_j dF^T M_j dF per conformation (C, OpenMP); metric [N,3,3] or [N,9]."""
+    fmm_a, fp = _d(fmm)
+    ref_a, rp = _d(ref_forces)
+    m_a, mp = _d(np.asarray(metric).reshape(-1, 9))
+    S, N, _ = fmm_a.shape
+    out = np.zeros(S)
+    lib().pmo_force_residuals(N, S, fp, rp, mp, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(n_threads))
+    return out
 
 
 def regularization(x, x0, prior_widths, method="L2", a=1.0, b=0.1):
