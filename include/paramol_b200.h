@@ -127,6 +127,32 @@ int pm_reduce_objective(const double *emm_dev, const double *fres_dev, const dou
                         const double *weights_dev, double d_shift, int n_vec, long n_conf,
                         double *partials_dev, double *scratch_dev, void *stream);
 
+/* ---- RESP (K5) ------------------------------------------------------------------------------------ */
+/* Normal-equation sums over conformations, the inverse distances R_m[j][i] = 1/|x_mj - g_mi| being generated on the fly:
+ *   out[0 .. N*N)      A = sum_m wt_m R_m R_m^T     (row-major, symmetric)
+ *   out[N*N .. N*N+N)  B = sum_m wt_m R_m V_m
+ *   out[N*N+N]         C = sum_m wt_m V_m . V_m
+ * coords [S][N][3], grid [S][G][3], vref [S][G], wt [S] or NULL (= 1), all device f64, any consistent length unit.
+ * Replaces RESP.calculate_inverse_distances / _calculate_a / _calculate_b (ParaMol/MM_engines/resp.py:99-134, 381-421,
+ * 463-496); with wt_m = w_m the same sums give the ESP objective of ESPProperty (esp_property.py:89-104) for ANY charge
+ * vector q as  C - 2 q.B + q^T A q.  scratch: pm_resp_scratch_doubles(N, S, G) doubles.  Acts on the current device. */
+long pm_resp_scratch_doubles(int n_atoms, long n_conf, int n_grid);
+int pm_resp_assemble(int n_atoms, const double *coords_dev, const double *grid_dev, const double *vref_dev,
+                     const double *wt_dev, long n_conf, int n_grid, double *out_dev, double *scratch_dev, void *stream);
+/* V_mm[m][i] = sum_j q_j / r_ij  (ParaMolSystem.get_esp_ensemble, ParaMol/System/system.py:356-382); charges [N]. */
+int pm_esp_potential(int n_atoms, const double *coords_dev, const double *grid_dev, const double *charges_dev,
+                     long n_conf, int n_grid, double *vmm_dev, void *stream);
+
+/* ---- LLS (K3) ------------------------------------------------------------------------------------- */
+/* Internal coordinates q[S][n_terms] with the conventions of ParaMol/Utils/geometry.py:4-107: kind 0 distance(a0,a1),
+ * 1 angle at a1 (arccos of the clipped cosine), 2 dihedral a0-a1-a2-a3 (atan2 form).  atoms [n_terms][4] int32 device. */
+int pm_lls_internal(int n_atoms, const double *coords_dev, long n_conf, int n_terms, const int *kind_dev,
+                    const int *atoms_dev, double *q_dev, void *stream);
+/* Design-matrix columns A[S][n_cols] (LinearLeastSquare._calculate_a, ParaMol/MM_engines/least_square.py:492-645):
+ * column c reads term col_term[c]; col_kind 0/1: 1/2 (q - p0)^2 ; col_kind 2: 1 + cos(per q - p0). */
+int pm_lls_columns(const double *q_dev, long n_conf, int n_terms, int n_cols, const int *col_term_dev,
+                   const int *col_kind_dev, const double *col_p0_dev, const int *col_per_dev, double *a_dev, void *stream);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Measured FMA-pipe peak of the current device: runs a register-only FMA kernel and returns FLOP/s
  * (2 flop per FMA) in *flops and the kernel time in *ms.  fp64 = 1: DFMA, 0: FFMA. */

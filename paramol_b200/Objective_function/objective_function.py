@@ -130,7 +130,7 @@ class ObjectiveFunction:
         self.parameter_space.update_systems(self.systems, parameters_values)
         if opt_mode:
             self._f_count += 1
-        if self._fused and not any(p.name == "ESP" for p in self.properties):
+        if self._fused:
             slots = [system.engine.current_slots()[None, :] for system in self.systems]
             objective_function = float(self._evaluate_fused(slots, np.asarray(parameters_values, dtype=np.float64)[None, :],
                                                            set_values=True)[0])
@@ -152,8 +152,6 @@ class ObjectiveFunction:
         is mutated except ``_f_count`` (+P).  NaN rows become 1e16.
         """
         X = np.atleast_2d(np.asarray(parameters_matrix, dtype=np.float64))
-        if any(p.name == "ESP" for p in self.properties):
-            raise NotImplementedError("f_batch does not evaluate the ESP property.")
         slots = self.parameter_space.update_systems_batch(self.systems, X)
         values = self._evaluate_fused(slots, X, set_values=False)
         self._f_count += X.shape[0]
@@ -333,6 +331,24 @@ class ObjectiveFunction:
                 if set_values:
                     f_prop.value = float(vals[0])
                 values += f_prop.weight * vals
+        esp_prop = self._prop("ESP")
+        if esp_prop is not None:
+            # quadratic form in the charges assembled once on the device (RESP.esp_objective); as in the reference the
+            # property value is the LAST system's (esp_property.py:104 overwrites instead of summing)
+            vals = np.zeros(n_vec)
+            for system in esp_prop.systems:
+                s_idx = self.systems.index(system)
+                if np.ndim(system.weights) == 0 or len(np.atleast_1d(system.weights)) != system.n_structures:
+                    system.compute_conformations_weights(temperature=self._weighting_temperature,
+                                                         weighting_method=self._weighting_method)
+                topo_n = system.n_atoms
+                off = 2 * len(system.engine.system.bond_idx) + 2 * len(system.engine.system.angle_idx) + \
+                    2 * len(system.engine.system.torsion_idx)
+                charges = np.asarray(slots_per_system[s_idx])[:, off:off + 3 * topo_n:3]
+                vals = np.atleast_1d(system.resp_engine.esp_objective(charges, system.weights))
+            if set_values:
+                esp_prop.value = float(vals[0])
+            values = values + esp_prop.weight * vals
         if r_prop is not None:
             if set_values:
                 reg = np.atleast_1d(r_prop.calculate_property(X[0]))

@@ -664,6 +664,7 @@ static int pm_fail(const std::string &msg) {
     g_err = msg;
     return 1;
 }
+int pm_fail_msg(const std::string &msg) { return pm_fail(msg); }  // for the other translation units
 #define PM_CUDA(call)                                                                              \
     do {                                                                                           \
         cudaError_t _e = (call);                                                                   \

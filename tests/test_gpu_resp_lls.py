@@ -1,0 +1,202 @@
+"""
+GPU parity of the two linear fitting paths (run with ``-m gpu``).
+
+RESP: the reference's own test body (ParaMol/Tests/Tasks/test_resp.py:78-151) -- explicit solver without restraint,
+with L2 (a = 0.5) and with hyperbolic (a = 0.001, b = 0.1) restraints -- against the three golden charge vectors
+(tolerance 1e-4 as in the reference), plus the assembled sums against the CPU oracle on seeded multi-conformation input.
+LLS: the reference has no test for this path ("parity unpinned" at the reference level); the device design matrix and the
+fitted parameters are compared with a numpy restatement of ParaMol/MM_engines/least_square.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from paramol_b200.MM_engines.b200_engine import B200Engine
+from paramol_b200.MM_engines.resp import RESP
+from paramol_b200.System.system import ParaMolSystem
+from paramol_b200.Parameter_space.parameter_space import ParameterSpace
+
+
+@pytest.fixture()
+def kwargs_dict(golden_dir):
+    return {"topology_format": "AMBER", "crd_format": "AMBER",
+            "top_file": os.path.join(golden_dir, "aniline.prmtop"), "crd_file": os.path.join(golden_dir, "aniline.inpcrd")}
+
+
+def _aniline_esp(kwargs_dict, golden_dir):
+    engine = B200Engine(True, **kwargs_dict)
+    aniline = ParaMolSystem(name="aniline", engine=engine, n_atoms=14)
+    d = np.load(os.path.join(golden_dir, "aniline_esp.npz"))
+    aniline.ref_coordinates, aniline.ref_esp_grid, aniline.ref_esp = [d["conformation"]], [d["grid"]], [d["esp"]]
+    aniline.ref_energies = [float(d["energy"])]
+    assert aniline.ref_esp_grid[0].shape == (39946, 3) and len(aniline.ref_esp[0]) == 39946
+    aniline.n_structures = len(aniline.ref_coordinates)
+    return aniline
+
+
+def _fit(aniline, include_reg, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01):
+    # RESPFitting.run_task(solver="explicit"), ParaMol/Tasks/resp_fitting.py:112-139
+    aniline.engine.set_non_bonded_parameters_to_zero()
+    aniline.force_field.create_force_field(opt_charges=True)
+    parameter_space = ParameterSpace()
+    parameter_space.get_optimizable_parameters([aniline], symmetry_constrained=False)
+    aniline.resp_engine = RESP(0, include_reg, method=method, scaling_factor=scaling_factor, hyperbolic_beta=hyperbolic_beta,
+                               weighting_method="uniform", weighting_temperature=300.0)
+    aniline.resp_engine.set_initial_charges(aniline.force_field.force_field)
+    aniline.resp_engine.set_charges(aniline.force_field.force_field)
+    aniline.resp_engine.calculate_inverse_distances(aniline)
+    aniline.resp_engine.set_symmetry_constraints(aniline, True)
+    aniline.resp_engine.set_not_optimize_atoms(aniline)
+    charges = aniline.resp_engine.fit_resp_charges_explicitly(aniline, 1e-8, 1000)
+    charges_to_update = [charges[i] for i in range(len(charges)) if i not in aniline.resp_engine._not_optimized.keys()]
+    parameter_space.update_systems([aniline], charges_to_update, symmetry_constrained=False)
+    return np.asarray(parameter_space.optimizable_parameters_values)[:14]
+
+
+def test_resp_explicit_goldens(kwargs_dict, golden_dir, goldens):
+    aniline = _aniline_esp(kwargs_dict, golden_dir)
+    charges = _fit(aniline, False)
+    assert np.abs(charges - np.asarray(goldens["test_resp.py::test_resp::charges_to_compare"])).max() < 1e-4
+    assert abs(charges.sum()) < 1e-10
+    charges = _fit(aniline, True, "L2", 0.5)
+    assert np.abs(charges - np.asarray(goldens["test_resp.py::test_resp::charges_to_compare#1"])).max() < 1e-4
+    charges = _fit(aniline, True, "hyperbolic", 0.001, 0.1)
+    assert np.abs(charges - np.asarray(goldens["test_resp.py::test_resp::charges_to_compare#2"])).max() < 1e-4
+
+
+def test_resp_sums_potential_and_objective_vs_oracle(golden_dir):
+    from oracle import oracle as O
+    from paramol_b200.Utils.synthetic import make_ligand
+    from paramol_b200.Objective_function.Properties.esp_property import ESPProperty
+    rng = np.random.default_rng(11)
+    mm, x0 = make_ligand(33)
+    n_conf, sizes = 7, [120, 97, 128, 33, 128, 64, 1]
+    X = [(x0 + rng.normal(0, 0.01, x0.shape)) * 18.897 for _ in range(n_conf)]
+    grids, vrefs = [], []
+    q_true = mm.particle_par[:, 0]
+    for m in range(n_conf):
+        g = rng.normal(0, 1.0, (sizes[m], 3))
+        g = X[m][rng.integers(0, 33, sizes[m])] + 4.0 * g / np.linalg.norm(g, axis=1)[:, None]
+        grids.append(g)
+        vrefs.append((1.0 / np.linalg.norm(X[m][:, None, :] - g[None], axis=2)).T @ q_true + rng.normal(0, 1e-3, sizes[m]))
+    engine = B200Engine(system=mm)
+    system = ParaMolSystem("lig33", engine, 33, ref_coordinates=X, ref_esp=vrefs, ref_esp_grid=grids)
+    system.force_field.create_force_field(opt_charges=True)
+    resp = RESP(0, False, "L2", 1.0, 0.01, "uniform", 300.0)
+    system.resp_engine = resp
+    resp.set_charges(system.force_field.force_field)
+    resp.calculate_inverse_distances(system)
+    w = rng.uniform(0.1, 1.0, n_conf)
+    A, B, C = resp._assemble(w)
+    A_want, B_want, C_want = np.zeros((33, 33)), np.zeros(33), 0.0
+    for m in range(n_conf):
+        inv_r, Am, Bm = O.resp_sums(X[m], grids[m], vrefs[m])
+        A_want += w[m] * Am
+        B_want += w[m] * Bm
+        C_want += w[m] * float(vrefs[m] @ vrefs[m])
+        assert np.abs(resp.inv_rij[m] - inv_r).max() < 1e-13
+    assert np.abs(A - A_want).max() <= 1e-12 * np.abs(A_want).max()
+    assert np.abs(B - B_want).max() <= 1e-12 * np.abs(B_want).max()
+    assert abs(C - C_want) <= 1e-12 * abs(C_want)
+    # potential and ESP objective, against the oracle's restatement of system.py:356-382 / esp_property.py:89-104
+    esp = system.get_esp_ensemble()
+    want = O.esp_ensemble(resp.charges, O.inverse_distances(X, grids))
+    for a, b in zip(esp, want):
+        assert np.abs(a - b).max() < 1e-12
+    system.weights = w
+    val = resp.esp_objective(np.asarray(resp.charges), w)
+    assert abs(val - O.esp_property(vrefs, want, w)) <= 1e-8 * abs(val)
+    prop = ESPProperty([system], weight=1.0)
+    prop.calculate_variance()
+    assert abs(prop.calculate_property([esp]) - val) <= 1e-8 * abs(val)
+
+
+def _numpy_lls(system, parameter_space, weights, include_reg, a_reg, alpha_bond=0.05):
+    """numpy restatement of LinearLeastSquare.fit_parameters_lls (least_square.py:68-146) with the oracle's geometry."""
+    from oracle import oracle as O
+    X = np.asarray(system.ref_coordinates)
+    cols, p0, keys, init, symm = [], [], [], [], []
+    for parameter in parameter_space.optimizable_parameters:
+        t = parameter.ff_term
+        if parameter.param_key == "bond_k":
+            q = O.internal_coordinates(X, [0], [t.atoms + [0, 0]])[:, 0]
+            eq = t.parameters["bond_eq"]
+            centres = [eq.value * (1 - alpha_bond), eq.value * (1 + alpha_bond)] if eq.optimize else [eq.value]
+            for tag, c in zip(("_x", "_y"), centres):
+                cols.append(0.5 * (q - c) ** 2); p0.append(c); keys.append("bond_k"); init.append(parameter.value)
+                symm.append(parameter.symmetry_group + (tag if eq.optimize else ""))
+        elif parameter.param_key == "angle_k":
+            q = O.internal_coordinates(X, [1], [t.atoms + [0]])[:, 0]
+            eq = t.parameters["angle_eq"]
+            centres = [q.min(), q.max()] if eq.optimize else [eq.value]
+            for tag, c in zip(("_x", "_y"), centres):
+                cols.append(0.5 * (q - c) ** 2); p0.append(c); keys.append("angle_k"); init.append(parameter.value)
+                symm.append(parameter.symmetry_group + (tag if eq.optimize else ""))
+        elif parameter.param_key == "torsion_k":
+            q = O.internal_coordinates(X, [2], [t.atoms])[:, 0]
+            ph = t.parameters["torsion_phase"]
+            n = t.parameters["torsion_periodicity"].value
+            centres = [-np.pi / 4, np.pi / 4] if ph.optimize else [ph.value]
+            for tag, c in zip(("_x", "_y"), centres):
+                cols.append(1 + np.cos(n * q - c)); p0.append(c); keys.append("torsion_k"); init.append(parameter.value)
+                symm.append(parameter.symmetry_group + (tag if ph.optimize else ""))
+    A = np.stack(cols, axis=1)
+    A = A - A.mean(axis=0)
+    return A, np.asarray(p0), keys, np.asarray(init), symm
+
+
+def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
+    from oracle import oracle as O
+    from paramol_b200.MM_engines.least_square import LinearLeastSquare
+    from paramol_b200.Utils.synthetic import perturbed_conformations
+    from paramol_b200.Utils.netcdf_lite import read_paramol_data
+    X10 = read_paramol_data(os.path.join(golden_dir, "aniline_10_struct.nc"))[0]
+    for eq_opt in (False, True):
+        engine = B200Engine(True, **kwargs_dict)
+        system = ParaMolSystem("aniline", engine, 14)
+        system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
+        if not eq_opt:
+            for force in ("HarmonicBondForce", "HarmonicAngleForce", "PeriodicTorsionForce"):
+                for term in system.force_field.force_field[force][0]:
+                    for key, p in term.parameters.items():
+                        if key in ("bond_eq", "angle_eq", "torsion_phase"):
+                            p.optimize = 0
+            system.force_field.create_force_field_optimizable()
+        X = perturbed_conformations(X10, 600, sigma=0.004, seed=5)
+        E, _ = O.energies_forces(engine.system, X)
+        rng = np.random.default_rng(1)
+        system.ref_coordinates, system.ref_energies = X, E + rng.normal(0, 2.0, len(E)) - 43000.0
+        system.n_structures = len(X)
+        ps = ParameterSpace()
+        ps.get_optimizable_parameters([system], symmetry_constrained=False)
+        lls = LinearLeastSquare(ps, True, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01, weighting_method="uniform",
+                                weighting_temperature=300.0)
+        A_want, p0, keys, init, symm = _numpy_lls(system, ps, None, True, 1.0)
+        A_dev = lls._calculate_a(system, 0.05, 0.05)
+        assert A_dev.shape == A_want.shape
+        assert np.abs(A_dev - A_want).max() <= 1e-10 * max(1.0, np.abs(A_want).max())
+        assert np.allclose(lls._p0, p0, rtol=0, atol=1e-12) and lls._param_keys_list == keys and lls._param_symmetries_list == symm
+        # full fit against the reference-structured numpy pipeline (lstsq on the full stacked matrix)
+        x_before = np.asarray(ps.optimizable_parameters_values).copy()
+        B = np.asarray(system.ref_energies) - lls._energies_with_zeroed_parameters(system)
+        B = B - B.mean()
+        w = np.ones(len(X)) / len(X)
+        var = np.var(system.ref_energies)
+        sc_dict, _ = ps.calculate_scaling_constants("default")
+        sc = np.asarray([sc_dict[k] for k in keys])
+        pw_dict, _ = ps.calculate_prior_widths("default")
+        pw = np.asarray([pw_dict[k] for k in keys])
+        Aw = A_want * np.sqrt(w)[:, None] / np.sqrt(var) / sc[None, :]
+        Bw = B * np.sqrt(w) / np.sqrt(var)
+        alpha = 1.0 / sc
+        Afull = np.vstack([Aw, np.identity(len(sc)) / pw[None, :] * alpha[None, :]])
+        Bfull = np.concatenate([Bw, alpha * init])
+        want = np.linalg.lstsq(Afull, Bfull, rcond=None)[0] / sc
+        assert np.allclose(np.asarray(ps.optimizable_parameters_values), x_before)
+        fitted = lls.fit_parameters_lls([system])
+        got = lls._parameters
+        assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max(), np.abs(got - want).max()
+        assert len(fitted) == len(x_before)
