@@ -259,6 +259,40 @@ class ObjectiveFunction:
             w = w * st["wham_scalar"]
         return w.contiguous()
 
+    def assemble_from_partials(self, per_system, w_scales, set_values=False):
+        """
+        ENERGY and FORCE contributions, numpy [P], from the ALLREDUCED partial sums of every system
+        (``per_system[s]`` = float64 [P, 8] as written by ``pm_reduce_objective``, or None):
+            ENERGY_s = ([2] - 2 m [1] + m^2 [3]) / var_s(E_ref),  m = [0] / [5]      (energy_property.py:99-108)
+            FORCE_s  = [4] / (3 N_s)                                                (force_property.py:85-117)
+        ``w_scales[s]`` folds the normalisation of uniform weights (device weights are 1 in that case).
+        """
+        e_prop, f_prop = self._prop("ENERGY"), self._prop("FORCE")
+        n_vec = next(hp.shape[0] for hp in per_system if hp is not None)
+        values = np.zeros(n_vec)
+        for hp, scale in zip(per_system, w_scales):
+            if hp is not None and scale != 1.0:
+                hp[:, 1:5] *= scale
+        if e_prop is not None:
+            vals = np.zeros(n_vec)
+            for system in e_prop.systems:
+                hp = per_system[self.systems.index(system)]
+                var = e_prop.variance[e_prop.systems.index(system)]
+                m = hp[:, 0] / hp[:, 5]
+                vals += (hp[:, 2] - 2.0 * m * hp[:, 1] + m * m * hp[:, 3]) / var
+            if set_values:
+                e_prop.value = float(vals[0])
+            values += e_prop.weight * vals
+        if f_prop is not None:
+            vals = np.zeros(n_vec)
+            for system in f_prop.systems:
+                hp = per_system[self.systems.index(system)]
+                vals += hp[:, 4] / (3 * system.n_atoms)
+            if set_values:
+                f_prop.value = float(vals[0])
+            values += f_prop.weight * vals
+        return values
+
     def _evaluate_fused(self, slots_per_system, X, set_values):
         """
         slots_per_system: list over ``self.systems`` of float64 [P, n_slots]; X [P, P_opt] for the regularisation.
@@ -308,29 +342,7 @@ class ObjectiveFunction:
                 else:
                     per_system.append(host_partials[k] * 1.0)
                     k += 1
-            # fold the uniform-weight normalisation (device weights were 1)
-            for st, hp in zip(states, per_system):
-                if hp is not None and st["w_scale"] != 1.0:
-                    hp[:, 1:5] *= st["w_scale"]
-            if e_prop is not None:
-                vals = np.zeros(n_vec)
-                for system in e_prop.systems:
-                    s_idx = self.systems.index(system)
-                    hp = per_system[s_idx]
-                    var = e_prop.variance[e_prop.systems.index(system)]
-                    m = hp[:, 0] / hp[:, 5]
-                    vals += (hp[:, 2] - 2.0 * m * hp[:, 1] + m * m * hp[:, 3]) / var
-                if set_values:
-                    e_prop.value = float(vals[0])
-                values += e_prop.weight * vals
-            if f_prop is not None:
-                vals = np.zeros(n_vec)
-                for system in f_prop.systems:
-                    hp = per_system[self.systems.index(system)]
-                    vals += hp[:, 4] / (3 * system.n_atoms)
-                if set_values:
-                    f_prop.value = float(vals[0])
-                values += f_prop.weight * vals
+            values = self.assemble_from_partials(per_system, [st["w_scale"] for st in states], set_values)
         esp_prop = self._prop("ESP")
         if esp_prop is not None:
             # quadratic form in the charges assembled once on the device (RESP.esp_objective); as in the reference the
