@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libparamol_b200.so")
+LIB_PATH = os.environ.get("PARAMOL_B200_LIB") or os.path.join(_HERE, "libparamol_b200.so")  # env: A/B builds only
 _LIB = None
 
 c_int_p = ctypes.POINTER(ctypes.c_int)

@@ -392,8 +392,9 @@ __global__ void __launch_bounds__(PM_MAX_WARPS * 32, 1)
                                 for (int t = t0; t < t1; ++t) {
                                     const int2 term = s_axis_terms[t];  // (torsion index, periodicity)
                                     const double2 kk = s_ptors[2 * term.x], cs = s_ptors[2 * term.x + 1];  // (k, k n), (cos, sin) delta
-                                    double cn = 1.0, sn = 0.0;
-                                    for (int mm = 0; mm < term.y; ++mm) {
+                                    // (cos, sin)(n phi) by the angle-addition recurrence, started at n = 1
+                                    double cn = term.y > 0 ? cphi : 1.0, sn = term.y > 0 ? sphi : 0.0;
+                                    for (int mm = 1; mm < term.y; ++mm) {
                                         const double c_new = fma(cn, cphi, -(sn * sphi));
                                         sn = fma(sn, cphi, cn * sphi);
                                         cn = c_new;
