@@ -10,7 +10,9 @@
 #include <stdint.h>
 
 #define PM_IT 4          // atoms of an i-tile kept in registers in the pair loop
+#ifndef PM_MAX_WARPS
 #define PM_MAX_WARPS 16  // warps per CTA (1 persistent CTA per SM)
+#endif
 #define PM_ACOS_N 256    // intervals of the (cos, sin) table behind pm_acos_cs
 #define PM_PI 3.14159265358979323846
 
