@@ -171,3 +171,32 @@ def test_nan_objective_becomes_1e16(kwargs_dict, golden_dir):
     x[1] = np.nan
     assert of.f(x) == 1e16
     assert of.f_batch(np.stack([x, np.asarray(x0)]))[0] == 1e16
+
+
+def test_optimizers_drive_the_device_objective(kwargs_dict, golden_dir):
+    """Monte Carlo and finite-difference gradient descent on the real objective: f_batch launches, objective decreases."""
+    from paramol_b200.Optimizers.monte_carlo import MonteCarlo
+    from paramol_b200.Optimizers.gradient_descent import GradientDescent
+    system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False, opt_bonds=False, opt_angles=False)
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    ps.calculate_scaling_constants("default")
+    ps.jacobi_preconditioning()
+    xs0 = np.asarray(ps.optimizable_parameters_values_scaled).copy()
+    e_prop = EnergyProperty([system])
+    e_prop.calculate_variance()
+    of = ObjectiveFunction(None, ps, [e_prop], [system], **dict(objective_function_settings, checkpoint_freq=10 ** 9))
+    f0 = of.f(xs0.copy())
+    np.random.seed(3)
+    mc = MonteCarlo(n_blocks=2, max_iter=3, f_tol=1e-14, avg_acceptance_rate=0.25, batch_size=16)
+    x_mc = mc.run_optimization(of.f, list(xs0))
+    f_mc = of.f(np.asarray(x_mc))
+    assert f_mc <= f0 and mc.n_launches < 2 * len(xs0)
+    gd = GradientDescent(max_iter=3, derivative_calculation="always", derivative_type="1-point", g_tol=1e9, f_tol=1e-16,
+                         dx=1e-4, derivative_h=1e-3)
+    x_gd = gd.run_optimization(of.f, xs0.copy())
+    assert of.f(np.asarray(x_gd)) <= f0 and gd.n_launches == 3
+    # f_batch on the gradient stencil equals row-by-row f (1e-12)
+    X = np.repeat(xs0[None], 5, axis=0)
+    X[np.arange(5), np.arange(5)] += 1e-3
+    assert np.allclose(of.f_batch(X), [of.f(x.copy()) for x in X], rtol=1e-12, atol=0)
