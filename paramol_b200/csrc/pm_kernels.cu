@@ -43,6 +43,8 @@ struct PmProg {
     int n_slots;
     int soff_bond, soff_angle, soff_tors, soff_part, soff_exc;
     double k_coul;
+    double rf_krf, rf_crf, rf_cut2;  // reaction field (CutoffNonPeriodic); pair_stride == 4 when active
+    int pair_stride;
     const int *ints;         // device blob
     const double *metric;    // device [9N]
     const int *pair_map;     // device [n_pairs][3] = (i, j, exception or -1)
@@ -83,16 +85,43 @@ __global__ void pm_prepare_kernel(PmProg g, const double *__restrict__ slots, do
             eps = pe[2];
         }
         const double s2 = sig * sig, s6 = s2 * s2 * s2;
-        double *o = d + g.doff_pair + 3 * q;
+        double *o = d + g.doff_pair + g.pair_stride * q;
         o[0] = 4.0 * eps * s6 * s6;  // c12
         o[1] = 4.0 * eps * s6;       // c6
         o[2] = g.k_coul * qq;        // Coulomb product
+        if (g.pair_stride == 4) o[3] = e < 0 ? 1.0 : 0.0;  // 1: plain pair (cutoff + reaction field apply), 0: exception
     }
 }
 
 // =============================================================================================
 // K1: energies (+ forces + force residual) of every conformation, for every parameter vector
 // =============================================================================================
+// CutoffNonPeriodic with reaction field (OpenMM ReferenceLJCoulombIxn with cutoff, the system of the reference's
+// Tests/aniline.xml): plain pairs beyond the cutoff vanish, inside it the Coulomb term is K qq (1/r + k_rf r^2 - c_rf);
+// exceptions keep the plain 1/r form.  pp = (c12, c6, K qq, plain flag).
+template <bool WITH_F>
+__device__ __forceinline__ void pm_pair_rf(const pm_d3 xi, const pm_d3 xj, const double *__restrict__ pp, const double krf,
+                                           const double crf, const double cut2, double &e_nb, pm_d3 &fi, pm_d3 &fj) {
+    const pm_d3 d = pm_sub(xi, xj);
+    const double r2 = pm_dot(d, d);
+    const double plain = pp[3];
+    if (plain != 0.0 && r2 >= cut2) return;
+    const double rinv = pm_rsqrt(r2);
+    const double u = rinv * rinv;
+    const double u3 = u * u * u;
+    const double c12 = pp[0], c6 = pp[1], cq = pp[2];
+    const double a = c12 * u3;
+    const double b = a - c6;
+    const double kr2 = plain * krf * r2;
+    e_nb = fma(b, u3, e_nb);
+    e_nb = fma(cq, rinv + kr2 - plain * crf, e_nb);
+    if (WITH_F) {
+        const double g = fma(6.0 * u3, a + b, cq * (rinv - 2.0 * kr2)) * u;
+        pm_axpy(fi, g, d);
+        pm_axpy(fj, g, d);
+    }
+}
+
 template <bool WITH_F>
 __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const double *__restrict__ pp, double &e_nb, pm_d3 &fi,
                                         pm_d3 &fj) {
@@ -129,7 +158,7 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
 
 // MAXW = warps per CTA the variant is compiled for: 16 (128 registers per thread) or 12 (168 registers, no spills).
 // Measured on B200: when shared memory admits at most 12 warps anyway, the 168-register variant is 5-10 % faster.
-template <int CPW, bool WITH_F, int MAXW>
+template <int CPW, bool WITH_F, int MAXW, bool RF = false>
 __global__ void __launch_bounds__(MAXW * 32, 1)
     pm_ef_kernel(PmProg g, const double *__restrict__ derived, int n_vec, const double *__restrict__ xt,
                  const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm,
@@ -462,10 +491,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     const int mask = (en.x >> 28) & 15;
                     if (mask) {
                         const int j = en.x & 0x0fffffff;  // byte offset of atom j
-                        const double *pp = s_ppair + 3 * en.y;
+                        const double *pp = s_ppair + (RF ? 4 : 3) * en.y;
                         const pm_d3 xj = pm_ldo<CPW>(xc_base, j);
                         pm_d3 fj{0.0, 0.0, 0.0};
-                        if (mask == 15) {
+                        if (RF) {
+#pragma unroll
+                            for (int k = 0; k < PM_IT; ++k) {
+                                if (mask & (1 << k)) {
+                                    pm_pair_rf<WITH_F>(xi[k], xj, pp, g.rf_krf, g.rf_crf, g.rf_cut2, e_nb, acc[k], fj);
+                                    pp += 4;
+                                }
+                            }
+                        } else if (mask == 15) {
                             // all four pairs interact: one branch-free block, four independent dependency chains
 #pragma unroll
                             for (int k = 0; k < PM_IT; ++k) pm_pair<WITH_F>(xi[k], xj, pp + 3 * k, e_nb, acc[k], fj);
@@ -686,6 +723,7 @@ struct pm_handle_s {
     double2 *d_acos;
     int warps[2];  // [with_forces]
     int maxw[2];   // kernel variant (registers per thread) per [with_forces]
+    int rf;        // reaction-field variant
     size_t smem_total[2];
 };
 
@@ -701,7 +739,8 @@ static pm_ef_fn pm_pick_kernel_w(int cpw, int wf) {
         default: return nullptr;
     }
 }
-static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw) {
+static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw, int rf = 0) {
+    if (rf) return wf ? pm_ef_kernel<32, true, 12, true> : pm_ef_kernel<32, false, 12, true>;  // CPW 32 only
     return maxw <= 12 ? pm_pick_kernel_w<12>(cpw, wf) : pm_pick_kernel_w<16>(cpw, wf);
 }
 
@@ -785,7 +824,8 @@ extern "C" int pm_program_check(const pm_topology *t, int cpw, int *stats10) {
 extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     if (!t || !out) return pm_fail("pm_create: null argument");
     if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_create: n_atoms out of range");
-    if (t->nonbonded_method != 0) return pm_fail("pm_create: only NoCutoff is implemented on the device path");
+    if (t->nonbonded_method != 0 && t->nonbonded_method != 1) return pm_fail("pm_create: unknown nonbonded method");
+    const int rf = t->nonbonded_method == 1;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -809,6 +849,7 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
         cpw = atoi(env);
         if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: PM_CPW must be 32, 16, 8 or 4");
     }
+    if (rf) cpw = 32;  // the reaction-field variant is instantiated for one lane per conformation only
     PmHostProgram host;
     const int n_derived_est = 2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * (N * (N - 1) / 2) + 2;
     if (!cpw) {
@@ -843,6 +884,7 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     h->d_pair_map = nullptr;
     h->d_acos = nullptr;
     h->host = host;
+    h->rf = rf;
     PmProg &g = h->prog;
     g.n_atoms = N;
     g.n_bonds = t->n_bonds;
@@ -867,12 +909,19 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     g.off_entries = host.off_entries;
     g.off_tper = host.off_tper;
     g.k_coul = t->one_4pi_eps0;
+    g.pair_stride = rf ? 4 : 3;
+    if (rf) {
+        const double rc = t->cutoff, ed = t->rf_dielectric;
+        g.rf_krf = pow(rc, -3.0) * (ed - 1.0) / (2.0 * ed + 1.0);
+        g.rf_crf = (1.0 / rc) * (3.0 * ed) / (2.0 * ed + 1.0);
+        g.rf_cut2 = rc * rc;
+    }
 
     g.doff_bond = 0;
     g.doff_angle = g.doff_bond + 2 * g.n_bonds;
     g.doff_tors = g.doff_angle + 2 * g.n_angles;
     g.doff_pair = g.doff_tors + 4 * g.n_torsions;
-    g.n_derived = g.doff_pair + 3 * g.n_pairs;
+    g.n_derived = g.doff_pair + g.pair_stride * g.n_pairs;
     g.n_derived = (g.n_derived + 1) & ~1;
 
     g.soff_bond = 0;
@@ -925,7 +974,8 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
         pm_plan(g.n_int, g.n_derived, N, cpw, max_smem, wf, &sh, &pw, &w);
         const char *envw = getenv("PM_WARPS");
         if (envw && *envw && atoi(envw) > 0 && atoi(envw) < w) w = atoi(envw);
-        h->maxw[wf] = w <= 12 ? 12 : 16;
+        h->maxw[wf] = (w <= 12 || rf) ? 12 : 16;
+        if (rf && w > 12) w = 12;
         h->warps[wf] = w;
         h->smem_total[wf] = w > 0 ? sh + pw * (size_t)w : 0;
     }
@@ -933,8 +983,8 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
         cleanup();
         return pm_fail("pm_create: molecule too large for the shared-memory tiles of this kernel generation");
     }
-    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 1, h->maxw[1]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
-    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 0, h->maxw[0]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 1, h->maxw[1], rf), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 0, h->maxw[0], rf), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
     *out = h;
     return 0;
 }
@@ -1035,7 +1085,7 @@ extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const 
         grid = (n_tiles + warps - 1) / warps;
         if (grid < 1) grid = 1;
     }
-    pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf]);
+    pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf], h->rf);
     fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(h->prog, derived_dev, n_vec, coord_tiles_dev,
                                                                                 fref_tiles_dev, n_conf, n_tiles, emm_dev,
                                                                                 wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr);

@@ -200,3 +200,26 @@ def test_optimizers_drive_the_device_objective(kwargs_dict, golden_dir):
     X = np.repeat(xs0[None], 5, axis=0)
     X[np.arange(5), np.arange(5)] += 1e-3
     assert np.allclose(of.f_batch(X), [of.f(x.copy()) for x in X], rtol=1e-12, atol=0)
+
+
+def test_openmm_wrapper_goldens_reaction_field(kwargs_dict, golden_dir, goldens):
+    """
+    Tests/MM_engines/test_openmm_wrapper.py:43-72: because an earlier test of that class mutates the shared kwargs, the
+    reference's single-structure energy/force goldens are evaluated on the serialized aniline.xml system
+    (CutoffNonPeriodic, reaction field eps = 78.3, r_c = 1.2 nm).  Same here, on the device.
+    """
+    from paramol_b200.Utils.amber import read_inpcrd
+    kw = dict(kwargs_dict, xml_file=os.path.join(golden_dir, "aniline.xml"))
+    engine = B200Engine(True, **kw)
+    assert engine.system.nonbonded_method == "CutoffNonPeriodic"
+    x = read_inpcrd(kwargs_dict["crd_file"])
+    e = engine.get_potential_energy(x)
+    assert abs(e - goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_potential_energy::energy_to_compare"]) < 1e-8
+    f = engine.get_forces(x)
+    gold = np.asarray(goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_forces::forces_to_compare"])
+    assert np.abs(f - gold).max() < 1e-4  # the golden table is printed to 8 significant digits
+    from oracle import oracle as O
+    E, F = O.energies_forces(engine.system, x)
+    assert abs(e - E[0]) < 1e-10 and np.abs(f - F[0]).max() < 1e-9
+    assert engine.get_atom_list() == goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_atom_list::atom_list_to_compare"]
+    assert engine.get_atomic_numbers() == goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_atomic_numbers::atomic_numbers_to_compare"]
