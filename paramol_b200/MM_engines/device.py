@@ -28,9 +28,19 @@ def _iptr(a):
     return a.ctypes.data_as(c_int_p)
 
 
+_STREAM_CACHE = {}
+
+
 def _stream_ptr(device):
+    """cudaStream_t of torch's current stream on ``device`` (cached while the current stream object is unchanged)."""
     torch = _torch()
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    stream = torch.cuda.current_stream(device)
+    key = (str(device), stream.cuda_stream)
+    ptr = _STREAM_CACHE.get(key)
+    if ptr is None:
+        ptr = ctypes.c_void_p(stream.cuda_stream)
+        _STREAM_CACHE[key] = ptr
+    return ptr
 
 
 class DeviceTopology:

@@ -331,7 +331,7 @@ class ObjectiveFunction:
         live = [p for p in partial_list if p is not None]
         values = np.zeros(n_vec)
         if live:
-            stacked = torch.stack(live, dim=0)           # [n_live, P, 8]
+            stacked = live[0].unsqueeze(0) if len(live) == 1 else torch.stack(live, dim=0)  # [n_live, P, 8]
             _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective
             host_partials = stacked.cpu().numpy()
             k = 0

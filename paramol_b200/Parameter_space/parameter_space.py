@@ -205,7 +205,9 @@ class ParameterSpace:
                                     per_system[s_idx]["src"].append(symm_groups[parameter.symmetry_group][parameter.param_key])
             per_system[s_idx]["dst"] = np.asarray(per_system[s_idx]["dst"], dtype=np.int64)
             per_system[s_idx]["src"] = np.asarray(per_system[s_idx]["src"], dtype=np.int64)
-        self._scatter = dict(key=key, per_system=per_system)
+        by_system_idx = [np.asarray([parameter._idx for parameter in parameters], dtype=np.int64)
+                         for parameters in self.optimizable_parameters_by_system]
+        self._scatter = dict(key=key, per_system=per_system, by_system_idx=by_system_idx)
         return self._scatter
 
     def _physical(self, parameters_values):
@@ -227,17 +229,20 @@ class ParameterSpace:
         x = np.asarray(self.optimizable_parameters_values, dtype=np.float64)
         plan = self._compile_scatter(systems, symmetry_constrained)
         system = None
-        for system, sc in zip(systems, plan["per_system"]):
+        by_system = []
+        for system, sc, idx in zip(systems, plan["per_system"], plan["by_system_idx"]):
             ff = system.force_field
             if len(sc["dst"]):
                 ff.store[sc["dst"]] = x[sc["src"]]
+            # per-system value list as the reference builds it right after the scatter (parameter_space.py:383-385),
+            # gathered from the value store instead of reading 232 Python properties per call
+            by_system.append(ff.store[idx].tolist())
             engine_plan = system.engine.compile_update_plan(ff)
             if len(engine_plan["abs_idx"]):
                 ff.store[engine_plan["abs_idx"]] = np.abs(ff.store[engine_plan["abs_idx"]])
             slots = system.engine.slots_from_store(ff, ff.store[None, :])
             system.engine.load_slots(slots[0])
-        self.optimizable_parameters_values_by_system = [[parameter.value for parameter in parameters]
-                                                        for parameters in self.optimizable_parameters_by_system]
+        self.optimizable_parameters_values_by_system = by_system
         # as in the reference, only the LAST system's RESP engine is refreshed (:394-395 uses the loop variable)
         if system is not None and system.resp_engine is not None:
             if hasattr(system.resp_engine, "set_charges"):
