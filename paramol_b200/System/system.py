@@ -6,7 +6,7 @@ Description
 function is built on; same attributes and methods as the reference class for this path
 (``ParaMol/System/system.py:32-752``): ``ref_coordinates``, ``ref_energies``, ``ref_forces``, ``ref_esp``,
 ``ref_esp_grid``, ``weights``, ``wham_weights``, ``n_structures``, ``n_atoms``, ``engine``, ``resp_engine``,
-``force_field``, ``n_cpus``; ``compute_conformations_weights``, ``get_energies_ensemble``, ``get_forces_ensemble``,
+``force_field``, ``n_cpus``; ``compute_conformations_weights``, ``wham_reweighing``, ``get_energies_ensemble``, ``get_forces_ensemble``,
 ``get_esp_ensemble``, ``energy_statistics``, ``force_statistics``, ``filter_conformations``,
 ``append_data_to_system``, ``read_data``, ``write_data``.
 
@@ -168,6 +168,52 @@ class ParaMolSystem:
         else:
             raise NotImplementedError("Weighting method {} is not implemented.".format(weighting_method))
         return self.weights
+
+    def wham_reweighing(self, parameters_generation):
+        """
+        WHAM weights of the conformations over the parameter generations of an adaptive parametrisation
+        (reference ``:250-322``).  The reference runs one full energy pass over the ensemble per generation; here the
+        slot rows of all generations are built with the object path and evaluated by ONE energy-only launch (P = number
+        of generations).  The fixed-point iteration on the [n_gen, S] weight matrices is the reference's, on the host.
+        """
+        import torch
+        n_gen = len(parameters_generation)
+        current_gen = n_gen - 1
+        rmsd = 999999.0
+        threshold = 1e-6
+        if n_gen < 2:
+            return np.ones(self.n_structures)
+        wham_weights = np.ones((n_gen, self.n_structures)) / self.n_structures
+        A = np.ones(n_gen) / n_gen
+        rows = []
+        for j in range(n_gen):
+            self.force_field.update_force_field(parameters_generation[j])
+            self.engine.set_bonded_parameters(self.force_field.force_field_optimizable)
+            self.engine.set_nonbonded_parameters(self.force_field.force_field_optimizable)
+            rows.append(self.engine.current_slots())
+        ens = self.device_ensemble()
+        derived = ens.topology.prepare(torch.from_numpy(np.ascontiguousarray(np.stack(rows))).to(ens.device))
+        emm, _, _ = ens.evaluate(derived, with_forces=False)
+        exp_energies = np.exp(-0.5 * emm.cpu().numpy())
+        weights = exp_energies / np.sum(exp_energies, axis=1, keepdims=True)
+        prev_weight = weights[current_gen, :]
+        final_weights = np.zeros((n_gen, self.n_structures))
+        G = current_gen
+        while rmsd > threshold:
+            final_weights = np.zeros((n_gen, self.n_structures))
+            for G in range(n_gen):
+                for j in range(G + 1):
+                    final_weights[G, :] = final_weights[G, :] + A[j] * (weights[G, :] / weights[j, :])
+                wham_weights[G, :] = final_weights[G, :]
+                A[G] = np.sum(wham_weights[G, :])
+                A = A / np.sum(A)
+            rmsd = np.sqrt(np.sum((final_weights[current_gen, :] - prev_weight) ** 2) / self.n_structures)
+            prev_weight = final_weights[current_gen, :]
+        self.wham_weights = final_weights[G, :]
+        self.force_field.update_force_field(parameters_generation[current_gen])
+        self.engine.set_bonded_parameters(self.force_field.force_field_optimizable)
+        self.engine.set_nonbonded_parameters(self.force_field.force_field_optimizable)
+        return self.wham_weights
 
     # ------------------------------------------------------------------------------------------
     # ensembles (reference :324-382)

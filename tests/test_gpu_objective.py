@@ -223,3 +223,36 @@ def test_openmm_wrapper_goldens_reaction_field(kwargs_dict, golden_dir, goldens)
     assert abs(e - E[0]) < 1e-10 and np.abs(f - F[0]).max() < 1e-9
     assert engine.get_atom_list() == goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_atom_list::atom_list_to_compare"]
     assert engine.get_atomic_numbers() == goldens["test_openmm_wrapper.py::test_OpenMMEngine_get_atomic_numbers::atomic_numbers_to_compare"]
+
+
+def test_wham_reweighing_matches_sequential_restatement(kwargs_dict, golden_dir):
+    """ParaMolSystem.wham_reweighing (System/system.py:250-322): batched energy passes == one pass per generation."""
+    system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False)
+    _, x0 = system.force_field.get_optimizable_parameters()
+    x0 = np.asarray(x0)
+    rng = np.random.default_rng(4)
+    gens = [list(x0 * (1.0 + 0.002 * rng.uniform(-1, 1, x0.shape))) for _ in range(3)]
+    got = system.wham_reweighing(gens)
+    # restatement with one ensemble pass per generation
+    weights = []
+    for g in gens:
+        system.force_field.update_force_field(g)
+        system.engine.set_bonded_parameters(system.force_field.force_field_optimizable)
+        system.engine.set_nonbonded_parameters(system.force_field.force_field_optimizable)
+        e = np.exp(-0.5 * system.get_energies_ensemble())
+        weights.append(e / e.sum())
+    weights = np.asarray(weights)
+    n_gen, S = weights.shape
+    A = np.ones(n_gen) / n_gen
+    prev, rmsd = weights[-1], 1e9
+    while rmsd > 1e-6:
+        final = np.zeros_like(weights)
+        for G in range(n_gen):
+            for j in range(G + 1):
+                final[G] += A[j] * weights[G] / weights[j]
+            A[G] = final[G].sum()
+            A = A / A.sum()
+        rmsd = np.sqrt(np.sum((final[-1] - prev) ** 2) / S)
+        prev = final[-1]
+    assert got.shape == (10,) and np.allclose(got, final[-1], rtol=1e-10, atol=0)
+    assert np.ndim(system.wham_weights) == 1
