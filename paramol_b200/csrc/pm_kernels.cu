@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 pm_d3 f[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) f[k] = pm_d3{0.0, 0.0, 0.0};
-                if (rec >= 0) {
+                if (L == 1 || rec >= 0) {
                     const int4 h0 = s_star_rec[4 * rec], h1 = s_star_rec[4 * rec + 1], h2 = s_star_rec[4 * rec + 2],
                                h3 = s_star_rec[4 * rec + 3];
                     center = h0.x;
@@ -342,12 +342,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             for (int step = 0; step < g.n_axis_steps; ++step) {
                 const int2 te = s_axis_tab[step * L + tl];  // (record, colour)
                 const int rec = te.x;
-                const bool live = rec >= 0;
+                const bool live = L == 1 || rec >= 0;
                 const int hdr = L > 1 ? s_axis_hdr[step] : 1;
                 const int n_col = hdr & 0xff;
                 int aj = 0, ak = 0, nI = 0, nL = 0;
-                int Ia[3] = {0, 0, 0}, La[3] = {0, 0, 0};
-                int ts[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                int La[3] = {0, 0, 0};
+                const int *arec = s_axis_rec + 20 * (rec < 0 ? 0 : rec);  // [4..6] i atoms, [10..19] cell starts
                 pm_d3 xj{0.0, 0.0, 0.0}, d1{1.0, 0.0, 0.0};
                 double rb = 1.0, ib2 = 1.0;
                 pm_d3 c2[3];
@@ -361,27 +361,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 }
                 if (live) {
                     const int4 *r4 = reinterpret_cast<const int4 *>(s_axis_rec + 20 * rec);
-                    const int4 h0 = r4[0], h1 = r4[1], h2 = r4[2], h3 = r4[3], h4 = r4[4];
+                    const int4 h0 = r4[0], h1 = r4[1], h2 = r4[2];
                     aj = h0.x;
                     ak = h0.y;
                     nI = h0.z;
                     nL = h0.w;
-                    Ia[0] = h1.x;
-                    Ia[1] = h1.y;
-                    Ia[2] = h1.z;
                     La[0] = h1.w;
                     La[1] = h2.x;
                     La[2] = h2.y;
-                    ts[0] = h2.z;
-                    ts[1] = h2.w;
-                    ts[2] = h3.x;
-                    ts[3] = h3.y;
-                    ts[4] = h3.z;
-                    ts[5] = h3.w;
-                    ts[6] = h4.x;
-                    ts[7] = h4.y;
-                    ts[8] = h4.z;
-                    ts[9] = h4.w;
                     xj = pm_ldo<CPW>(xc_base, aj);
                     const pm_d3 xk = pm_ldo<CPW>(xc_base, ak);
                     d1 = pm_sub(xk, xj);
@@ -402,19 +389,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 pm_d3 Fj{0.0, 0.0, 0.0}, Fk{0.0, 0.0, 0.0};
                 const int ni_loop = L > 1 ? (hdr >> 8) : nI;
                 for (int pi = 0; pi < ni_loop; ++pi) {
-                    const bool act = live && pi < nI;
+                    const bool act = L == 1 || (live && pi < nI);
                     int ai = 0;
                     pm_d3 fi{0.0, 0.0, 0.0};
                     if (act) {
-                        ai = pi == 0 ? Ia[0] : (pi == 1 ? Ia[1] : Ia[2]);
+                        ai = arec[4 + pi];
+                        const int *cells = arec + 10 + 3 * pi;
                         const pm_d3 d0 = pm_sub(pm_ldo<CPW>(xc_base, ai), xj);
                         const pm_d3 c1 = pm_cross(d0, d1);
                         const double s1 = pm_rsqrt(pm_dot(c1, c1));
                         double A = 0.0;
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const int t0 = pi == 0 ? ts[q] : (pi == 1 ? ts[3 + q] : ts[6 + q]);
-                            const int t1 = pi == 0 ? ts[q + 1] : (pi == 1 ? ts[4 + q] : ts[7 + q]);
+                            const int t0 = cells[q], t1 = cells[q + 1];
                             if (t1 > t0) {
                                 const double inv12 = s1 * s2[q];
                                 const double cphi = pm_dot(c1, c2[q]) * inv12;
