@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""
+Measurements for BASELINE.json configs 3-5 (the headline config 2 is bench.py): prints one JSON line per config.
+  config 3  lig60, 256 parameter vectors x 100k conformations per launch (Monte Carlo / SA / FD-gradient batches)
+  config 4  LLS on lig60 bonded terms over 200k conformations (design matrix + QR reduction)
+  config 5  RESP: 500 grid points x 50k conformations, N = 60 (normal-equation assembly + ESP objective)
+"""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from paramol_b200 import _lib  # noqa: E402
+from paramol_b200.MM_engines.b200_engine import B200Engine  # noqa: E402
+from paramol_b200.MM_engines.device import DeviceEnsemble  # noqa: E402
+from paramol_b200.MM_engines.resp import RESP  # noqa: E402
+from paramol_b200.MM_engines.least_square import LinearLeastSquare  # noqa: E402
+from paramol_b200.System.system import ParaMolSystem  # noqa: E402
+from paramol_b200.Parameter_space.parameter_space import ParameterSpace  # noqa: E402
+from paramol_b200.Utils.synthetic import make_ligand  # noqa: E402
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def config3(P=256, S=100_000):
+    mm, x0 = make_ligand(60)
+    engine = B200Engine(system=mm)
+    topo = engine.device_topology()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.from_numpy(x0).cuda()[None] + 0.005 * torch.randn((S,) + x0.shape, dtype=torch.float64, device="cuda", generator=g)
+    F = 50.0 * torch.randn((S,) + x0.shape, dtype=torch.float64, device="cuda", generator=g)
+    E = torch.randn(S, dtype=torch.float64, device="cuda", generator=g)
+    ens = DeviceEnsemble(topo, X, F, E)
+    base = engine.current_slots()
+    rng = np.random.default_rng(0)
+    slots = torch.from_numpy(base[None, :] * (1.0 + 0.02 * rng.uniform(-1, 1, (P, len(base))))).cuda()
+    derived = topo.prepare(slots)
+    emm, fres, _ = ens.evaluate(derived)
+    ens.reduce(emm, fres)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    derived = topo.prepare(slots)
+    emm, fres, _ = ens.evaluate(derived)
+    part = ens.reduce(emm, fres)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    flops = 36 * topo.n_pairs + 30 * topo.n_bonds + 90 * topo.n_angles + 160 * topo.n_torsions + 21 * 60 + 4
+    return dict(config=3, workload="lig60 x %d vectors x %d conformations, E+F+residual" % (P, S), ms=ms,
+                conf_evals_per_s=P * S / (ms * 1e-3), objective_evals_per_s=P / (ms * 1e-3),
+                tflops_algorithmic=flops * P * S / (ms * 1e-3) / 1e12, launch=topo.launch_info(True), program=topo.program_info())
+
+
+def config4(S=200_000):
+    mm, x0 = make_ligand(60)
+    engine = B200Engine(system=mm)
+    system = ParaMolSystem("lig60", engine, 60)
+    system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
+    rng = np.random.default_rng(2)
+    system.ref_coordinates = x0[None] + rng.normal(0, 0.005, (S,) + x0.shape)
+    system.n_structures = S
+    system.ref_energies = system.get_energies_ensemble() + rng.normal(0, 3.0, S)
+    ps = ParameterSpace()
+    ps.get_optimizable_parameters([system], symmetry_constrained=False)
+    lls = LinearLeastSquare(ps, True, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01, weighting_method="uniform",
+                            weighting_temperature=300.0)
+    lls._calculate_a_device(system, 0.05, 0.05)  # warm-up (allocations, cusolver handles)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    A = lls._calculate_a_device(system, 0.05, 0.05)
+    torch.cuda.synchronize()
+    t_design = time.perf_counter() - t0
+    M = A.shape[1]
+    t0 = time.perf_counter()
+    lls.fit_parameters_lls([system])
+    torch.cuda.synchronize()
+    t_fit = time.perf_counter() - t0
+    return dict(config=4, workload="LLS lig60: S=%d conformations x M=%d columns" % (S, M), design_matrix_s=t_design,
+                design_GB_s=(S * 60 * 24 + S * M * 8) / t_design / 1e9, full_fit_s=t_fit,
+                note="full fit = design matrix + zero-parameter energy pass + weighting + device QR (library) + host lstsq on the "
+                     "stacked (M + reg) x M system")
+
+
+def config5(S=50_000, G=500, N=60):
+    mm, x0 = make_ligand(N)
+    rng = np.random.default_rng(11)
+    X = (x0[None] + rng.normal(0, 0.005, (S,) + x0.shape)) * 18.897
+    dirs = rng.normal(size=(S, G, 3))
+    dirs /= np.linalg.norm(dirs, axis=2, keepdims=True)
+    centres = X[np.arange(S)[:, None], rng.integers(0, N, (S, G))]
+    grid = centres + dirs * rng.uniform(1.4, 2.0, (S, G, 1)) * 3.2
+    q_true = mm.particle_par[:, 0]
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    xd, gd = torch.from_numpy(X).to(dev), torch.from_numpy(grid).to(dev)
+    qd = torch.from_numpy(np.ascontiguousarray(q_true)).to(dev)
+    vref = torch.empty((S, G), dtype=torch.float64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a, b = ev(), ev()
+    _lib.check(L.pm_esp_potential(N, xd.data_ptr(), gd.data_ptr(), qd.data_ptr(), S, G, vref.data_ptr(), st))
+    torch.cuda.synchronize()
+    a.record()
+    _lib.check(L.pm_esp_potential(N, xd.data_ptr(), gd.data_ptr(), qd.data_ptr(), S, G, vref.data_ptr(), st))
+    b.record()
+    torch.cuda.synchronize()
+    ms_pot = a.elapsed_time(b)
+    vref += 1e-3 * torch.randn_like(vref)
+    out = torch.empty(N * N + N + 1, dtype=torch.float64, device=dev)
+    scratch = torch.empty(int(L.pm_resp_scratch_doubles(N, S, G)), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        _lib.check(L.pm_resp_assemble(N, xd.data_ptr(), gd.data_ptr(), vref.data_ptr(), None, S, G, out.data_ptr(), scratch.data_ptr(), st))
+    torch.cuda.synchronize()
+    a.record()
+    _lib.check(L.pm_resp_assemble(N, xd.data_ptr(), gd.data_ptr(), vref.data_ptr(), None, S, G, out.data_ptr(), scratch.data_ptr(), st))
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    flops = 2.0 * S * G * N * N + 2.0 * S * G * N + 12.0 * S * G * N
+    return dict(config=5, workload="RESP N=%d, G=%d grid points x S=%d conformations" % (N, G, S), assemble_ms=ms,
+                assemble_tflops=flops / (ms * 1e-3) / 1e12, conformations_per_s=S / (ms * 1e-3), esp_potential_ms=ms_pot,
+                bytes_per_conformation=24 * N + 32 * G, hbm_GB_s=S * (24 * N + 32 * G) / (ms * 1e-3) / 1e9)
+
+
+if __name__ == "__main__":
+    which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
+    for c in which:
+        print(json.dumps({3: config3, 4: config4, 5: config5}[c]()), flush=True)
