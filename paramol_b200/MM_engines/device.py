@@ -28,19 +28,16 @@ def _iptr(a):
     return a.ctypes.data_as(c_int_p)
 
 
-_STREAM_CACHE = {}
-
-
 def _stream_ptr(device):
-    """cudaStream_t of torch's current stream on ``device`` (cached while the current stream object is unchanged)."""
+    """cudaStream_t (as void*) of torch's current stream on ``device``."""
     torch = _torch()
-    stream = torch.cuda.current_stream(device)
-    key = (str(device), stream.cuda_stream)
-    ptr = _STREAM_CACHE.get(key)
-    if ptr is None:
-        ptr = ctypes.c_void_p(stream.cuda_stream)
-        _STREAM_CACHE[key] = ptr
-    return ptr
+    index = device.index if hasattr(device, "index") else int(device)
+    if index is None:
+        index = torch.cuda.current_device()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return ctypes.c_void_p(raw(index))
+    return ctypes.c_void_p(torch.cuda.current_stream(index).cuda_stream)
 
 
 class DeviceTopology:
