@@ -38,9 +38,10 @@ class EnergyProperty(Property):
 
     def calculate_property(self, emm_data):
         obj_fun_energies = []
-        emm_data = np.asarray(emm_data)
+        # (the reference converts emm_data with np.asarray, which only works when every system has the same number of
+        # conformations; the per-system arrays are used as they are here)
         for system, emm, var in zip(self.systems, emm_data, self.variance):
-            diff = system.ref_energies - emm
+            diff = np.asarray(system.ref_energies) - np.asarray(emm)
             n_global = system.n_structures_global()
             avg_diff = float(_dist.allreduce_sum_numpy(np.array([np.sum(diff)]))[0]) / n_global \
                 if _dist.world_size() > 1 else np.mean(diff)

@@ -256,3 +256,77 @@ def test_wham_reweighing_matches_sequential_restatement(kwargs_dict, golden_dir)
         prev = final[-1]
     assert got.shape == (10,) and np.allclose(got, final[-1], rtol=1e-10, atol=0)
     assert np.ndim(system.wham_weights) == 1
+
+
+def test_two_systems_manual_weights_fused_equals_seam_path(kwargs_dict, golden_dir):
+    """Two systems (aniline twice, different data), MANUAL weights: fused device reduction == reference-structured path."""
+    from oracle import oracle as O
+    from paramol_b200.Utils.synthetic import perturbed_conformations
+    rng = np.random.default_rng(21)
+    systems = []
+    for k, n_conf in enumerate((37, 64)):
+        system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False)
+        system.name = "aniline%d" % k
+        X = perturbed_conformations(np.asarray(system.ref_coordinates), n_conf, sigma=0.004, seed=30 + k)
+        E, F = O.energies_forces(system.engine.system, X)
+        system.ref_coordinates, system.n_structures = X, n_conf
+        system.ref_energies = E + rng.normal(0, 4.0, n_conf) - 43000.0
+        system.ref_forces = F + rng.normal(0, 60.0, F.shape)
+        w = rng.uniform(0.2, 1.0, n_conf)
+        system.compute_conformations_weights(weighting_method="manual", manual_weights_array=w / w.sum())
+        systems.append(system)
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters(systems)
+    x0 = np.asarray(x0)
+    assert len(x0) == 2 * (28 + 42 + 70)
+    e_prop, f_prop = EnergyProperty(systems, weight=0.4), ForceProperty(systems, term_type="components", weight=2.0)
+    e_prop.calculate_variance()
+    f_prop.calculate_variance()
+    settings = dict(objective_function_settings, weighting_method="manual", checkpoint_freq=10 ** 9)
+    of = ObjectiveFunction(None, ps, [e_prop, f_prop], systems, **settings)
+    of_seam = ObjectiveFunction(None, ps, [e_prop, f_prop], systems, fused=False, **settings)
+    x = x0 * (1.0 + 0.01 * rng.uniform(-1, 1, x0.shape))
+    a = of.f(x.copy())
+    fused_values = (e_prop.value, f_prop.value)
+    b = of_seam.f(x.copy())
+    assert abs(a - b) <= 1e-10 * abs(b)
+    assert abs(fused_values[0] - e_prop.value) <= 1e-10 * abs(e_prop.value)
+    assert abs(fused_values[1] - f_prop.value) <= 1e-10 * abs(f_prop.value)
+    # oracle cross-check of the first system's energy term
+    ps.update_systems(systems, x.copy())
+    E0, _ = O.energies_forces(systems[0].engine.system, systems[0].ref_coordinates)
+    want0 = O.energy_property(systems[0].ref_energies, E0, systems[0].weights)
+    got = e_prop.calculate_property([s.get_energies_ensemble() for s in systems])
+    assert abs(got[0] - want0) <= 1e-8 * abs(want0)
+
+
+def test_esp_property_in_the_objective(kwargs_dict, golden_dir):
+    """ESP property through ObjectiveFunction.f: fused quadratic form == seam path (system.py:356-382 + esp_property.py:89-104)."""
+    from paramol_b200.MM_engines.resp import RESP
+    from paramol_b200.Objective_function.Properties.esp_property import ESPProperty
+    engine = B200Engine(True, **kwargs_dict)
+    system = ParaMolSystem(name="aniline", engine=engine, n_atoms=14)
+    d = np.load(os.path.join(golden_dir, "aniline_esp.npz"))
+    rng = np.random.default_rng(2)
+    sel = rng.choice(len(d["esp"]), 3000, replace=False)
+    system.ref_coordinates = [d["conformation"], d["conformation"] + rng.normal(0, 0.01, (14, 3))]
+    system.ref_esp_grid = [d["grid"][sel], d["grid"][sel[:2000]]]
+    system.ref_esp = [d["esp"][sel], d["esp"][sel[:2000]]]
+    system.n_structures = 2
+    system.force_field.create_force_field(opt_charges=True)
+    ps = ParameterSpace()
+    _, q0 = ps.get_optimizable_parameters([system])
+    system.resp_engine = RESP(0, False, "L2", 1.0, 0.01, "uniform", 300.0)
+    system.resp_engine.set_initial_charges(system.force_field.force_field)
+    system.resp_engine.set_charges(system.force_field.force_field)
+    system.resp_engine.calculate_inverse_distances(system)
+    prop = ESPProperty([system], weight=1.5)
+    prop.calculate_variance()
+    settings = dict(objective_function_settings, checkpoint_freq=10 ** 9)
+    of = ObjectiveFunction(None, ps, [prop], [system], **settings)
+    of_seam = ObjectiveFunction(None, ps, [prop], [system], fused=False, **settings)
+    q = np.asarray(q0) + rng.normal(0, 0.05, len(q0))
+    a, b = of.f(q.copy()), of_seam.f(q.copy())
+    assert abs(a - b) <= 1e-8 * abs(b) and a > 0
+    vals = of.f_batch(np.stack([q, np.asarray(q0)]))
+    assert abs(vals[0] - b) <= 1e-8 * abs(b)
