@@ -144,6 +144,41 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     }
 }
 
+// All NL cells of one i-substituent of a "simple" axis (one torsion of periodicity 1..4 per cell) as ONE branch-free block:
+// NL independent dependency chains.  Returns A = sum_l a_il; B[q] and e_tors are accumulated in place.
+template <int NL, bool WITH_F>
+__device__ __forceinline__ double pm_axis_cells(const int *__restrict__ cells, const int2 *__restrict__ s_axis_terms,
+                                                const double2 *__restrict__ s_ptors, const pm_d3 c1, const pm_d3 d0, const double s1,
+                                                const double rb, const pm_d3 (&c2)[3], const double (&s2)[3], double (&B)[3],
+                                                double &e_tors) {
+    double A = 0.0;
+#pragma unroll
+    for (int q = 0; q < NL; ++q) {
+        const int2 term = s_axis_terms[cells[q]];  // (torsion index, periodicity)
+        const double2 kk = s_ptors[2 * term.x], cs = s_ptors[2 * term.x + 1];
+        const double inv12 = s1 * s2[q];
+        const double cphi = pm_dot(c1, c2[q]) * inv12;
+        const double sphi = rb * pm_dot(d0, c2[q]) * inv12;
+        double cn = cphi, sn = sphi;
+#pragma unroll
+        for (int mm = 1; mm < 4; ++mm) {
+            const double c_new = fma(cn, cphi, -(sn * sphi));
+            const double s_new = fma(sn, cphi, cn * sphi);
+            const bool step = mm < term.y;
+            cn = step ? c_new : cn;
+            sn = step ? s_new : sn;
+        }
+        const double cda = fma(cn, cs.x, sn * cs.y);
+        e_tors = fma(kk.x, cda, e_tors + kk.x);
+        if (WITH_F) {
+            const double w = -kk.y * fma(sn, cs.x, -(cn * cs.y)) * rb;
+            A = fma(-w, s1 * s1, A);
+            B[q] = fma(w, s2[q] * s2[q], B[q]);
+        }
+    }
+    return A;
+}
+
 // Force write-back of one step.  One lane per conformation (L == 1): plain.  Teams: the records of a step that share a
 // colour touch disjoint atoms (pm_program.hpp), colours are serialised with __syncwarp between them.
 #define PM_ORDERED(n_col, colour, cond, ...)           \
@@ -346,6 +381,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 const int hdr = L > 1 ? s_axis_hdr[step] : 1;
                 const int n_col = hdr & 0xff;
                 int aj = 0, ak = 0, nI = 0, nL = 0;
+                bool simple = false;
                 int La[3] = {0, 0, 0};
                 const int *arec = s_axis_rec + 20 * (rec < 0 ? 0 : rec);  // [4..6] i atoms, [10..19] cell starts
                 pm_d3 xj{0.0, 0.0, 0.0}, d1{1.0, 0.0, 0.0};
@@ -364,7 +400,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     const int4 h0 = r4[0], h1 = r4[1], h2 = r4[2];
                     aj = h0.x;
                     ak = h0.y;
-                    nI = h0.z;
+                    nI = h0.z & 255;
+                    simple = (h0.z & 256) != 0;
                     nL = h0.w;
                     La[0] = h1.w;
                     La[1] = h2.x;
@@ -399,6 +436,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         const pm_d3 c1 = pm_cross(d0, d1);
                         const double s1 = pm_rsqrt(pm_dot(c1, c1));
                         double A = 0.0;
+                        if (L == 1 && simple) {  // (with teams the lanes of a step would diverge between the two paths)
+                            if (nL == 2)
+                                A = pm_axis_cells<2, WITH_F>(cells, s_axis_terms, s_ptors, c1, d0, s1, rb, c2, s2, B, e_tors);
+                            else if (nL == 3)
+                                A = pm_axis_cells<3, WITH_F>(cells, s_axis_terms, s_ptors, c1, d0, s1, rb, c2, s2, B, e_tors);
+                            else
+                                A = pm_axis_cells<1, WITH_F>(cells, s_axis_terms, s_ptors, c1, d0, s1, rb, c2, s2, B, e_tors);
+                        } else
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             const int t0 = cells[q], t1 = cells[q + 1];

@@ -326,7 +326,15 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
         axis_items.push_back(it);
         axis_rec.push_back(ax.j * AO);
         axis_rec.push_back(ax.k * AO);
-        axis_rec.push_back((int)ax.I.size());
+        // "simple" axis: every (i, l) cell holds exactly one torsion of periodicity 1..4 -> the kernel runs the cells of an
+        // i-substituent as one branch-free block (independent dependency chains the compiler can interleave)
+        bool simple = true;
+        for (int pi = 0; pi < (int)ax.I.size(); ++pi)
+            for (int pl = 0; pl < (int)ax.Lst.size(); ++pl) {
+                const auto &c = ax.cell[pi * 3 + pl];
+                if (c.size() != 1 || tors_per[c[0]] < 1 || tors_per[c[0]] > 4) simple = false;
+            }
+        axis_rec.push_back((int)ax.I.size() | (simple ? 256 : 0));
         axis_rec.push_back((int)ax.Lst.size());
         for (int q = 0; q < 3; ++q) axis_rec.push_back((q < (int)ax.I.size() ? ax.I[q] : ax.j) * AO);
         for (int q = 0; q < 3; ++q) axis_rec.push_back((q < (int)ax.Lst.size() ? ax.Lst[q] : ax.k) * AO);
@@ -497,7 +505,7 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
         int max_ni = 0;
         for (int l = 0; l < L; ++l) {
             const int rec = axis_tab[2 * (st * L + l)];
-            if (rec >= 0) max_ni = std::max(max_ni, axis_rec[20 * rec + 2]);
+            if (rec >= 0) max_ni = std::max(max_ni, axis_rec[20 * rec + 2] & 255);
         }
         axis_hdr[st] |= max_ni << 8;
     }
@@ -583,7 +591,7 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
             if (colour < 0 || colour >= n_col) return 27;
             std::set<int> &used = used_by_colour[colour];
             const int *r = b + p.off_axis_rec + 20 * rec;
-            const int j = r[0] / AO, k = r[1] / AO, nI = r[2], nL = r[3];
+            const int j = r[0] / AO, k = r[1] / AO, nI = r[2] & 255, nL = r[3];
             if (nI < 1 || nI > 3 || nL < 1 || nL > 3 || nI > max_ni) return 20;
             std::set<int> mine;
             mine.insert(j);
