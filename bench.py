@@ -330,6 +330,20 @@ def run_ours(args):
     t_dev = max_over_ranks(e_all0.elapsed_time(e_all1) * 1e-3)
     t_kernel = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3)
 
+    # ======================= (3) optional mode, reported separately: nonbonded terms cached across calls =====================
+    # (legitimate here because the reference's all-optimizable setup never pushes nonbonded parameters, openmm.py:752-754;
+    #  NOT part of `value` / `e2e`, which time full evaluations)
+    of_c = ObjectiveFunction(None, ps, [e_prop, f_prop, r_prop], [system], platform_name="B200", weighting_method="uniform",
+                             checkpoint_freq=10 ** 12, cache_nonbonded=True)
+    for x in trial[:args.warmup]:
+        of_c.f(x)
+    barrier()
+    t0 = time.perf_counter()
+    f_vals_c = [of_c.f(x) for x in trial[args.warmup:]]
+    barrier()
+    t_e2e_cached = max_over_ranks(time.perf_counter() - t0)
+    cache_ok = bool(np.allclose(f_vals_c, f_vals, rtol=1e-12, atol=0))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,6 +398,10 @@ def run_ours(args):
                      "kernel_share_of_step": t_kernel * args.steps / t_dev, "launch": info,
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "bytes_per_conformation": bytes_conf, "peak_source": hbm_src}},
+        "nonbonded_cache_mode": {"e2e_value": world * S * args.steps / t_e2e_cached, "unit": "conformations/s",
+                                 "ms_per_step": 1e3 * t_e2e_cached / args.steps, "same_objective_values": cache_ok,
+                                 "note": "optional ObjectiveFunction(cache_nonbonded=True): pair terms evaluated once while the "
+                                         "nonbonded parameters stay unchanged, bonded terms every call; not the headline"},
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
         "objective_value_last_step": f_vals[-1] if f_vals else None,

@@ -116,6 +116,16 @@ int pm_eval(pm_handle h, const double *derived_dev, int n_vec,
             const double *coord_tiles_dev, const double *fref_tiles_dev, long n_conf,
             int with_forces, double *emm_dev, double *fres_dev, double *fmm_tiles_dev, void *stream);
 
+/* pm_eval with a term selection.  mode 0: all terms (= pm_eval).  mode 1: nonbonded terms only -- with emm_dev and
+ * fmm_tiles_dev as outputs this builds the nonbonded cache (E_nb [S], F_nb tiles) of ONE parameter vector.  mode 2:
+ * bonded terms evaluated, nonbonded energies/forces taken from the cache (nb_e_dev [S], nb_f_tiles_dev): for batches of
+ * trial vectors that share their nonbonded parameters -- every bonded-only fit, and the reference's "everything
+ * optimizable" setup in which set_nonbonded_parameters pushes nothing (ParaMol/MM_engines/openmm.py:752-754). */
+int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec,
+               const double *coord_tiles_dev, const double *fref_tiles_dev, long n_conf,
+               int with_forces, double *emm_dev, double *fres_dev, double *fmm_tiles_dev,
+               int mode, const double *nb_e_dev, const double *nb_f_tiles_dev, void *stream);
+
 /* Weighted residual partial sums of this rank's conformations, one row of PM_NPARTIAL doubles per vector:
  *   [0] sum d'          d' = (E_ref - E_mm) - d_shift       (energy_property.py:99-108)
  *   [1] sum w d'   [2] sum w d'^2   [3] sum w   [4] sum w * fres   [5] count   [6],[7] reserved (0)

@@ -240,10 +240,12 @@ class DeviceEnsemble:
         return b
 
     # ------------------------------------------------------------------------------------------
-    def evaluate(self, derived, with_forces=True, want_fres=True, want_fmm=False):
+    def evaluate(self, derived, with_forces=True, want_fres=True, want_fmm=False, nb_cache=None):
         """
         Launch the E(+F) kernel for ``derived`` [P, n_derived] (CUDA).  Returns (emm [P,S], fres [P,S] or None,
         fmm_tiles [P, tiles*tile_doubles] or None); outputs are views of reusable device buffers.
+        ``nb_cache`` = (E_nb [S], F_nb tiles) from :meth:`build_nonbonded_cache`: bonded terms are evaluated, nonbonded
+        contributions come from the cache.
         """
         topo = self.topology
         n_vec = int(derived.shape[0])
@@ -256,12 +258,27 @@ class DeviceEnsemble:
             fres = self._buf("fres", (n_vec, self.n_conf))
         if with_forces and want_fmm:
             fmm = self._buf("fmm", (n_vec, topo.n_tiles(self.n_conf) * topo.tile_doubles))
-        _lib.check(topo._L.pm_eval(topo._h, derived.data_ptr(), n_vec, self.coord_tiles.data_ptr(),
-                                   self.fref_tiles.data_ptr() if (fres is not None) else None, self.n_conf,
-                                   int(bool(with_forces)), emm.data_ptr(),
-                                   fres.data_ptr() if fres is not None else None,
-                                   fmm.data_ptr() if fmm is not None else None, _stream_ptr(self.device)), "pm_eval")
+        mode, nb_e, nb_f = 0, None, None
+        if nb_cache is not None:
+            mode, nb_e, nb_f = 2, nb_cache[0].data_ptr(), nb_cache[1].data_ptr()
+        _lib.check(topo._L.pm_eval_ex(topo._h, derived.data_ptr(), n_vec, self.coord_tiles.data_ptr(),
+                                      self.fref_tiles.data_ptr() if (fres is not None) else None, self.n_conf,
+                                      int(bool(with_forces)), emm.data_ptr(),
+                                      fres.data_ptr() if fres is not None else None,
+                                      fmm.data_ptr() if fmm is not None else None, mode, nb_e, nb_f,
+                                      _stream_ptr(self.device)), "pm_eval_ex")
         return emm, fres, fmm
+
+    def build_nonbonded_cache(self, derived_row):
+        """(E_nb [S], F_nb tiles) of ONE parameter vector ``derived_row`` [1, n_derived]: the nonbonded terms only."""
+        torch = _torch()
+        topo = self.topology
+        e_nb = torch.empty((1, self.n_conf), dtype=torch.float64, device=self.device)
+        f_nb = torch.empty(topo.n_tiles(self.n_conf) * topo.tile_doubles, dtype=torch.float64, device=self.device)
+        _lib.check(topo._L.pm_eval_ex(topo._h, derived_row.data_ptr(), 1, self.coord_tiles.data_ptr(), None, self.n_conf, 1,
+                                      e_nb.data_ptr(), None, f_nb.data_ptr(), 1, None, None, _stream_ptr(self.device)),
+                   "pm_eval_ex")
+        return e_nb.reshape(-1), f_nb
 
     def reduce(self, emm, fres, d_shift=0.0, weights="own"):
         """Partial sums [P, 8] (CUDA) of this ensemble; see ``pm_reduce_objective`` in include/paramol_b200.h."""

@@ -52,10 +52,16 @@ class ObjectiveFunction:
     checkpoint_freq : int
     fused : bool
         True (default): device-side residual reduction.  False: reference-structured seam path.
+    cache_nonbonded : bool
+        When the trial vectors of a call share their nonbonded parameters with the previous call (bonded-only fits; the
+        reference's all-optimizable setup, where ``set_nonbonded_parameters`` pushes nothing), evaluate the pair terms
+        once, keep E_nb and F_nb per conformation on the device and re-evaluate only the bonded terms.  Off by default
+        (and off in ``bench.py``'s headline numbers, which time full evaluations).
     """
 
     def __init__(self, restart_settings, parameter_space, properties, systems, platform_name="B200", parallel=False,
-                 weighting_method="uniform", weighting_temperature=300.0, checkpoint_freq=1000, fused=True):
+                 weighting_method="uniform", weighting_temperature=300.0, checkpoint_freq=1000, fused=True,
+                 cache_nonbonded=False):
         self.restart_settings = restart_settings
         self.parameter_space = parameter_space
         self.properties = properties
@@ -67,6 +73,7 @@ class ObjectiveFunction:
         self._weighting_temperature = weighting_temperature
         self._f_count = 0
         self._fused = bool(fused)
+        self._cache_nonbonded = bool(cache_nonbonded)
         self._total_n_batches = None
         self._batch_lims = None
         self._parallel_function = None
@@ -318,7 +325,16 @@ class ObjectiveFunction:
             pin.copy_(host)
             slots_dev = pin.to(ens.device, non_blocking=True)
             derived = ens.topology.prepare(slots_dev)
-            emm, fres, _ = ens.evaluate(derived, with_forces=st["need_f"], want_fres=st["need_f"])
+            nb_cache = None
+            if self._cache_nonbonded:
+                block = np.ascontiguousarray(slots[:, ens.topology.off_particle:])
+                if np.all(block == block[0]):
+                    key = block[0].tobytes()
+                    if st.get("nb_key") != key:
+                        st["nb_cache"] = ens.build_nonbonded_cache(derived[0:1])
+                        st["nb_key"] = key
+                    nb_cache = st["nb_cache"]
+            emm, fres, _ = ens.evaluate(derived, with_forces=st["need_f"], want_fres=st["need_f"], nb_cache=nb_cache)
             if self._weighting_method.upper() == "NON_BOLTZMANN":
                 w = self._non_boltzmann_weights(st, system, emm)
                 rows = []

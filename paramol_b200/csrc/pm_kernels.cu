@@ -49,6 +49,9 @@ struct PmProg {
     const double *metric;    // device [9N]
     const int *pair_map;     // device [n_pairs][3] = (i, j, exception or -1)
     const double2 *acos_tab; // device [PM_ACOS_N + 1] = (cos, sin)(q pi / PM_ACOS_N)
+    // cached nonbonded contribution (pm_eval_ex mode 2): forces in tile layout and energies [S]; null otherwise
+    const double *nb_f_tiles;
+    const double *nb_e;
 };
 
 // =============================================================================================
@@ -259,10 +262,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 
         for (long tile = first_tile; tile < n_tiles; tile += warp_stride) {
             // ---- coordinates of CPW conformations: one TMA bulk copy into this warp's tile ---------
+            const bool nb_cached = g.nb_e != nullptr;
             if (lane == 0) {
                 pm_fence_proxy_async();
-                pm_mbar_expect_tx(bar, (uint32_t)(tile_d * sizeof(double)));
-                pm_bulk_g2s(xs, xt + (size_t)tile * tile_d, (uint32_t)(tile_d * sizeof(double)), bar);
+                const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));
+                pm_mbar_expect_tx(bar, (WITH_F && nb_cached) ? 2 * tile_bytes : tile_bytes);
+                pm_bulk_g2s(xs, xt + (size_t)tile * tile_d, tile_bytes, bar);
+                // cached nonbonded forces seed the force tile (instead of zeros) when the pair phase is skipped
+                if (WITH_F && nb_cached) pm_bulk_g2s(fs, g.nb_f_tiles + (size_t)tile * tile_d, tile_bytes, bar);
                 // hide HBM latency of what comes next: this tile's reference forces (read in the epilogue) and the
                 // coordinates of the next tile of this warp
                 if (WITH_F && fres != nullptr)
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (tile + warp_stride < n_tiles)
                     pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * tile_d, (uint32_t)(tile_d * sizeof(double)));
             }
-            if (WITH_F) {
+            if (WITH_F && !nb_cached) {
                 for (int k = lane; k < tile_d; k += 32) fs[k] = 0.0;
             }
             pm_mbar_wait(bar, parity);
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             __syncwarp();
 
             double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
+            if (nb_cached && tl == 0 && tile * CPW + col < n_conf) e_nb = g.nb_e[tile * CPW + col];
             const double *xc_base = xs + col;  // this lane's column of the coordinate / force tiles
             double *fc_base = fs + col;
 
@@ -1101,13 +1109,15 @@ extern "C" int pm_prepare_params(pm_handle h, const double *slots_dev, int n_vec
     return 0;
 }
 
-extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
-                       const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
-                       double *fmm_tiles_dev, void *stream) {
+extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                          const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
+                          double *fmm_tiles_dev, int mode, const double *nb_e_dev, const double *nb_f_tiles_dev, void *stream) {
     if (!h || !derived_dev || !coord_tiles_dev || !emm_dev) return pm_fail("pm_eval: null argument");
     if (n_vec < 1 || n_conf < 1) return pm_fail("pm_eval: empty batch");
     if (fres_dev && !fref_tiles_dev) return pm_fail("pm_eval: fres requested without reference forces");
     if (!with_forces && (fres_dev || fmm_tiles_dev)) return pm_fail("pm_eval: force outputs requested with with_forces=0");
+    if (mode < 0 || mode > 2) return pm_fail("pm_eval_ex: mode must be 0 (all terms), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
+    if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval_ex: mode 2 needs the cached nonbonded arrays");
     PM_CUDA(cudaSetDevice(h->device));
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
@@ -1117,12 +1127,28 @@ extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const 
         grid = (n_tiles + warps - 1) / warps;
         if (grid < 1) grid = 1;
     }
+    PmProg prog = h->prog;
+    if (mode == 1) {
+        prog.n_star_steps = 0;
+        prog.n_axis_steps = 0;
+    } else if (mode == 2) {
+        prog.n_segs = 0;
+        prog.nb_e = nb_e_dev;
+        prog.nb_f_tiles = nb_f_tiles_dev;
+    }
     pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf], h->rf);
-    fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(h->prog, derived_dev, n_vec, coord_tiles_dev,
+    fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(prog, derived_dev, n_vec, coord_tiles_dev,
                                                                                 fref_tiles_dev, n_conf, n_tiles, emm_dev,
                                                                                 wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr);
     PM_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                       const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
+                       double *fmm_tiles_dev, void *stream) {
+    return pm_eval_ex(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, with_forces, emm_dev, fres_dev, fmm_tiles_dev,
+                      0, nullptr, nullptr, stream);
 }
 
 extern "C" long pm_reduce_scratch_doubles(int n_vec) { return (long)n_vec * PM_RED_BLOCKS * 5; }

@@ -330,3 +330,31 @@ def test_esp_property_in_the_objective(kwargs_dict, golden_dir):
     assert abs(a - b) <= 1e-8 * abs(b) and a > 0
     vals = of.f_batch(np.stack([q, np.asarray(q0)]))
     assert abs(vals[0] - b) <= 1e-8 * abs(b)
+
+
+def test_nonbonded_cache_gives_the_same_objective(kwargs_dict, golden_dir):
+    """cache_nonbonded=True: pair terms evaluated once per set of nonbonded parameters, bonded terms every call."""
+    rng = np.random.default_rng(8)
+    for opt, expect_refresh in ((dict(opt_charges=False, opt_lj=False, opt_sc=False), False), (dict(opt_sc=False), True)):
+        systems = [_aniline(kwargs_dict, golden_dir, **opt) for _ in range(2)]
+        objs = []
+        for system, cached in zip(systems, (False, True)):
+            ps = ParameterSpace()
+            _, x0 = ps.get_optimizable_parameters([system])
+            e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type="components")
+            e_prop.calculate_variance()
+            f_prop.calculate_variance()
+            objs.append(ObjectiveFunction(None, ps, [e_prop, f_prop], [system], cache_nonbonded=cached,
+                                          **dict(objective_function_settings, checkpoint_freq=10 ** 9)))
+        x0 = np.asarray(x0)
+        keys = set()
+        for _ in range(4):
+            x = x0 * (1.0 + 0.01 * rng.uniform(-1, 1, x0.shape))
+            a, b = objs[0].f(x.copy()), objs[1].f(x.copy())
+            assert abs(a - b) <= 1e-12 * abs(a), (a, b)
+            keys.add(objs[1]._state[0]["nb_key"])
+        X = np.stack([x0 * (1.0 + 0.01 * rng.uniform(-1, 1, x0.shape)) for _ in range(3)])
+        va, vb = objs[0].f_batch(X), objs[1].f_batch(X)
+        assert np.all(np.abs(va - vb) <= 1e-12 * np.abs(va))
+        # bonded-only fit: one cache for all calls; with optimizable charges/LJ every vector brings its own
+        assert (len(keys) > 1) == expect_refresh
