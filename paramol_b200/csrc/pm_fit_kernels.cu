@@ -17,7 +17,12 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <string.h>
+
+#include <algorithm>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/paramol_b200.h"
 #include "pm_device.cuh"
@@ -30,48 +35,61 @@ int pm_fail_msg(const std::string &msg);  // pm_kernels.cu
         if (_e != cudaSuccess) return pm_fail_msg(std::string(#call) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-#define RESP_THREADS 128
-#define RESP_GT 32      // grid points per shared-memory tile
-#define RESP_CHUNK 512  // grid points per work item
+#ifndef RESP_CTAS_PER_SM
+#define RESP_CTAS_PER_SM 4
+#endif
+#define RESP_MAX_WARPS 8   // warps per CTA
+#define RESP_MAX_TPT 4     // 4x4 micro-tiles per thread
+#define RESP_GT 32         // grid points per shared-memory tile
+#define RESP_CHUNK 512     // grid points per work item
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K5
 // ---------------------------------------------------------------------------------------------------------------------
-template <int TPT>  // micro-tiles (4x4 blocks of the upper triangle) per thread
-__global__ void __launch_bounds__(RESP_THREADS)
-    pm_resp_kernel(int N, const double *__restrict__ coords, const double *__restrict__ grid, const double *__restrict__ vref,
-                   const double *__restrict__ wt, long S, int G, long n_items, int chunks_per_conf, double *__restrict__ partial) {
-    const int NP = (N + 3) & ~3, NB = NP >> 2;
-    const int n_tri = NB * (NB + 1) / 2;
-    extern __shared__ __align__(16) double sm[];
-    double *xs = sm;                    // [N][3]
-    double *Rt = xs + ((3 * N + 1) & ~1);  // [RESP_GT][NP]
-    double *Vt = Rt + RESP_GT * NP;     // [RESP_GT]
-    const int tid = threadIdx.x;
+// Which 4x4 micro-tile of the upper triangle of the padded (N+1) x (N+1) matrix every thread owns.  Built on the host
+// (resp_make_plan): micro-tiles are grouped by 4 x 8 super-blocks and packed 32 to a warp, so that the 32 lanes of a warp read
+// at most ~8 distinct 32-byte row pieces and ~8 distinct column pieces of R per grid point -- shared-memory traffic, which
+// bounded the first version of this kernel, drops to ~4 wavefronts per 16 warp-wide DFMAs.
+struct RespPlan {
+    unsigned char bi[RESP_MAX_TPT * RESP_MAX_WARPS * 32];  // 0xFF = no tile
+    unsigned char bj[RESP_MAX_TPT * RESP_MAX_WARPS * 32];
+};
 
-    // micro-tiles owned by this thread
+// R is kept in shared memory as Rt[k][half][block][2]: element j of grid point k lives at rt_off(j); the two 16-byte halves
+// of a micro-tile row piece are then contiguous across neighbouring blocks (conflict-free LDS.128).
+__device__ __forceinline__ int rt_off(int j, int NB) { return ((j >> 1) & 1) * (2 * NB) + 2 * (j >> 2) + (j & 1); }
+
+// The reference potential V rides along as an extra "atom row" (row N of the padded R tile), so that the same rank-32 update
+// that forms A = sum R R^T also yields B = sum R V (column N) and C = sum V.V (entry [N][N]).
+template <int TPT>
+__global__ void __launch_bounds__(RESP_MAX_WARPS * 32)
+    pm_resp_kernel(const __grid_constant__ RespPlan plan, int N, const double *__restrict__ coords, const double *__restrict__ grid,
+                   const double *__restrict__ vref, const double *__restrict__ wt, long S, int G, long n_items, int chunks_per_conf,
+                   double *__restrict__ partial) {
+    const int NP = (N + 1 + 3) & ~3, NB = NP >> 2;  // N atom rows + the V row, padded to a multiple of 4
+    extern __shared__ __align__(16) double sm[];
+    double *xs = sm;                       // [N][3]
+    double *gs = xs + ((3 * N + 1) & ~1);  // [RESP_GT][4]: grid point (x, y, z) and sqrt(w) V
+    double *Rt = gs + 4 * RESP_GT;         // [RESP_GT][NP]
+    const int tid = threadIdx.x, T = blockDim.x;
+
     int bi[TPT], bj[TPT];
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
-        int q = tid + t * RESP_THREADS;
-        bi[t] = -1;
-        bj[t] = 0;
-        if (q < n_tri) {
-            int r = 0;
-            while (q >= NB - r) {
-                q -= NB - r;
-                ++r;
-            }
-            bi[t] = r;
-            bj[t] = r + q;
-        }
+        const int e = t * T + tid;
+        bi[t] = plan.bi[e] == 0xFF ? -1 : plan.bi[e];
+        bj[t] = plan.bj[e];
     }
     double acc[TPT][16];
 #pragma unroll
     for (int t = 0; t < TPT; ++t)
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[t][e] = 0.0;
-    double bacc = 0.0, cacc = 0.0;
+
+    // generation: thread -> (row j, grid-point group kg); with T >= NP every thread keeps one row, else rows are strided
+    const int kgroups = T >= NP ? T / NP : 1;
+    const int j0 = T >= NP ? tid % NP : tid, kg = T >= NP ? tid / NP : 0, jstride = T >= NP ? NP : T;
+    const bool gen_active = kg < kgroups;
 
     for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
         const long m = item / chunks_per_conf;
@@ -79,33 +97,51 @@ __global__ void __launch_bounds__(RESP_THREADS)
         const int g1 = min(G, g0 + RESP_CHUNK);
         const double sw = wt ? sqrt(wt[m]) : 1.0;
         __syncthreads();
-        for (int i = tid; i < 3 * N; i += RESP_THREADS) xs[i] = coords[(size_t)m * 3 * N + i];
+        for (int i = tid; i < 3 * N; i += T) xs[i] = coords[(size_t)m * 3 * N + i];
         const double *gm = grid + (size_t)m * 3 * G;
         const double *vm = vref + (size_t)m * G;
         for (int t0 = g0; t0 < g1; t0 += RESP_GT) {
-            __syncthreads();
+            __syncthreads();  // previous update done with Rt / gs
             const int nk = min(RESP_GT, g1 - t0);
-            for (int e = tid; e < RESP_GT * NP; e += RESP_THREADS) {
-                const int k = e / NP, j = e - k * NP;
-                double r = 0.0;
-                if (k < nk && j < N) {
-                    const double dx = xs[3 * j] - gm[3 * (t0 + k)], dy = xs[3 * j + 1] - gm[3 * (t0 + k) + 1],
-                                 dz = xs[3 * j + 2] - gm[3 * (t0 + k) + 2];
-                    r = sw * pm_rsqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
-                }
-                Rt[e] = r;
+            if (tid < RESP_GT) {
+                const bool in = tid < nk;
+                double4 g4;
+                g4.x = in ? gm[3 * (t0 + tid)] : 0.0;
+                g4.y = in ? gm[3 * (t0 + tid) + 1] : 0.0;
+                g4.z = in ? gm[3 * (t0 + tid) + 2] : 0.0;
+                g4.w = in ? sw * vm[t0 + tid] : 0.0;
+                *reinterpret_cast<double2 *>(gs + 4 * tid) = make_double2(g4.x, g4.y);
+                *reinterpret_cast<double2 *>(gs + 4 * tid + 2) = make_double2(g4.z, g4.w);
             }
-            if (tid < RESP_GT) Vt[tid] = tid < nk ? sw * vm[t0 + tid] : 0.0;
+            __syncthreads();
+            if (gen_active) {
+                for (int j = j0; j < NP; j += jstride) {
+                    double *dst = Rt + rt_off(j, NB);
+                    if (j < N) {
+                        const double xj = xs[3 * j], yj = xs[3 * j + 1], zj = xs[3 * j + 2];
+#pragma unroll 4
+                        for (int k = kg; k < RESP_GT; k += kgroups) {
+                            const double2 gxy = *reinterpret_cast<const double2 *>(gs + 4 * k);
+                            const double dx = xj - gxy.x, dy = yj - gxy.y, dz = zj - gs[4 * k + 2];
+                            const double r = sw * pm_rsqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
+                            dst[k * NP] = k < nk ? r : 0.0;
+                        }
+                    } else {
+                        for (int k = kg; k < RESP_GT; k += kgroups) dst[k * NP] = j == N ? gs[4 * k + 3] : 0.0;
+                    }
+                }
+            }
             __syncthreads();
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
                 if (bi[t] >= 0) {
-                    const double *ra = Rt + 4 * bi[t], *rb = Rt + 4 * bj[t];
+                    const double *ra = Rt + 2 * bi[t], *rb = Rt + 2 * bj[t];
+#pragma unroll 4
                     for (int k = 0; k < RESP_GT; ++k) {
                         const double2 a01 = *reinterpret_cast<const double2 *>(ra + k * NP),
-                                      a23 = *reinterpret_cast<const double2 *>(ra + k * NP + 2);
+                                      a23 = *reinterpret_cast<const double2 *>(ra + k * NP + 2 * NB);
                         const double2 b01 = *reinterpret_cast<const double2 *>(rb + k * NP),
-                                      b23 = *reinterpret_cast<const double2 *>(rb + k * NP + 2);
+                                      b23 = *reinterpret_cast<const double2 *>(rb + k * NP + 2 * NB);
                         const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
@@ -113,15 +149,6 @@ __global__ void __launch_bounds__(RESP_THREADS)
                             for (int v = 0; v < 4; ++v) acc[t][4 * u + v] = fma(a[u], b[v], acc[t][4 * u + v]);
                     }
                 }
-            }
-            if (tid < NP) {
-                double s = 0.0;
-                for (int k = 0; k < RESP_GT; ++k) s = fma(Rt[k * NP + tid], Vt[k], s);
-                bacc += s;
-            } else if (tid == RESP_THREADS - 1) {
-                double s = 0.0;
-                for (int k = 0; k < RESP_GT; ++k) s = fma(Vt[k], Vt[k], s);
-                cacc += s;
             }
         }
     }
@@ -135,18 +162,18 @@ __global__ void __launch_bounds__(RESP_THREADS)
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const int r = 4 * bi[t] + u, c = 4 * bj[t] + v;
-                    if (r < N && c < N) {
-                        // diagonal micro-tiles hold the full 4x4 block; off-diagonal ones fill both triangles
-                        if (bi[t] != bj[t] || r <= c) {
-                            out[(size_t)r * N + c] = acc[t][4 * u + v];
-                            out[(size_t)c * N + r] = acc[t][4 * u + v];
-                        }
+                    if (bi[t] == bj[t] && r > c) continue;  // diagonal micro-tiles hold both triangles: take the upper one
+                    const double val = acc[t][4 * u + v];
+                    if (c < N) {  // r <= c < N: the A block
+                        out[(size_t)r * N + c] = val;
+                        out[(size_t)c * N + r] = val;
+                    } else if (c == N) {
+                        if (r < N) out[(size_t)N * N + r] = val;  // B
+                        else if (r == N) out[(size_t)N * N + N] = val;  // C
                     }
                 }
         }
     }
-    if (tid < N) out[(size_t)N * N + tid] = bacc;
-    if (tid == RESP_THREADS - 1) out[(size_t)N * N + N] = cacc;
 }
 
 __global__ void pm_sum_partials_kernel(const double *__restrict__ partial, int n_partial, long stride, double *__restrict__ out) {
@@ -234,7 +261,7 @@ static int resp_grid_size(long n_items) {
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    long g = (long)n_sm * 4;
+    long g = (long)n_sm * RESP_CTAS_PER_SM;
     if (g > n_items) g = n_items;
     if (g < 1) g = 1;
     return (int)g;
@@ -245,33 +272,75 @@ extern "C" long pm_resp_scratch_doubles(int n_atoms, long n_conf, int n_grid) {
     return (long)resp_grid_size(n_conf * chunks) * ((long)n_atoms * n_atoms + n_atoms + 1);
 }
 
+// Packs the micro-tiles of the upper triangle into warp slots of 32 (see RespPlan).  Returns the number of slots, or -1.
+static int resp_make_plan(int NB, RespPlan *plan, int *n_warps, int *tpt) {
+    struct Sb {
+        std::vector<std::pair<int, int>> tiles;
+    };
+    std::vector<Sb> sbs;
+    for (int I = 0; 4 * I < NB; ++I)
+        for (int J = 0; 8 * J < NB; ++J) {
+            Sb sb;
+            for (int r = 4 * I; r < 4 * I + 4 && r < NB; ++r)
+                for (int c = 8 * J; c < 8 * J + 8 && c < NB; ++c)
+                    if (r <= c) sb.tiles.push_back({r, c});
+            if (!sb.tiles.empty()) sbs.push_back(sb);
+        }
+    std::stable_sort(sbs.begin(), sbs.end(), [](const Sb &x, const Sb &y) { return x.tiles.size() > y.tiles.size(); });
+    std::vector<std::vector<std::pair<int, int>>> slots;  // first-fit decreasing
+    for (const Sb &sb : sbs) {
+        size_t s = 0;
+        while (s < slots.size() && slots[s].size() + sb.tiles.size() > 32) ++s;
+        if (s == slots.size()) slots.emplace_back();
+        slots[s].insert(slots[s].end(), sb.tiles.begin(), sb.tiles.end());
+    }
+    const int ns = (int)slots.size();
+    if (ns > RESP_MAX_TPT * RESP_MAX_WARPS) return -1;
+    const int per = (ns + RESP_MAX_WARPS - 1) / RESP_MAX_WARPS;  // tiles per thread
+    const int W = (ns + per - 1) / per;                          // warps per CTA
+    memset(plan->bi, 0xFF, sizeof(plan->bi));
+    memset(plan->bj, 0, sizeof(plan->bj));
+    for (int s = 0; s < ns; ++s) {
+        const int t = s / W, w = s % W;
+        for (size_t l = 0; l < slots[s].size(); ++l) {
+            const int e = t * W * 32 + w * 32 + (int)l;
+            plan->bi[e] = (unsigned char)slots[s][l].first;
+            plan->bj[e] = (unsigned char)slots[s][l].second;
+        }
+    }
+    *n_warps = W;
+    *tpt = per;
+    return ns;
+}
+
 extern "C" int pm_resp_assemble(int n_atoms, const double *coords_dev, const double *grid_dev, const double *vref_dev,
                                 const double *wt_dev, long n_conf, int n_grid, double *out_dev, double *scratch_dev, void *stream) {
     if (!coords_dev || !grid_dev || !vref_dev || !out_dev || !scratch_dev) return pm_fail_msg("pm_resp_assemble: null argument");
     if (n_atoms < 1 || n_conf < 1 || n_grid < 1) return pm_fail_msg("pm_resp_assemble: empty problem");
-    const int N = n_atoms, NP = (N + 3) & ~3, NB = NP / 4, n_tri = NB * (NB + 1) / 2;
-    const int tpt = (n_tri + RESP_THREADS - 1) / RESP_THREADS;
-    if (tpt > 4) return pm_fail_msg("pm_resp_assemble: more than 124 atoms is not supported by this kernel generation");
+    const int N = n_atoms, NP = (N + 1 + 3) & ~3, NB = NP / 4;
+    RespPlan plan;
+    int W = 0, tpt = 0;
+    if (NB > 255 || resp_make_plan(NB, &plan, &W, &tpt) < 0)
+        return pm_fail_msg("pm_resp_assemble: too many atoms for this kernel generation (the limit is about 160)");
     const int chunks = (n_grid + RESP_CHUNK - 1) / RESP_CHUNK;
     const long n_items = n_conf * chunks;
     const int gridsz = resp_grid_size(n_items);
-    const size_t smem = sizeof(double) * (((3 * N + 1) & ~1) + (size_t)RESP_GT * NP + RESP_GT);
+    const size_t smem = sizeof(double) * (((3 * N + 1) & ~1) + 4 * RESP_GT + (size_t)RESP_GT * NP);
     const long stride = (long)N * N + N + 1;
     cudaStream_t st = (cudaStream_t)stream;
+#define RESP_LAUNCH(K)                                                                                                        \
+    do {                                                                                                                      \
+        if (smem > 48 * 1024) PMF_CUDA(cudaFuncSetAttribute(pm_resp_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pm_resp_kernel<K><<<gridsz, W * 32, smem, st>>>(plan, N, coords_dev, grid_dev, vref_dev, wt_dev, n_conf, n_grid, n_items, \
+                                                       chunks, scratch_dev);                                                  \
+    } while (0)
     switch (tpt) {
-        case 1:
-            pm_resp_kernel<1><<<gridsz, RESP_THREADS, smem, st>>>(N, coords_dev, grid_dev, vref_dev, wt_dev, n_conf, n_grid, n_items,
-                                                                chunks, scratch_dev);
-            break;
-        case 2:
-            pm_resp_kernel<2><<<gridsz, RESP_THREADS, smem, st>>>(N, coords_dev, grid_dev, vref_dev, wt_dev, n_conf, n_grid, n_items,
-                                                                chunks, scratch_dev);
-            break;
-        default:
-            pm_resp_kernel<4><<<gridsz, RESP_THREADS, smem, st>>>(N, coords_dev, grid_dev, vref_dev, wt_dev, n_conf, n_grid, n_items,
-                                                                chunks, scratch_dev);
-            break;
+        case 1: RESP_LAUNCH(1); break;
+        case 2: RESP_LAUNCH(2); break;
+        case 3: RESP_LAUNCH(3); break;
+        default: RESP_LAUNCH(4); break;
     }
+#undef RESP_LAUNCH
     PMF_CUDA(cudaGetLastError());
     pm_sum_partials_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(scratch_dev, gridsz, stride, out_dev);
     PMF_CUDA(cudaGetLastError());

@@ -1,0 +1,6 @@
+#!/bin/bash
+# scripts/build_variant.sh <name> [-DFLAG=..]...  ->  build/lib<name>.so  (A/B builds; select with PARAMOL_B200_LIB)
+name=$1; shift
+mkdir -p build
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared "$@" \
+  paramol_b200/csrc/pm_kernels.cu paramol_b200/csrc/pm_fit_kernels.cu -o build/lib$name.so

@@ -200,3 +200,50 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
         got = lls._parameters
         assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max(), np.abs(got - want).max()
         assert len(fitted) == len(x_before)
+
+
+@pytest.mark.parametrize("n_atoms,n_grid,n_conf", [(1, 5, 3), (3, 33, 4), (14, 600, 3), (31, 64, 5), (59, 77, 4), (60, 513, 3),
+                                                   (63, 40, 3), (64, 100, 2), (97, 130, 3), (131, 70, 2), (160, 45, 2)])
+def test_resp_assemble_sizes_vs_numpy(n_atoms, n_grid, n_conf):
+    """pm_resp_assemble through the C ABI for atom counts on both sides of every tiling boundary (micro-tile padding, number of
+    warps, micro-tiles per thread) and grid sizes that leave partial tiles and partial chunks, against numpy."""
+    import ctypes
+    import torch
+    from paramol_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(100 * n_atoms + n_grid)
+    X = rng.normal(0, 3.0, (n_conf, n_atoms, 3))
+    Gd = rng.normal(0, 3.0, (n_conf, n_grid, 3)) + 12.0 * np.sign(rng.normal(size=(n_conf, n_grid, 3)))
+    V = rng.normal(0, 0.1, (n_conf, n_grid))
+    w = rng.uniform(0.2, 1.0, n_conf)
+    R = 1.0 / np.linalg.norm(X[:, :, None, :] - Gd[:, None, :, :], axis=3)      # [m][j][i]
+    A_want = np.einsum("m,mji,mki->jk", w, R, R)
+    B_want = np.einsum("m,mji,mi->j", w, R, V)
+    C_want = float(np.einsum("m,mi,mi->", w, V, V))
+    dev = torch.device("cuda:0")
+    xd, gd, vd, wd = (torch.from_numpy(a).to(dev) for a in (X, Gd, V, w))
+    out = torch.empty(n_atoms * n_atoms + n_atoms + 1, dtype=torch.float64, device=dev)
+    scratch = torch.empty(int(L.pm_resp_scratch_doubles(n_atoms, n_conf, n_grid)), dtype=torch.float64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for wt, scale in ((wd, 1.0), (None, None)):
+        _lib.check(L.pm_resp_assemble(n_atoms, xd.data_ptr(), gd.data_ptr(), vd.data_ptr(), wt.data_ptr() if wt is not None else None,
+                                      n_conf, n_grid, out.data_ptr(), scratch.data_ptr(), stream), "pm_resp_assemble")
+        host = out.cpu().numpy()
+        A, B, C = host[:n_atoms * n_atoms].reshape(n_atoms, n_atoms), host[n_atoms * n_atoms:-1], host[-1]
+        if wt is None:
+            A_want = np.einsum("mji,mki->jk", R, R)
+            B_want = np.einsum("mji,mi->j", R, V)
+            C_want = float(np.einsum("mi,mi->", V, V))
+        assert np.array_equal(A, A.T)
+        assert np.abs(A - A_want).max() <= 1e-12 * np.abs(A_want).max()
+        assert np.abs(B - B_want).max() <= 1e-12 * max(np.abs(B_want).max(), np.abs(A_want).max() * 0.1)
+        assert abs(C - C_want) <= 1e-12 * abs(C_want)
+
+
+def test_resp_assemble_rejects_oversize():
+    import torch
+    from paramol_b200 import _lib
+    L = _lib.lib()
+    d = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+    assert L.pm_resp_assemble(400, d.data_ptr(), d.data_ptr(), d.data_ptr(), None, 1, 1, d.data_ptr(), d.data_ptr(), None) != 0
+    assert b"too many atoms" in L.pm_last_error()
