@@ -10,7 +10,7 @@
 //       pm_lls_columns     design-matrix columns 1/2 (q - q0)^2 and 1 + cos(n phi - delta)  (least_square.py:492-645)
 //
 // All FP64 (the reference is numpy float64 throughout).  The RESP kernel is a batched rank-G update of an N x N matrix:
-// each CTA keeps its share of the accumulators in registers (4x4 micro-tiles of the upper triangle per thread) across all
+// each CTA keeps the accumulators of the upper triangle in registers (8x8 DMMA tiles, two tile rows per warp) across all
 // the (conformation, grid chunk) work items it processes and writes ONE partial at the end; a second kernel sums the
 // partials in a fixed order (deterministic, no atomics).
 #include <cuda_runtime.h>
@@ -35,143 +35,218 @@ int pm_fail_msg(const std::string &msg);  // pm_kernels.cu
         if (_e != cudaSuccess) return pm_fail_msg(std::string(#call) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-#ifndef RESP_CTAS_PER_SM
-#define RESP_CTAS_PER_SM 4
+#define RESP_GT 32          // grid points per shared-memory tile (8 DMMA k-steps of 4)
+#define RESP_CHUNK 512      // grid points per work item
+#define RESP_MAX_CTAS_PER_SM 6
+#ifndef RESP_SKIP_GEN
+#define RESP_SKIP_GEN 0  // timing experiments only
 #endif
-#define RESP_MAX_WARPS 8   // warps per CTA
-#define RESP_MAX_TPT 4     // 4x4 micro-tiles per thread
-#define RESP_GT 32         // grid points per shared-memory tile
-#define RESP_CHUNK 512     // grid points per work item
+#ifndef RESP_SKIP_UPD
+#define RESP_SKIP_UPD 0
+#endif
+#ifndef RESP_GEN_UNROLL
+#define RESP_GEN_UNROLL 4
+#endif
+constexpr int kRespGenUnroll = RESP_GEN_UNROLL;
+#ifndef RESP_WARPS_PER_SM
+#define RESP_WARPS_PER_SM 20  // resident warps per SM the variants for up to 63 atoms are compiled for (register cap 96)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K5
 // ---------------------------------------------------------------------------------------------------------------------
-// Which 4x4 micro-tile of the upper triangle of the padded (N+1) x (N+1) matrix every thread owns.  Built on the host
-// (resp_make_plan): micro-tiles are grouped by 4 x 8 super-blocks and packed 32 to a warp, so that the 32 lanes of a warp read
-// at most ~8 distinct 32-byte row pieces and ~8 distinct column pieces of R per grid point -- shared-memory traffic, which
-// bounded the first version of this kernel, drops to ~4 wavefronts per 16 warp-wide DFMAs.
-struct RespPlan {
-    unsigned char bi[RESP_MAX_TPT * RESP_MAX_WARPS * 32];  // 0xFF = no tile
-    unsigned char bj[RESP_MAX_TPT * RESP_MAX_WARPS * 32];
-};
+// A = sum R R^T is a symmetric rank-k update, so it runs on the FP64 tensor-core path: mma.sync m8n8k4 (SASS DMMA.8x8x4), which
+// on B200 has the same peak as scalar DFMA (measured 37.1 TFLOP/s both, scripts/micro/dmma.cu) but needs one operand double per
+// lane per 8x8x4 product instead of eight per 16 FMAs -- the scalar 4x4 register-tile version of this kernel was bound by
+// shared-memory bandwidth, not by the FP64 pipe.
+//
+// The padded matrix ((N+1) rows: N atoms + the reference potential V as an extra row, so that column N of the product is
+// B = sum R V and entry [N][N] is C = sum V.V) is cut into 8x8 tiles; only tiles (I, J >= I) are computed.  Warp u of a k-slice
+// owns tile rows i0 = u and i1 = NB8-1-u (a short row paired with a long one: every warp has NB8+1 tiles), keeps their
+// accumulators in registers for the whole kernel and walks the columns from the right, so that one B fragment feeds both rows
+// and all register indices are static.  For both operands the fragment of tile row I at k-step k4 is
+// Rt[4 k4 + (lane & 3)][8 I + (lane >> 2)]; the row stride of Rt is = 4 (mod 8) doubles, which makes that load conflict-free.
+__device__ __forceinline__ void pm_dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
-// R is kept in shared memory as Rt[k][half][block][2]: element j of grid point k lives at rt_off(j); the two 16-byte halves
-// of a micro-tile row piece are then contiguous across neighbouring blocks (conflict-free LDS.128).
-__device__ __forceinline__ int rt_off(int j, int NB) { return ((j >> 1) & 1) * (2 * NB) + 2 * (j >> 2) + (j & 1); }
-
-// The reference potential V rides along as an extra "atom row" (row N of the padded R tile), so that the same rank-32 update
-// that forms A = sum R R^T also yields B = sum R V (column N) and C = sum V.V (entry [N][N]).
-template <int TPT>
-__global__ void __launch_bounds__(RESP_MAX_WARPS * 32)
-    pm_resp_kernel(const __grid_constant__ RespPlan plan, int N, const double *__restrict__ coords, const double *__restrict__ grid,
-                   const double *__restrict__ vref, const double *__restrict__ wt, long S, int G, long n_items, int chunks_per_conf,
-                   double *__restrict__ partial) {
-    const int NP = (N + 1 + 3) & ~3, NB = NP >> 2;  // N atom rows + the V row, padded to a multiple of 4
-    extern __shared__ __align__(16) double sm[];
-    double *xs = sm;                       // [N][3]
-    double *gs = xs + ((3 * N + 1) & ~1);  // [RESP_GT][4]: grid point (x, y, z) and sqrt(w) V
-    double *Rt = gs + 4 * RESP_GT;         // [RESP_GT][NP]
-    const int tid = threadIdx.x, T = blockDim.x;
-
-    int bi[TPT], bj[TPT];
+// Writes (first) or adds one 8x8 accumulator tile into a CTA's partial [N*N A | N B | C]; kept out of line so that the unrolled
+// epilogue does not inflate the register budget of the main loop.
+__device__ __noinline__ void pm_resp_emit(double c0, double c1, int I, int J, bool first, double *__restrict__ out, int N, int lane) {
+    const int r = 8 * I + (lane >> 2);
 #pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-        const int e = t * T + tid;
-        bi[t] = plan.bi[e] == 0xFF ? -1 : plan.bi[e];
-        bj[t] = plan.bj[e];
-    }
-    double acc[TPT][16];
-#pragma unroll
-    for (int t = 0; t < TPT; ++t)
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[t][e] = 0.0;
-
-    // generation: thread -> (row j, grid-point group kg); with T >= NP every thread keeps one row, else rows are strided
-    const int kgroups = T >= NP ? T / NP : 1;
-    const int j0 = T >= NP ? tid % NP : tid, kg = T >= NP ? tid / NP : 0, jstride = T >= NP ? NP : T;
-    const bool gen_active = kg < kgroups;
-
-    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const long m = item / chunks_per_conf;
-        const int g0 = (int)(item - m * chunks_per_conf) * RESP_CHUNK;
-        const int g1 = min(G, g0 + RESP_CHUNK);
-        const double sw = wt ? sqrt(wt[m]) : 1.0;
-        __syncthreads();
-        for (int i = tid; i < 3 * N; i += T) xs[i] = coords[(size_t)m * 3 * N + i];
-        const double *gm = grid + (size_t)m * 3 * G;
-        const double *vm = vref + (size_t)m * G;
-        for (int t0 = g0; t0 < g1; t0 += RESP_GT) {
-            __syncthreads();  // previous update done with Rt / gs
-            const int nk = min(RESP_GT, g1 - t0);
-            if (tid < RESP_GT) {
-                const bool in = tid < nk;
-                double4 g4;
-                g4.x = in ? gm[3 * (t0 + tid)] : 0.0;
-                g4.y = in ? gm[3 * (t0 + tid) + 1] : 0.0;
-                g4.z = in ? gm[3 * (t0 + tid) + 2] : 0.0;
-                g4.w = in ? sw * vm[t0 + tid] : 0.0;
-                *reinterpret_cast<double2 *>(gs + 4 * tid) = make_double2(g4.x, g4.y);
-                *reinterpret_cast<double2 *>(gs + 4 * tid + 2) = make_double2(g4.z, g4.w);
-            }
-            __syncthreads();
-            if (gen_active) {
-                for (int j = j0; j < NP; j += jstride) {
-                    double *dst = Rt + rt_off(j, NB);
-                    if (j < N) {
-                        const double xj = xs[3 * j], yj = xs[3 * j + 1], zj = xs[3 * j + 2];
-#pragma unroll 4
-                        for (int k = kg; k < RESP_GT; k += kgroups) {
-                            const double2 gxy = *reinterpret_cast<const double2 *>(gs + 4 * k);
-                            const double dx = xj - gxy.x, dy = yj - gxy.y, dz = zj - gs[4 * k + 2];
-                            const double r = sw * pm_rsqrt(fma(dz, dz, fma(dy, dy, dx * dx)));
-                            dst[k * NP] = k < nk ? r : 0.0;
-                        }
-                    } else {
-                        for (int k = kg; k < RESP_GT; k += kgroups) dst[k * NP] = j == N ? gs[4 * k + 3] : 0.0;
-                    }
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int t = 0; t < TPT; ++t) {
-                if (bi[t] >= 0) {
-                    const double *ra = Rt + 2 * bi[t], *rb = Rt + 2 * bj[t];
-#pragma unroll 4
-                    for (int k = 0; k < RESP_GT; ++k) {
-                        const double2 a01 = *reinterpret_cast<const double2 *>(ra + k * NP),
-                                      a23 = *reinterpret_cast<const double2 *>(ra + k * NP + 2 * NB);
-                        const double2 b01 = *reinterpret_cast<const double2 *>(rb + k * NP),
-                                      b23 = *reinterpret_cast<const double2 *>(rb + k * NP + 2 * NB);
-                        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) acc[t][4 * u + v] = fma(a[u], b[v], acc[t][4 * u + v]);
-                    }
-                }
-            }
+    for (int e = 0; e < 2; ++e) {
+        const int col = 8 * J + 2 * (lane & 3) + e;
+        if (r > col) continue;  // lower part of a diagonal tile
+        double *p0 = nullptr, *p1 = nullptr;
+        if (col < N) {
+            p0 = out + (size_t)r * N + col;
+            if (r != col) p1 = out + (size_t)col * N + r;
+        } else if (col == N) {
+            p0 = out + (size_t)N * N + r;  // r < N: B[r];  r == N: C
+        }
+        if (p0) {
+            const double c = e ? c1 : c0;
+            const double v = first ? c : *p0 + c;
+            *p0 = v;
+            if (p1) *p1 = v;
         }
     }
-    // one partial per CTA: [N*N] A (both triangles), [N] B, [1] C
-    double *out = partial + (size_t)blockIdx.x * ((size_t)N * N + N + 1);
+}
+
+template <int NB8, int KS>  // NB8 8-wide tile columns ((N + 1) padded to 8 * NB8 rows); KS k-slices (warps per tile row pair)
+__global__ void __launch_bounds__(32 * ((NB8 + 1) / 2) * KS, NB8 <= 8 ? RESP_WARPS_PER_SM / (((NB8 + 1) / 2) * KS) : 1)
+    pm_resp_kernel(int N, const double *__restrict__ coords, const double *__restrict__ grid, const double *__restrict__ vref,
+                   const double *__restrict__ wt, long S, int G, long n_items, int chunks_per_conf, double *__restrict__ partial) {
+    constexpr int NP = 8 * NB8, RS = NP + 4, NS = NB8 + 1;  // NS accumulator tiles ("slots") per warp
+    constexpr int U = (NB8 + 1) / 2;                        // warps per k-slice
+    const int XS = (3 * N + 1) & ~1;
+    extern __shared__ __align__(16) double sm[];
+    double *xs = sm;                       // [2][XS]          atom coordinates / sqrt(w), double-buffered over work items
+    double *gs = xs + 2 * XS;              // [2][RESP_GT][4]  grid point (x, y, z)/sqrt(w) and sqrt(w) V, double-buffered over steps
+    double *Rt = gs + 2 * 4 * RESP_GT;     // [2][RESP_GT][RS] the R tile, double-buffered over steps
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int ks = warp / U, u = warp - ks * U;
+    // Slot s < len0 is tile (i0, NB8-1-s); slot s >= len0 is tile (i1, NB8-1-(s-len0)).  For the middle row of an odd NB8
+    // (i1 == i0) the second half of the slots is fed zeros and never written out.
+    const int i0 = u, i1 = NB8 - 1 - u;
+    const int len0 = NB8 - i0;
+    const bool has1 = i1 > i0;
+
+    double acc[NS][2];
 #pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-        if (bi[t] >= 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int r = 4 * bi[t] + u, c = 4 * bj[t] + v;
-                    if (bi[t] == bj[t] && r > c) continue;  // diagonal micro-tiles hold both triangles: take the upper one
-                    const double val = acc[t][4 * u + v];
-                    if (c < N) {  // r <= c < N: the A block
-                        out[(size_t)r * N + c] = val;
-                        out[(size_t)c * N + r] = val;
-                    } else if (c == N) {
-                        if (r < N) out[(size_t)N * N + r] = val;  // B
-                        else if (r == N) out[(size_t)N * N + N] = val;  // C
+    for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = 0.0;
+
+    // generation: thread -> (atom row j, grid-point group kg); rows are strided when there are more rows than threads
+    const int kgroups = T >= N ? T / N : 1;
+    const int j0 = T >= N ? tid % N : tid, kg = T >= N ? tid / N : 0, jstride = T >= N ? N : T;
+    const bool gen_active = kg < kgroups;
+    const int frag_off = (lane & 3) * RS + (lane >> 2);
+
+    // A work item is (conformation m, chunk of RESP_CHUNK grid points); a step is RESP_GT grid points of an item.  Items whose
+    // weight is (numerically) zero are skipped; the scaling by 1/sqrt(w) of both coordinate sets makes rsqrt return sqrt(w)/r.
+    auto next_item = [&](long it) {
+        for (; it < n_items; it += gridDim.x) {
+            const double w = wt ? wt[it / chunks_per_conf] : 1.0;
+            if (!(w < 1e-280)) break;  // NaN weights are processed (and poison the sums, as they do in the reference)
+        }
+        return it;
+    };
+    auto stage_x = [&](long it, int xb) {
+        const long m = it / chunks_per_conf;
+        const double isw = wt ? 1.0 / sqrt(wt[m]) : 1.0;
+        for (int i = tid; i < 3 * N; i += T) xs[xb * XS + i] = isw * coords[(size_t)m * 3 * N + i];
+    };
+    // threads 0..RESP_GT-1 fetch one grid point each (raw values: nothing may depend on the loads yet) ...
+    auto load_g = [&](long it, int t0, double (&r)[4]) {
+        const long m = it / chunks_per_conf;
+        const int g1 = min(G, ((int)(it - m * chunks_per_conf) + 1) * RESP_CHUNK);
+        const int i = min(t0 + tid, g1 - 1);
+        const double *gp = grid + ((size_t)m * G + i) * 3;
+        r[0] = gp[0];
+        r[1] = gp[1];
+        r[2] = gp[2];
+        r[3] = vref[(size_t)m * G + i];
+    };
+    // ... and publish it, scaled, after the loads have had a generation phase to land; points beyond the chunk are pushed
+    // 1e150 away (R = 0 for them)
+    auto store_g = [&](long it, int t0, const double (&r)[4], int gb) {
+        const long m = it / chunks_per_conf;
+        const int g1 = min(G, ((int)(it - m * chunks_per_conf) + 1) * RESP_CHUNK);
+        const double w = wt ? wt[m] : 1.0, sw = sqrt(w), isw = 1.0 / sw;
+        const bool in = t0 + tid < g1;
+        double *d = gs + gb * 4 * RESP_GT + 4 * tid;
+        *reinterpret_cast<double2 *>(d) = make_double2(in ? isw * r[0] : 1e150, in ? isw * r[1] : 1e150);
+        *reinterpret_cast<double2 *>(d + 2) = make_double2(in ? isw * r[2] : 1e150, in ? sw * r[3] : 0.0);
+    };
+
+    for (int i = tid; i < 2 * RESP_GT * RS; i += T) Rt[i] = 0.0;  // the padding rows stay zero for the whole kernel
+    long item = next_item(blockIdx.x);
+    int t0 = 0, g1 = 0, xb = 0, b = 0;
+    if (item < n_items) {
+        const long m = item / chunks_per_conf;
+        t0 = (int)(item - m * chunks_per_conf) * RESP_CHUNK;
+        g1 = min(G, t0 + RESP_CHUNK);
+        stage_x(item, 0);
+        if (tid < RESP_GT) {
+            double r[4];
+            load_g(item, t0, r);
+            store_g(item, t0, r, 0);
+        }
+    }
+    __syncthreads();
+    while (item < n_items) {
+        // where the next step is; its grid points are requested now and stored after the generation phase
+        long n_item = item;
+        int n_t0 = t0 + RESP_GT, n_g1 = g1;
+        if (n_t0 >= g1) {
+            n_item = next_item(item + gridDim.x);
+            if (n_item < n_items) {
+                const long m = n_item / chunks_per_conf;
+                n_t0 = (int)(n_item - m * chunks_per_conf) * RESP_CHUNK;
+                n_g1 = min(G, n_t0 + RESP_CHUNK);
+            }
+        }
+        double gnext[4];
+        if (n_item < n_items && tid < RESP_GT) load_g(n_item, n_t0, gnext);
+        // (A) generate the R tile of this step: atom rows by everybody, the V row by the first warp
+        {
+            const double *g = gs + b * 4 * RESP_GT, *x = xs + xb * XS;
+            double *rt = Rt + b * RESP_GT * RS;
+            if (gen_active && !RESP_SKIP_GEN) {
+#pragma unroll 1
+                for (int j = j0; j < N; j += jstride) {
+                    double *dst = rt + j;
+                    const double xj = x[3 * j], yj = x[3 * j + 1], zj = x[3 * j + 2];
+#pragma unroll kRespGenUnroll
+                    for (int k = kg; k < RESP_GT; k += kgroups) {
+                        const double2 gxy = *reinterpret_cast<const double2 *>(g + 4 * k);
+                        const double dx = xj - gxy.x, dy = yj - gxy.y, dz = zj - g[4 * k + 2];
+                        dst[k * RS] = pm_rsqrt(fma(dz, dz, fma(dy, dy, dx * dx)));  // = sqrt(w) / |x - g|
                     }
                 }
+            }
+            if (tid < RESP_GT) rt[tid * RS + N] = g[4 * tid + 3];
+        }
+        // (B) stage the inputs of the next step into the other buffers
+        if (n_item < n_items) {
+            if (n_item != item) stage_x(n_item, xb ^ 1);
+            if (tid < RESP_GT) store_g(n_item, n_t0, gnext, b ^ 1);
+        }
+        __syncthreads();
+        // (C) rank-RESP_GT update of this warp's two tile rows
+        // Every warp issues exactly NS unguarded DMMAs per k-step (a predicated-off DMMA costs as much as a live one:
+        // scripts/micro/dmma3.cu); which of its two A fragments and which column a slot uses is warp-uniform arithmetic.
+        if (!RESP_SKIP_UPD) {
+            constexpr int Q = (RESP_GT / 4) / KS;  // k-steps of this warp per tile
+            const double *fb0 = Rt + b * RESP_GT * RS + frag_off + 4 * ks * RS;
+#pragma unroll NB8 <= 8 ? 2 : 1
+            for (int q = 0; q < Q; ++q) {
+                const double *fb = fb0 + 4 * KS * RS * q;
+                const double a0 = fb[8 * i0], a1 = has1 ? fb[8 * i1] : 0.0;
+                double bf[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) bf[s] = fb[8 * (NB8 - 1 - s) + (s >= len0 ? 8 * len0 : 0)];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) pm_dmma(acc[s], s >= len0 ? a1 : a0, bf[s]);
+            }
+        }
+        if (n_item != item) xb ^= 1;
+        item = n_item;
+        t0 = n_t0;
+        g1 = n_g1;
+        b ^= 1;
+    }
+    // one partial per CTA: [N*N] A (both triangles), [N] B, [1] C.  The k-slices add theirs one after the other (fixed order).
+    double *out = partial + (size_t)blockIdx.x * ((size_t)N * N + N + 1);
+    for (int round = 0; round < KS; ++round) {
+        if (round) __syncthreads();
+        if (ks == round) {
+#pragma unroll
+            for (int sl = 0; sl < NS; ++sl) {
+                const bool second = sl >= len0;
+                if (!second || has1) pm_resp_emit(acc[sl][0], acc[sl][1], second ? i1 : i0, NB8 - 1 - (second ? sl - len0 : sl), round == 0, out, N, lane);
+            }
         }
     }
 }
@@ -257,92 +332,66 @@ __global__ void pm_lls_columns_kernel(const double *__restrict__ q, long S, int 
 // ---------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------------
-static int resp_grid_size(long n_items) {
-    int dev = 0, n_sm = 148;
+struct RespLaunch {
+    int ks, threads, grid;
+    size_t smem;
+    const void *fn;
+};
+
+// Launch geometry for an N-atom problem (independent of the data, so that pm_resp_scratch_doubles can size the partials).
+static int resp_launch(int N, long n_items, RespLaunch *L) {
+    const int NP = (N + 1 + 7) & ~7, NB8 = NP / 8, U = (NB8 + 1) / 2;
+    if (NB8 > 22) return -1;
+    L->ks = U >= 4 ? 1 : U == 1 ? 4 : 2;  // small molecules: split the 8 k-steps of a tile over several warps per tile row
+    L->threads = 32 * U * L->ks;
+    L->smem = sizeof(double) * 2 * (((3 * N + 1) & ~1) + 4 * RESP_GT + (size_t)RESP_GT * (NP + 4));
+    switch (NB8) {
+#define RESP_CASE(B, K) case B: L->fn = (const void *)pm_resp_kernel<B, K>; break;
+        RESP_CASE(1, 4) RESP_CASE(2, 4) RESP_CASE(3, 2) RESP_CASE(4, 2) RESP_CASE(5, 2) RESP_CASE(6, 2) RESP_CASE(7, 1) RESP_CASE(8, 1)
+        RESP_CASE(9, 1) RESP_CASE(10, 1) RESP_CASE(11, 1) RESP_CASE(12, 1) RESP_CASE(13, 1) RESP_CASE(14, 1) RESP_CASE(15, 1)
+        RESP_CASE(16, 1) RESP_CASE(17, 1) RESP_CASE(18, 1) RESP_CASE(19, 1) RESP_CASE(20, 1) RESP_CASE(21, 1) RESP_CASE(22, 1)
+#undef RESP_CASE
+        default: return -1;
+    }
+    int dev = 0, n_sm = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    long g = (long)n_sm * RESP_CTAS_PER_SM;
+    if (L->smem > 48 * 1024 && cudaFuncSetAttribute(L->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem) != cudaSuccess) return -2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, L->fn, L->threads, L->smem) != cudaSuccess || per_sm < 1) return -2;
+    if (per_sm > RESP_MAX_CTAS_PER_SM) per_sm = RESP_MAX_CTAS_PER_SM;
+    long g = (long)n_sm * per_sm;
     if (g > n_items) g = n_items;
-    if (g < 1) g = 1;
-    return (int)g;
+    L->grid = (int)(g < 1 ? 1 : g);
+    return 0;
 }
 
 extern "C" long pm_resp_scratch_doubles(int n_atoms, long n_conf, int n_grid) {
     const long chunks = (n_grid + RESP_CHUNK - 1) / RESP_CHUNK;
-    return (long)resp_grid_size(n_conf * chunks) * ((long)n_atoms * n_atoms + n_atoms + 1);
-}
-
-// Packs the micro-tiles of the upper triangle into warp slots of 32 (see RespPlan).  Returns the number of slots, or -1.
-static int resp_make_plan(int NB, RespPlan *plan, int *n_warps, int *tpt) {
-    struct Sb {
-        std::vector<std::pair<int, int>> tiles;
-    };
-    std::vector<Sb> sbs;
-    for (int I = 0; 4 * I < NB; ++I)
-        for (int J = 0; 8 * J < NB; ++J) {
-            Sb sb;
-            for (int r = 4 * I; r < 4 * I + 4 && r < NB; ++r)
-                for (int c = 8 * J; c < 8 * J + 8 && c < NB; ++c)
-                    if (r <= c) sb.tiles.push_back({r, c});
-            if (!sb.tiles.empty()) sbs.push_back(sb);
-        }
-    std::stable_sort(sbs.begin(), sbs.end(), [](const Sb &x, const Sb &y) { return x.tiles.size() > y.tiles.size(); });
-    std::vector<std::vector<std::pair<int, int>>> slots;  // first-fit decreasing
-    for (const Sb &sb : sbs) {
-        size_t s = 0;
-        while (s < slots.size() && slots[s].size() + sb.tiles.size() > 32) ++s;
-        if (s == slots.size()) slots.emplace_back();
-        slots[s].insert(slots[s].end(), sb.tiles.begin(), sb.tiles.end());
-    }
-    const int ns = (int)slots.size();
-    if (ns > RESP_MAX_TPT * RESP_MAX_WARPS) return -1;
-    const int per = (ns + RESP_MAX_WARPS - 1) / RESP_MAX_WARPS;  // tiles per thread
-    const int W = (ns + per - 1) / per;                          // warps per CTA
-    memset(plan->bi, 0xFF, sizeof(plan->bi));
-    memset(plan->bj, 0, sizeof(plan->bj));
-    for (int s = 0; s < ns; ++s) {
-        const int t = s / W, w = s % W;
-        for (size_t l = 0; l < slots[s].size(); ++l) {
-            const int e = t * W * 32 + w * 32 + (int)l;
-            plan->bi[e] = (unsigned char)slots[s][l].first;
-            plan->bj[e] = (unsigned char)slots[s][l].second;
-        }
-    }
-    *n_warps = W;
-    *tpt = per;
-    return ns;
+    RespLaunch L;
+    if (n_atoms < 1 || resp_launch(n_atoms, n_conf * chunks, &L) != 0) return 0;
+    return (long)L.grid * ((long)n_atoms * n_atoms + n_atoms + 1);
 }
 
 extern "C" int pm_resp_assemble(int n_atoms, const double *coords_dev, const double *grid_dev, const double *vref_dev,
                                 const double *wt_dev, long n_conf, int n_grid, double *out_dev, double *scratch_dev, void *stream) {
     if (!coords_dev || !grid_dev || !vref_dev || !out_dev || !scratch_dev) return pm_fail_msg("pm_resp_assemble: null argument");
     if (n_atoms < 1 || n_conf < 1 || n_grid < 1) return pm_fail_msg("pm_resp_assemble: empty problem");
-    const int N = n_atoms, NP = (N + 1 + 3) & ~3, NB = NP / 4;
-    RespPlan plan;
-    int W = 0, tpt = 0;
-    if (NB > 255 || resp_make_plan(NB, &plan, &W, &tpt) < 0)
-        return pm_fail_msg("pm_resp_assemble: too many atoms for this kernel generation (the limit is about 160)");
+    int N = n_atoms, G = n_grid;
+    long S = n_conf;
     const int chunks = (n_grid + RESP_CHUNK - 1) / RESP_CHUNK;
-    const long n_items = n_conf * chunks;
-    const int gridsz = resp_grid_size(n_items);
-    const size_t smem = sizeof(double) * (((3 * N + 1) & ~1) + 4 * RESP_GT + (size_t)RESP_GT * NP);
+    long n_items = n_conf * chunks;
+    RespLaunch L;
+    const int rc = resp_launch(N, n_items, &L);
+    if (rc == -1) return pm_fail_msg("pm_resp_assemble: too many atoms for this kernel generation (the limit is 175)");
+    if (rc != 0) return pm_fail_msg(std::string("pm_resp_assemble: launch configuration failed: ") + cudaGetErrorString(cudaGetLastError()));
     const long stride = (long)N * N + N + 1;
     cudaStream_t st = (cudaStream_t)stream;
-#define RESP_LAUNCH(K)                                                                                                        \
-    do {                                                                                                                      \
-        if (smem > 48 * 1024) PMF_CUDA(cudaFuncSetAttribute(pm_resp_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pm_resp_kernel<K><<<gridsz, W * 32, smem, st>>>(plan, N, coords_dev, grid_dev, vref_dev, wt_dev, n_conf, n_grid, n_items, \
-                                                       chunks, scratch_dev);                                                  \
-    } while (0)
-    switch (tpt) {
-        case 1: RESP_LAUNCH(1); break;
-        case 2: RESP_LAUNCH(2); break;
-        case 3: RESP_LAUNCH(3); break;
-        default: RESP_LAUNCH(4); break;
-    }
-#undef RESP_LAUNCH
-    PMF_CUDA(cudaGetLastError());
-    pm_sum_partials_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(scratch_dev, gridsz, stride, out_dev);
+    int cpc = chunks;
+    // the partials of CTAs that find all their items weightless must still be defined
+    PMF_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * (size_t)L.grid * stride, st));
+    void *args[] = {&N, &coords_dev, &grid_dev, &vref_dev, &wt_dev, &S, &G, &n_items, &cpc, &scratch_dev};
+    PMF_CUDA(cudaLaunchKernel(L.fn, dim3(L.grid), dim3(L.threads), args, L.smem, st));
+    pm_sum_partials_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(scratch_dev, L.grid, stride, out_dev);
     PMF_CUDA(cudaGetLastError());
     return 0;
 }

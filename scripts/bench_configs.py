@@ -124,9 +124,15 @@ def config5(S=50_000, G=500, N=60):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
-    flops = 2.0 * S * G * N * N + 2.0 * S * G * N + 12.0 * S * G * N
+    flops = 2.0 * S * G * N * N + 2.0 * S * G * N + 12.0 * S * G * N  # SURVEY count: full N x N product, B, inverse distances
+    # what the kernel executes: 8x8 DMMA tiles of the upper triangle of the (N+1)-row matrix over grid tiles of 32, + 11 FP64
+    # operations (22 flops) per generated inverse distance
+    nb8, gpad = (N + 1 + 7) // 8, (G + 31) // 32 * 32
+    executed = S * gpad * (2.0 * 64 * nb8 * (nb8 + 1) / 2 + 22.0 * N)
     return dict(config=5, workload="RESP N=%d, G=%d grid points x S=%d conformations" % (N, G, S), assemble_ms=ms,
-                assemble_tflops=flops / (ms * 1e-3) / 1e12, conformations_per_s=S / (ms * 1e-3), esp_potential_ms=ms_pot,
+                assemble_tflops=flops / (ms * 1e-3) / 1e12, executed_tflops=executed / (ms * 1e-3) / 1e12,
+                fp64_peak_tflops=37.1, executed_frac_of_fp64_peak=executed / (ms * 1e-3) / 1e12 / 37.1,
+                conformations_per_s=S / (ms * 1e-3), esp_potential_ms=ms_pot,
                 bytes_per_conformation=24 * N + 32 * G, hbm_GB_s=S * (24 * N + 32 * G) / (ms * 1e-3) / 1e9)
 
 
