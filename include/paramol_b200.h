@@ -153,6 +153,23 @@ int pm_resp_assemble(int n_atoms, const double *coords_dev, const double *grid_d
 int pm_esp_potential(int n_atoms, const double *coords_dev, const double *grid_dev, const double *charges_dev,
                      long n_conf, int n_grid, double *vmm_dev, void *stream);
 
+/* ---- analytic parameter gradient ---------------------------------------------------------------------- */
+/* d f / d p for ONE parameter vector, where f = sum_s [ g(E_s) + b_s sum_a (F_sa - Fref_sa)^T M_a (F_sa - Fref_sa) ]:
+ * the caller passes a_s = d f / d E_s (coef_e_dev [S], or NULL when the objective has no energy part) and b_s (coef_f_dev [S],
+ * or NULL; needs the MM force tiles written by pm_eval(..., fmm_tiles_dev) and the reference force tiles).  The reference
+ * has no counterpart: it differences ObjectiveFunction.f (scipy jac="2-point", ParaMol/Utils/settings.py:64;
+ * ParaMol/Optimizers/gradient_descent.py:106-121); this replaces those P_opt + 1 evaluations of
+ * ParaMol/Objective_function/objective_function.py:231-359 with one pass.
+ * gout_dev [pm_grad_out_doubles(h)] = bonds (d/d r0, d/d k), angles (d/d theta0, d/d k), torsions (d/d phase, d/d k),
+ * pairs in pm_get_pairs order (d/d c12, d/d c6, d/d (K qq)) with c12 = 4 eps sigma^12, c6 = 4 eps sigma^6 as in the derived
+ * table of pm_prepare_params.  scratch_dev: pm_grad_scratch_doubles(h) doubles.  Deterministic (no atomics).
+ * Fails for the cutoff / reaction-field variant. */
+long pm_grad_out_doubles(pm_handle h);
+long pm_grad_scratch_doubles(pm_handle h);
+int pm_grad(pm_handle h, const double *derived_dev, const double *coord_tiles_dev, const double *fmm_tiles_dev,
+            const double *fref_tiles_dev, long n_conf, const double *coef_e_dev, const double *coef_f_dev, double *gout_dev,
+            double *scratch_dev, void *stream);
+
 /* ---- LLS (K3) ------------------------------------------------------------------------------------- */
 /* Internal coordinates q[S][n_terms] with the conventions of ParaMol/Utils/geometry.py:4-107: kind 0 distance(a0,a1),
  * 1 angle at a1 (arccos of the clipped cosine), 2 dihedral a0-a1-a2-a3 (atan2 form).  atoms [n_terms][4] int32 device. */

@@ -462,6 +462,49 @@ class B200Engine:
             exc[:, :n, 2] = np.abs(store_rows[:, plan["b_scnb"]]) * np.sqrt(eps1 * eps2)
         return slots
 
+    def slots_gradient_to_store(self, force_field, g_slots, store_row, base_slots=None):
+        """
+        Adjoint of :meth:`slots_from_store` at ``store_row`` (sign conventions already applied): maps d f / d slots
+        [n_slots] to d f / d store [len(store)], following the same branches (direct bonded entries, wrapped phases,
+        branch A exceptions rebuilt from the particle parameters, branch B exceptions scaled by scee / scnb).
+        """
+        plan = self.compile_update_plan(force_field)
+        g_slots = np.asarray(g_slots, dtype=np.float64)
+        store_row = np.asarray(store_row, dtype=np.float64).reshape(-1)
+        base = self.current_slots() if base_slots is None else np.asarray(base_slots, dtype=np.float64)
+        g = np.zeros_like(store_row)
+        if len(plan["dst"]):
+            np.add.at(g, plan["src"], g_slots[plan["dst"]])
+        if len(plan["ph_dst"]):
+            np.add.at(g, plan["ph_src"], g_slots[plan["ph_dst"]])   # wrap_phase has unit slope
+        off_part, off_exc = plan["off_part"], plan["off_exc"]
+        if plan["branch"] == "A":
+            np.add.at(g, plan["a_part_src"], g_slots[plan["a_part_dst"]])
+            gexc = g_slots[off_exc:].reshape(-1, 3)
+            if gexc.shape[0]:
+                upd = np.abs(base[off_exc:].reshape(-1, 3)[:, 0]) >= 1e-8
+                q1, q2 = store_row[plan["a_q1"]], store_row[plan["a_q2"]]
+                e1, e2 = store_row[plan["a_e1"]], store_row[plan["a_e2"]]
+                g_qq, g_sig, g_eps = (np.where(upd, gexc[:, c], 0.0) for c in range(3))
+                np.add.at(g, plan["a_q1"], g_qq * self.scnb * q2)
+                np.add.at(g, plan["a_q2"], g_qq * self.scnb * q1)
+                np.add.at(g, plan["a_s1"], 0.5 * g_sig)
+                np.add.at(g, plan["a_s2"], 0.5 * g_sig)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    d1 = np.where(e1 > 0, 0.5 * self.scee * np.sqrt(e2) / np.sqrt(e1), 0.0)
+                    d2 = np.where(e2 > 0, 0.5 * self.scee * np.sqrt(e1) / np.sqrt(e2), 0.0)
+                np.add.at(g, plan["a_e1"], g_eps * d1)
+                np.add.at(g, plan["a_e2"], g_eps * d2)
+        elif plan["branch"] == "B":
+            n = plan["b_n"]
+            part = base[off_part:off_exc].reshape(-1, 3)
+            gexc = g_slots[off_exc:].reshape(-1, 3)
+            chg1, chg2 = part[plan["b_at1"], 0], part[plan["b_at2"], 0]
+            eps1, eps2 = part[plan["b_at1"], 2], part[plan["b_at2"], 2]
+            np.add.at(g, plan["b_scee"], gexc[:n, 0] * chg1 * chg2)
+            np.add.at(g, plan["b_scnb"], gexc[:n, 2] * np.sqrt(eps1 * eps2))
+        return g
+
     def load_slots(self, slots_row):
         """Writes one slots row back into the MM system arrays (keeps ``self.system`` in step with the fast path)."""
         s = self.system

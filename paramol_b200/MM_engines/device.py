@@ -62,6 +62,7 @@ class DeviceTopology:
         self.device = torch.cuda.current_device() if device is None else int(device)
         s = mm_system
         self.n_atoms = int(s.n_atoms)
+        self.k_coul = float(s.one_4pi_eps0)
         self._keep = dict(
             bond=np.ascontiguousarray(s.bond_idx, dtype=np.int32).reshape(-1, 2),
             angle=np.ascontiguousarray(s.angle_idx, dtype=np.int32).reshape(-1, 3),
@@ -159,6 +160,55 @@ class DeviceTopology:
         _lib.check(self._L.pm_unpack_tiles(self._h, tiles.data_ptr(), n_conf, dst.data_ptr(), _stream_ptr(tiles.device)),
                    "pm_unpack_tiles")
         return dst
+
+    def term_gradient_to_slots(self, gout, slots_row):
+        """
+        Chain the kernel's term gradient ``gout`` (numpy [pm_grad_out_doubles]: bonded entries are slot derivatives already,
+        pair entries are d/d(c12, c6, K qq)) back to the slot layout: the adjoint of ``pm_prepare_params`` with
+        c12 = 4 eps sigma^12, c6 = 4 eps sigma^6, plain pairs combined as qq = q_i q_j, sigma = (s_i + s_j)/2,
+        eps = sqrt(e_i e_j) and exceptions carrying their own (qq, sigma, eps).  Returns numpy [n_slots].
+        """
+        gout = np.asarray(gout, dtype=np.float64)
+        slots_row = np.asarray(slots_row, dtype=np.float64)
+        g = np.zeros(self.n_slots)
+        nbond = 2 * (self.n_bonds + self.n_angles + self.n_torsions)
+        g[:nbond] = gout[:nbond]
+        if self.n_pairs == 0:
+            return g
+        if getattr(self, "_pairs_cache", None) is None:
+            self._pairs_cache = self.pairs()
+        pm = self._pairs_cache
+        gp = gout[nbond:nbond + 3 * self.n_pairs].reshape(-1, 3)
+        part = slots_row[self.off_particle:self.off_exception].reshape(-1, 3)
+        exc = slots_row[self.off_exception:].reshape(-1, 3)
+        i, j, e = pm[:, 0], pm[:, 1], pm[:, 2]
+        plain = e < 0
+        sig = np.where(plain, 0.5 * part[i, 1] + 0.5 * part[j, 1], exc[np.maximum(e, 0), 1])
+        eps = np.where(plain, np.sqrt(part[i, 2]) * np.sqrt(part[j, 2]), exc[np.maximum(e, 0), 2])
+        s6 = sig ** 6
+        g_eps = gp[:, 0] * 4.0 * s6 * s6 + gp[:, 1] * 4.0 * s6
+        g_sig = gp[:, 0] * 48.0 * eps * sig ** 11 + gp[:, 1] * 24.0 * eps * sig ** 5
+        g_qq = gp[:, 2] * self.k_coul
+        gpart = np.zeros_like(part)
+        gexc = np.zeros_like(exc)
+        ip, jp = i[plain], j[plain]
+        np.add.at(gpart[:, 0], ip, g_qq[plain] * part[jp, 0])
+        np.add.at(gpart[:, 0], jp, g_qq[plain] * part[ip, 0])
+        np.add.at(gpart[:, 1], ip, 0.5 * g_sig[plain])
+        np.add.at(gpart[:, 1], jp, 0.5 * g_sig[plain])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            # d sqrt(e_i e_j) / d e_i = sqrt(e_j / e_i) / 2; a vanishing epsilon has no finite derivative: report 0
+            di = np.where(part[ip, 2] > 0, 0.5 * np.sqrt(part[jp, 2]) / np.sqrt(part[ip, 2]), 0.0)
+            dj = np.where(part[jp, 2] > 0, 0.5 * np.sqrt(part[ip, 2]) / np.sqrt(part[jp, 2]), 0.0)
+        np.add.at(gpart[:, 2], ip, g_eps[plain] * di)
+        np.add.at(gpart[:, 2], jp, g_eps[plain] * dj)
+        ee = e[~plain]
+        np.add.at(gexc[:, 0], ee, g_qq[~plain])
+        np.add.at(gexc[:, 1], ee, g_sig[~plain])
+        np.add.at(gexc[:, 2], ee, g_eps[~plain])
+        g[self.off_particle:self.off_exception] = gpart.ravel()
+        g[self.off_exception:] = gexc.ravel()
+        return g
 
     def prepare(self, slots_dev, derived_dev=None):
         """slots [P, n_slots] CUDA float64 -> derived [P, n_derived]."""
@@ -296,6 +346,35 @@ class DeviceEnsemble:
                                                partials.data_ptr(), self._scratch.data_ptr(), _stream_ptr(self.device)),
                    "pm_reduce_objective")
         return partials
+
+    def term_gradient(self, derived_row, coef_e=None, coef_f=None, fmm_tiles=None):
+        """
+        ``pm_grad``: sum_s [coef_e[s] dE_s/dp + coef_f[s] d/dp sum_a (F_sa - Fref_sa)^T M_a (F_sa - Fref_sa)] for ONE parameter
+        vector ``derived_row`` [1, n_derived]; ``fmm_tiles`` = the MM force tiles of that vector (``evaluate(want_fmm=True)``).
+        Returns a CUDA tensor [pm_grad_out_doubles] (see include/paramol_b200.h for its layout).
+        """
+        torch = _torch()
+        topo = self.topology
+        L = topo._L
+        n_out = int(L.pm_grad_out_doubles(topo._h))
+        need = int(L.pm_grad_scratch_doubles(topo._h))
+        if need < 0:
+            raise B200Error("pm_grad_scratch_doubles: " + L.pm_last_error().decode())
+        scratch = self._buffers.get("grad_scratch")
+        if scratch is None or scratch.numel() < max(need, 1):
+            scratch = torch.empty(max(need, 1), dtype=torch.float64, device=self.device)
+            self._buffers["grad_scratch"] = scratch
+        gout = self._buf("gout", (max(n_out, 1),))
+        gout.zero_()
+        if coef_f is not None and (fmm_tiles is None or self.fref_tiles is None):
+            raise B200Error("force coefficients need MM force tiles and reference forces")
+        _lib.check(L.pm_grad(topo._h, derived_row.data_ptr(), self.coord_tiles.data_ptr(),
+                             fmm_tiles.data_ptr() if coef_f is not None else None,
+                             self.fref_tiles.data_ptr() if coef_f is not None else None, self.n_conf,
+                             coef_e.data_ptr() if coef_e is not None else None,
+                             coef_f.data_ptr() if coef_f is not None else None, gout.data_ptr(), scratch.data_ptr(),
+                             _stream_ptr(self.device)), "pm_grad")
+        return gout[:n_out]
 
     def forces_from_tiles(self, fmm_tiles):
         """[P, tiles] -> torch [P, S, N, 3]."""

@@ -164,6 +164,16 @@ class RESP:
         val = C - 2.0 * q @ B + np.einsum("pi,ij,pj->p", q, A, q)
         return val if np.ndim(charges) > 1 else float(val[0])
 
+    def esp_objective_gradient(self, charges, weights):
+        """d esp_objective / d charges = 2 (A q - B), numpy [N]."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        key = ("esp", w.tobytes())
+        if key not in self._sums:
+            self._sums = {key: self._assemble(w)}
+        A, B, _ = self._sums[key]
+        q = np.asarray(charges, dtype=np.float64).reshape(-1)
+        return 2.0 * (0.5 * (A + A.T) @ q - B)
+
     # ------------------------------------------------------------------------------------------
     # charges / constraints (reference :136-379)
     # ------------------------------------------------------------------------------------------

@@ -78,3 +78,19 @@ class Regularization(Property):
             b = self._hyperbolic_beta
         reg = np.sum(((np.asarray(current_parameters)) ** 2 + b ** 2) ** (1 / 2.) - b, axis=-1)
         return self._store(a * reg)
+
+    def calculate_gradient(self, current_parameters, a=None, b=None):
+        """d(penalty)/d(current_parameters), numpy [P_opt] (no reference counterpart: the reference differentiates numerically)."""
+        if a is None:
+            a = self._scaling_factor
+        x = np.asarray(current_parameters, dtype=np.float64)
+        kind = self._regularization_type.upper()
+        if kind == "L2":
+            return 2.0 * a * (x - self._initial_parameters_values) / np.power(self._prior_widths, 2)
+        elif kind == "L1":
+            return a * np.sign(x - self._initial_parameters_values) / np.asarray(self._prior_widths)
+        elif kind == "HYPERBOLIC":
+            if b is None:
+                b = self._hyperbolic_beta
+            return a * x / np.sqrt(x ** 2 + b ** 2)
+        raise NotImplementedError("Regularization {} scheme not implement.".format(self._regularization_type))

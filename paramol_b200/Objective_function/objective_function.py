@@ -153,6 +153,41 @@ class ObjectiveFunction:
             self._print_table(time.time() - start_time)
         return objective_function
 
+    def f_and_grad(self, parameters_values, opt_mode=True):
+        """
+        (f, d f / d parameters_values) with the ANALYTIC gradient: one forward pass (energies, forces, residual sums) and
+        one ``pm_grad`` pass per system instead of the P_opt + 1 objective evaluations of a finite-difference gradient
+        (the only gradient the reference has: scipy ``jac="2-point"``, ``ParaMol/Utils/settings.py:64``, and
+        ``GradientDescent``, ``ParaMol/Optimizers/gradient_descent.py:106-121``).  Side effects as :meth:`f`.
+
+        Supported: ENERGY, FORCE, ESP and REGULARIZATION properties; uniform, Boltzmann and manual weights (which do not
+        depend on the parameters).  NON_BOLTZMANN weights depend on the MM energies and raise ``NotImplementedError``.
+        Derivatives with respect to a vanishing lj_eps are reported as 0 (sqrt is not differentiable there).
+        """
+        if not self._fused:
+            raise NotImplementedError("the analytic gradient needs the fused device path")
+        if self._weighting_method.upper() == "NON_BOLTZMANN":
+            raise NotImplementedError("analytic gradient: NON_BOLTZMANN weights depend on the parameters")
+        start_time = time.time()
+        x = np.asarray(parameters_values, dtype=np.float64)
+        self.parameter_space.update_systems(self.systems, parameters_values)
+        if opt_mode:
+            self._f_count += 1
+        slots = [system.engine.current_slots()[None, :] for system in self.systems]
+        value, grad = self._evaluate_fused_grad(slots, x)
+        if np.isnan(value):
+            value = 1e16
+        if self._f_count % self._checkpoint_freq == 1:
+            for system in self.systems:
+                system.engine.write_system_xml("{}_checkpoint.xml".format(system.name))
+        if not opt_mode:
+            self._print_table(time.time() - start_time)
+        return value, grad
+
+    def grad(self, parameters_values):
+        """Analytic gradient only (see :meth:`f_and_grad`); usable as ``jac`` of ``scipy.optimize.minimize``."""
+        return self.f_and_grad(parameters_values)[1]
+
     def f_batch(self, parameters_matrix):
         """
         Objective values, numpy [P], for the rows of ``parameters_matrix`` [P, P_opt] in one set of launches.  Nothing
@@ -299,6 +334,101 @@ class ObjectiveFunction:
                 f_prop.value = float(vals[0])
             values += f_prop.weight * vals
         return values
+
+    def _evaluate_fused_grad(self, slots_per_system, x):
+        """Forward pass + ``pm_grad`` for ONE parameter vector; returns (value, gradient [P_opt])."""
+        import torch
+        e_prop, f_prop, r_prop = self._prop("ENERGY"), self._prop("FORCE"), self._prop("REGULARIZATION")
+        X = x[None, :]
+        work, partial_list, states = [], [], []
+        for s_idx, (system, slots) in enumerate(zip(self.systems, slots_per_system)):
+            st = self._system_state(s_idx, system)
+            states.append(st)
+            if not (st["need_e"] or st["need_f"]):
+                partial_list.append(None)
+                work.append(None)
+                continue
+            ens = st["ens"]
+            slots_dev = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64)).to(ens.device)
+            derived = ens.topology.prepare(slots_dev)
+            emm, fres, fmm = ens.evaluate(derived, with_forces=st["need_f"], want_fres=st["need_f"], want_fmm=st["need_f"])
+            partial_list.append(ens.reduce(emm, fres, d_shift=st["d_shift"]).clone())
+            work.append((derived, emm, fmm))
+        live = [p for p in partial_list if p is not None]
+        value = 0.0
+        per_system = [None] * len(self.systems)
+        if live:
+            stacked = torch.stack(live, dim=0)
+            _dist.allreduce_sum_tensor_(stacked)
+            host_partials = stacked.cpu().numpy()
+            k = 0
+            for i, p in enumerate(partial_list):
+                if p is not None:
+                    per_system[i] = host_partials[k] * 1.0
+                    k += 1
+            raw = [None if hp is None else hp.copy() for hp in per_system]
+            value = float(self.assemble_from_partials(per_system, [st["w_scale"] for st in states], True)[0])
+        # per-conformation coefficients and the term-gradient pass
+        slot_grads = [None] * len(self.systems)
+        gouts = []
+        for s_idx, (system, st) in enumerate(zip(self.systems, states)):
+            if work[s_idx] is None:
+                continue
+            derived, emm, fmm = work[s_idx]
+            ens = st["ens"]
+            hp = raw[s_idx][0]
+            scale = st["w_scale"]
+            w = ens.weights if ens.weights is not None else None
+            coef_e = coef_f = None
+            if st["need_e"]:
+                var = float(e_prop.variance[e_prop.systems.index(system)])
+                n = hp[5]
+                m = hp[0] / n
+                sum_w, sum_wd = scale * hp[3], scale * hp[1]
+                d = ens.eref - emm[0] - st["d_shift"]      # d' of pm_reduce_objective: (E_ref - E_mm) - shift, so dd'/dE_mm = -1
+                wv = w * scale if w is not None else scale
+                coef_e = ((2.0 * wv) * (d - m) + (2.0 / n) * (m * sum_w - sum_wd)) * (-e_prop.weight / var)
+                coef_e = coef_e.contiguous()
+            if st["need_f"]:
+                c = f_prop.weight * scale / (3 * system.n_atoms)
+                coef_f = (w * c).contiguous() if w is not None else torch.full((ens.n_conf,), c, dtype=torch.float64, device=ens.device)
+            gouts.append((s_idx, ens.term_gradient(derived, coef_e, coef_f, None if fmm is None else fmm[0]).clone()))
+        for s_idx, gout in gouts:
+            _dist.allreduce_sum_tensor_(gout)
+            topo = states[s_idx]["ens"].topology
+            slot_grads[s_idx] = topo.term_gradient_to_slots(gout.cpu().numpy(), slots_per_system[s_idx][0])
+        esp_prop = self._prop("ESP")
+        if esp_prop is not None:
+            vals = 0.0
+            for system in esp_prop.systems:
+                s_idx = self.systems.index(system)
+                if np.ndim(system.weights) == 0 or len(np.atleast_1d(system.weights)) != system.n_structures:
+                    system.compute_conformations_weights(temperature=self._weighting_temperature,
+                                                         weighting_method=self._weighting_method)
+                topo_n = system.n_atoms
+                off = 2 * len(system.engine.system.bond_idx) + 2 * len(system.engine.system.angle_idx) + \
+                    2 * len(system.engine.system.torsion_idx)
+                charges = np.asarray(slots_per_system[s_idx])[0, off:off + 3 * topo_n:3]
+                vals = float(system.resp_engine.esp_objective(charges, system.weights))
+                last = (s_idx, off, topo_n, charges)
+            esp_prop.value = vals
+            value += esp_prop.weight * vals
+            # as in the forward pass only the LAST system's ESP term survives (esp_property.py:104)
+            s_idx, off, topo_n, charges = last
+            system = self.systems[s_idx]
+            if slot_grads[s_idx] is None:
+                slot_grads[s_idx] = np.zeros(slots_per_system[s_idx].shape[1])
+            slot_grads[s_idx][off:off + 3 * topo_n:3] += esp_prop.weight * system.resp_engine.esp_objective_gradient(charges, system.weights)
+        store_grads = []
+        for system, gs in zip(self.systems, slot_grads):
+            store_grads.append(None if gs is None else
+                               system.engine.slots_gradient_to_store(system.force_field, gs, system.force_field.store))
+        grad = self.parameter_space.gradient_from_store(self.systems, x, store_grads)
+        if r_prop is not None:
+            reg = float(np.atleast_1d(r_prop.calculate_property(x))[0])
+            value += r_prop.weight * reg
+            grad = grad + r_prop.weight * r_prop.calculate_gradient(x)
+        return value, grad
 
     def _evaluate_fused(self, slots_per_system, X, set_values):
         """

@@ -251,6 +251,38 @@ class ParameterSpace:
                 raise NotImplementedError("MM RESP Engine {} is not implemented.".format(type(system.resp_engine)))
         return self.optimizable_parameters_values
 
+    def gradient_from_store(self, systems, parameters_values, store_gradients, symmetry_constrained=True):
+        """
+        Adjoint of the scatter of :meth:`update_systems`: ``store_gradients[s]`` = d f / d (value store of system s, after
+        the abs() sign conventions) -> d f / d parameters_values (scaled coordinates if ``preconditioned``).  Where the
+        scatter writes a store entry twice the last write wins, as in the forward pass; abs() contributes sign(x).
+        """
+        x = self._physical(parameters_values)
+        plan = self._compile_scatter(systems, symmetry_constrained)
+        g = np.zeros(len(x))
+        for system, sc, gs in zip(systems, plan["per_system"], store_gradients):
+            if gs is None or not len(sc["dst"]):
+                continue
+            gs = np.asarray(gs, dtype=np.float64).copy()
+            engine_plan = system.engine.compile_update_plan(system.force_field)
+            last = {}
+            for d, src in zip(sc["dst"].tolist(), sc["src"].tolist()):
+                last[d] = src
+            dst = np.fromiter(last.keys(), dtype=np.int64, count=len(last))
+            src = np.fromiter(last.values(), dtype=np.int64, count=len(last))
+            sign = np.ones(len(gs))
+            if len(engine_plan["abs_idx"]):
+                pre = np.zeros(len(gs))
+                pre[dst] = x[src]
+                idx = engine_plan["abs_idx"]
+                in_scatter = np.zeros(len(gs), dtype=bool)
+                in_scatter[dst] = True
+                sign[idx] = np.where(in_scatter[idx], np.sign(pre[idx]), 1.0)
+            np.add.at(g, src, gs[dst] * sign[dst])
+        if self.preconditioned:
+            g = g * self.scaling_constants
+        return g
+
     def update_systems_batch(self, systems, parameters_matrix, symmetry_constrained=True):
         """
         Slot rows for P trial vectors: list over systems of float64 [P, n_slots].  Parameter objects, force fields

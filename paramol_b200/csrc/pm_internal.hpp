@@ -1,0 +1,60 @@
+// pm_internal.hpp -- definitions shared by the translation units of libparamol_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/paramol_b200.h"
+#include "pm_program.hpp"
+
+// =============================================================================================
+// Device-visible description of one topology
+// =============================================================================================
+struct PmProg {
+    int n_atoms, n_bonds, n_angles, n_torsions, n_pairs;
+    int cpw, L;
+    int n_star_steps, n_axis_steps, n_segs;
+    int n_int;      // ints in the blob
+    int n_derived;  // doubles per parameter vector in the derived table
+    int off_star_tab, off_star_hdr, off_star_rec, off_axis_tab, off_axis_hdr, off_axis_rec, off_axis_terms, off_seg_hdr, off_seg_tile,
+        off_entries, off_tper;
+    int doff_bond, doff_angle, doff_tors, doff_pair;
+    int n_slots;
+    int soff_bond, soff_angle, soff_tors, soff_part, soff_exc;
+    double k_coul;
+    double rf_krf, rf_crf, rf_cut2;  // reaction field (CutoffNonPeriodic); pair_stride == 4 when active
+    int pair_stride;
+    const int *ints;         // device blob
+    const double *metric;    // device [9N]
+    const int *pair_map;     // device [n_pairs][3] = (i, j, exception or -1)
+    const double2 *acos_tab; // device [PM_ACOS_N + 1] = (cos, sin)(q pi / PM_ACOS_N)
+    // cached nonbonded contribution (pm_eval_ex mode 2): forces in tile layout and energies [S]; null otherwise
+    const double *nb_f_tiles;
+    const double *nb_e;
+};
+
+// =============================================================================================
+// The object behind pm_handle
+// =============================================================================================
+struct pm_handle_s {
+    int device;
+    int n_sm;
+    int max_smem;
+    PmProg prog;
+    PmHostProgram host;
+    int *d_ints;
+    double *d_metric;
+    int *d_pair_map;
+    double2 *d_acos;
+    int warps[2];  // [with_forces]
+    int maxw[2];   // kernel variant (registers per thread) per [with_forces]
+    int rf;        // reaction-field variant
+    size_t smem_total[2];
+    // raw bonded term lists (the gradient kernel walks flat term lists, pm_grad_kernels.cu)
+    std::vector<int> bond_idx, angle_idx, torsion_idx, torsion_per;
+    void *grad_state;               // owned by pm_grad_kernels.cu
+    void (*grad_free)(void *);
+};
+
+int pm_fail_msg(const std::string &msg);  // sets pm_last_error(), returns 1 (pm_kernels.cu)

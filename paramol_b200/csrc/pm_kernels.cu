@@ -27,32 +27,7 @@
 #include "../../include/paramol_b200.h"
 #include "pm_device.cuh"
 #include "pm_program.hpp"
-
-// =============================================================================================
-// Device-visible description of one topology
-// =============================================================================================
-struct PmProg {
-    int n_atoms, n_bonds, n_angles, n_torsions, n_pairs;
-    int cpw, L;
-    int n_star_steps, n_axis_steps, n_segs;
-    int n_int;      // ints in the blob
-    int n_derived;  // doubles per parameter vector in the derived table
-    int off_star_tab, off_star_hdr, off_star_rec, off_axis_tab, off_axis_hdr, off_axis_rec, off_axis_terms, off_seg_hdr, off_seg_tile,
-        off_entries, off_tper;
-    int doff_bond, doff_angle, doff_tors, doff_pair;
-    int n_slots;
-    int soff_bond, soff_angle, soff_tors, soff_part, soff_exc;
-    double k_coul;
-    double rf_krf, rf_crf, rf_cut2;  // reaction field (CutoffNonPeriodic); pair_stride == 4 when active
-    int pair_stride;
-    const int *ints;         // device blob
-    const double *metric;    // device [9N]
-    const int *pair_map;     // device [n_pairs][3] = (i, j, exception or -1)
-    const double2 *acos_tab; // device [PM_ACOS_N + 1] = (cos, sin)(q pi / PM_ACOS_N)
-    // cached nonbonded contribution (pm_eval_ex mode 2): forces in tile layout and energies [S]; null otherwise
-    const double *nb_f_tiles;
-    const double *nb_e;
-};
+#include "pm_internal.hpp"
 
 // =============================================================================================
 // K0: slots -> derived table (one block per parameter vector)
@@ -751,22 +726,6 @@ int pm_fail_msg(const std::string &msg) { return pm_fail(msg); }  // for the oth
         if (_e != cudaSuccess) return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-struct pm_handle_s {
-    int device;
-    int n_sm;
-    int max_smem;
-    PmProg prog;
-    PmHostProgram host;
-    int *d_ints;
-    double *d_metric;
-    int *d_pair_map;
-    double2 *d_acos;
-    int warps[2];  // [with_forces]
-    int maxw[2];   // kernel variant (registers per thread) per [with_forces]
-    int rf;        // reaction-field variant
-    size_t smem_total[2];
-};
-
 typedef void (*pm_ef_fn)(PmProg, const double *, int, const double *, const double *, long, long, double *, double *, double *);
 
 template <int MAXW>
@@ -925,6 +884,12 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     h->d_acos = nullptr;
     h->host = host;
     h->rf = rf;
+    h->grad_state = nullptr;
+    h->grad_free = nullptr;
+    h->bond_idx.assign(t->bond_idx, t->bond_idx + 2 * (size_t)t->n_bonds);
+    h->angle_idx.assign(t->angle_idx, t->angle_idx + 3 * (size_t)t->n_angles);
+    h->torsion_idx.assign(t->torsion_idx, t->torsion_idx + 4 * (size_t)t->n_torsions);
+    h->torsion_per.assign(t->torsion_per, t->torsion_per + (size_t)t->n_torsions);
     PmProg &g = h->prog;
     g.n_atoms = N;
     g.n_bonds = t->n_bonds;
@@ -1036,6 +1001,7 @@ extern "C" int pm_destroy(pm_handle h) {
     cudaFree(h->d_metric);
     cudaFree(h->d_pair_map);
     cudaFree(h->d_acos);
+    if (h->grad_state && h->grad_free) h->grad_free(h->grad_state);
     delete h;
     return 0;
 }
