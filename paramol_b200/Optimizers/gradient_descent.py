@@ -6,7 +6,7 @@ Description
 (``ParaMol/Optimizers/gradient_descent.py:11-151``).  The P_opt (1-point) or 2 P_opt (2-point) displaced vectors of a
 gradient are evaluated in ONE ``f_batch`` call when the objective supports it -- the case the reference calls
 "prohibitive" for >= 1000 conformations (``:54-57``).  Formulas, including the 2-point quotient (f+ - f-)/dx, are the
-reference's.
+reference's.  Additive: ``derivative_type="analytic"`` takes the closed-form gradient of ``ObjectiveFunction.grad``.
 """
 import copy
 
@@ -25,9 +25,15 @@ class GradientDescent:
         self._dx = dx
         self._derivative_h = derivative_h
         self.n_launches = 0
+        self._analytic = None
 
     def _gradient(self, evaluate, parameters, dp, f_new):
         n = len(parameters)
+        if self._derivative_type == "analytic":
+            if self._analytic is None:
+                raise ValueError('derivative_type="analytic" needs an objective function that offers grad')
+            self.n_launches += 1
+            return np.asarray(self._analytic(parameters), dtype=np.float64)
         if self._derivative_type == "1-point":
             X = np.repeat(parameters[None, :], n, axis=0)
             X[np.arange(n), np.arange(n)] += dp
@@ -49,6 +55,7 @@ class GradientDescent:
         print("!                        STARTING GRADIENT DESCENT OPTIMIZER                      !")
         print("!=================================================================================!")
         evaluate, _ = batch_evaluator(f)
+        self._analytic = getattr(getattr(f, "__self__", None), "grad", None)
         parameters = np.asarray(parameters, dtype=np.float64)
         grad = np.ones(len(parameters))
         dp = np.ones(len(parameters)) * self._dx

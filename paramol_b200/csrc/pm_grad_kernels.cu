@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -35,9 +36,11 @@
     } while (0)
 
 #define PMG_THREADS 256
-#define PMG_MAX_SMEM (100 * 1024)  // two CTAs per SM
+#define PMG_MAX_SMEM (100 * 1024)  // at least two CTAs per SM
 
 enum { PMG_BOND = 0, PMG_ANGLE = 1, PMG_TORSION = 2, PMG_PAIR = 3 };
+
+struct PmGradArgs;
 
 struct PmGradState {
     int n_blocks;        // blocks of 32 terms of one kind
@@ -45,8 +48,11 @@ struct PmGradState {
     int4 *d_atoms;       // [n_blocks * 32]
     int4 *d_meta;        // [n_blocks * 32] = (kind or -1 for padding, offset in the derived table, periodicity, offset in gout)
     int cpt;             // conformations per CTA tile
+    int threads;         // 32 x min(8, n_blocks): a small molecule has fewer blocks of terms than a full CTA has warps
     size_t smem;
     int grid_max;
+    int minb;
+    void (*fn)(const PmGradArgs);
 };
 
 static void pm_grad_free(void *p) {
@@ -62,6 +68,7 @@ struct PmGradArgs {
     long n_conf, n_tiles;  // n_tiles = CTA tiles of cpt conformations
     const int4 *atoms, *meta;
     const double *derived, *x_tiles, *fmm_tiles, *fref_tiles, *metric, *coef_e, *coef_f;
+    const double2 *acos_tab;
     double *partial;  // [gridDim.x][n_blocks][4][32]
 };
 
@@ -72,7 +79,8 @@ __device__ __forceinline__ void pmg_load(const double *__restrict__ s, pm_d3 &x,
     l = pm_d3{b.y, c.x, c.y};
 }
 
-__global__ void __launch_bounds__(PMG_THREADS, 2) pm_grad_kernel(const PmGradArgs g) {
+template <int MINB>
+__global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGradArgs g) {
     extern __shared__ __align__(16) double sm[];
     const int N = g.n_atoms, CPT = g.cpt;
     double *tile = sm;                       // [CPT][N][6]
@@ -160,13 +168,13 @@ __global__ void __launch_bounds__(PMG_THREADS, 2) pm_grad_kernel(const PmGradArg
                         pmg_load(sc + c * stride, xc, lc);
                         const pm_d3 d0 = pm_sub(xb, xa), d1 = pm_sub(xb, xc);
                         const pm_d3 p = pm_cross(d0, d1);
-                        const double r0 = pm_dot(d0, d0), r1 = pm_dot(d1, d1);
-                        const double rp = fmax(sqrt(pm_dot(p, p)), 1.0e-6);
-                        const double cs = pm_dot(d0, d1) / sqrt(r0 * r1);
-                        const double th = cs >= 1.0 ? 0.0 : (cs <= -1.0 ? PM_PI : acos(cs));
+                        const double r0 = pm_dot(d0, d0), r1 = pm_dot(d1, d1), pp2 = pm_dot(p, p);
+                        const double i01 = pm_rsqrt(r0 * r1);          // 1 / (|d0| |d1|)
+                        const double ip = pm_rsqrt(fmax(pp2, 1.0e-12));  // 1 / max(|p|, 1e-6), as ReferenceAngleBondIxn
+                        const double th = pm_acos_cs(pm_dot(d0, d1) * i01, pp2 * ip * i01, g.acos_tab);
                         // grad_a theta = -(d0 x p) / (|d0|^2 |p|),  grad_c theta = (d1 x p) / (|d1|^2 |p|)
-                        const double dth = pm_dot(pm_cross(d1, p), pm_sub(lc, lb)) / (r1 * rp) -
-                                           pm_dot(pm_cross(d0, p), pm_sub(la, lb)) / (r0 * rp);
+                        const double ir0 = r1 * i01 * i01, ir1 = r0 * i01 * i01;  // 1 / |d0|^2, 1 / |d1|^2
+                        const double dth = ip * (ir1 * pm_dot(pm_cross(d1, p), pm_sub(lc, lb)) - ir0 * pm_dot(pm_cross(d0, p), pm_sub(la, lb)));
                         const double dl = th - t0;
                         const double a = ca[c];
                         acc0 += k * (dth - a * dl);
@@ -174,7 +182,8 @@ __global__ void __launch_bounds__(PMG_THREADS, 2) pm_grad_kernel(const PmGradArg
                     }
                 } else {  // PMG_TORSION: derived = (k, k n, cos phase, sin phase)
                     const double k = dp[0], cph = dp[2], sph = dp[3];
-                    const double n = (double)me.z;
+                    const int per = me.z;
+                    const double n = (double)per;
                     const double *s0 = tile + at.x * 6, *s1 = tile + at.y * 6, *s2 = tile + at.z * 6, *s3 = tile + at.w * 6;
                     for (int c = 0; c < nc; ++c) {
                         pm_d3 x0, l0, x1, l1, x2, l2, x3, l3;
@@ -185,21 +194,27 @@ __global__ void __launch_bounds__(PMG_THREADS, 2) pm_grad_kernel(const PmGradArg
                         const pm_d3 d0 = pm_sub(x0, x1), d1 = pm_sub(x2, x1), d2 = pm_sub(x2, x3);
                         const pm_d3 c1 = pm_cross(d0, d1), c2 = pm_cross(d1, d2);
                         const double n1 = pm_dot(c1, c1), n2 = pm_dot(c2, c2), bb = pm_dot(d1, d1);
-                        // phi = signed angle between c1 and c2 (sign of d0 . c2), as ReferenceProperDihedralBond
-                        const pm_d3 cc = pm_cross(c1, c2);
-                        double phi = atan2(sqrt(pm_dot(cc, cc)), pm_dot(c1, c2));
-                        if (pm_dot(d0, c2) < 0.0) phi = -phi;
-                        double sn, cn;
-                        sincos(n * phi, &sn, &cn);
+                        // one reciprocal for 1/n1, 1/n2, 1/bb; phi is the signed angle between c1 and c2 (sign of d0 . c2, as
+                        // ReferenceProperDihedralBond): cos phi = c1.c2 / (|c1||c2|), sin phi = |d1| (d0.c2) / (|c1||c2|)
+                        const double inv = 1.0 / (n1 * n2 * bb);
+                        const double in1 = inv * n2 * bb, in2 = inv * n1 * bb, ibb = inv * n1 * n2;
+                        const double i12 = pm_rsqrt(n1 * n2), nb = bb * pm_rsqrt(bb);
+                        const double cphi = pm_dot(c1, c2) * i12, sphi = nb * pm_dot(d0, c2) * i12;
+                        double cn = 1.0, sn = 0.0;  // cos(n phi), sin(n phi) by n complex multiplications (n is 1..6 in practice)
+                        for (int q = 0; q < per; ++q) {
+                            const double t = cn * cphi - sn * sphi;
+                            sn = fma(sn, cphi, cn * sphi);
+                            cn = t;
+                        }
                         const double cpsi = cn * cph + sn * sph, spsi = sn * cph - cn * sph;  // psi = n phi - phase
                         // grad_0 phi = |d1| c1 / |c1|^2, grad_3 phi = -|d1| c2 / |c2|^2,
                         // grad_1 = (ff1 - 1) grad_0 - ff2 grad_3, grad_2 = (ff2 - 1) grad_3 - ff1 grad_0
-                        const double nb = sqrt(bb), ff1 = pm_dot(d0, d1) / bb, ff2 = pm_dot(d2, d1) / bb;
+                        const double ff1 = pm_dot(d0, d1) * ibb, ff2 = pm_dot(d2, d1) * ibb;
                         const pm_d3 w0{l0.x + (ff1 - 1.0) * l1.x - ff1 * l2.x, l0.y + (ff1 - 1.0) * l1.y - ff1 * l2.y,
                                        l0.z + (ff1 - 1.0) * l1.z - ff1 * l2.z};
                         const pm_d3 w3{l3.x - ff2 * l1.x + (ff2 - 1.0) * l2.x, l3.y - ff2 * l1.y + (ff2 - 1.0) * l2.y,
                                        l3.z - ff2 * l1.z + (ff2 - 1.0) * l2.z};
-                        const double dphi = nb * (pm_dot(c1, w0) / n1 - pm_dot(c2, w3) / n2);
+                        const double dphi = nb * (pm_dot(c1, w0) * in1 - pm_dot(c2, w3) * in2);
                         const double a = ca[c];
                         acc0 += k * (a * spsi - n * cpsi * dphi);   // d/d phase: a k sin psi - k n cos psi dphi
                         acc1 += fma(a, 1.0 + cpsi, n * spsi * dphi);  // d/d k   : a (1 + cos psi) + n sin psi dphi
@@ -273,9 +288,13 @@ static PmGradState *pm_grad_state(pm_handle h) {
     st->n_gout = go_pair + 3 * g.n_pairs;
     st->d_atoms = nullptr;
     st->d_meta = nullptr;
-    st->cpt = 32;
+    const int warps = std::min(PMG_THREADS / 32, std::max(st->n_blocks, 2));
+    st->threads = 32 * warps;
+    const int ctas_per_sm = std::max(2, std::min(6, (16 + warps - 1) / warps));  // aim at >= 16 resident warps per SM
+    const size_t smem_cap = std::min<size_t>((size_t)200 * 1024 / ctas_per_sm, PMG_MAX_SMEM);
+    st->cpt = 128;  // long tiles amortise the per-tile staging, barrier and partial-sum update of small molecules
     auto smem_for = [&](int cpt) { return sizeof(double) * ((size_t)cpt * g.n_atoms * 6 + cpt); };
-    while (st->cpt > 1 && smem_for(st->cpt) > PMG_MAX_SMEM) st->cpt >>= 1;
+    while (st->cpt > 1 && smem_for(st->cpt) > smem_cap) st->cpt >>= 1;
     st->smem = smem_for(st->cpt);
     if (st->smem > (size_t)h->max_smem) {
         delete st;
@@ -288,9 +307,12 @@ static PmGradState *pm_grad_state(pm_handle h) {
     }
     cudaMemcpy(st->d_atoms, atoms.data(), sizeof(int4) * atoms.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(st->d_meta, meta.data(), sizeof(int4) * meta.size(), cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(pm_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem);
+    const char *env = getenv("PM_GRAD_MINB");
+    st->minb = env && *env ? atoi(env) : 2;
+    st->fn = st->minb >= 3 ? pm_grad_kernel<3> : pm_grad_kernel<2>;
+    cudaFuncSetAttribute(st->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem);
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pm_grad_kernel, PMG_THREADS, st->smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, st->fn, st->threads, st->smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     st->grid_max = h->n_sm * per_sm;
     h->grad_state = st;
     h->grad_free = pm_grad_free;
@@ -337,13 +359,14 @@ extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coo
     a.fmm_tiles = fmm_tiles_dev;
     a.fref_tiles = fref_tiles_dev;
     a.metric = h->d_metric;
+    a.acos_tab = h->d_acos;
     a.coef_e = coef_e_dev;
     a.coef_f = coef_f_dev;
     a.partial = scratch_dev;
     const int grid = (int)std::min<long>(st->grid_max, a.n_tiles);
     PMG_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * (size_t)grid * st->n_blocks * 128, s));
     if (st->n_blocks > 0) {
-        pm_grad_kernel<<<grid, PMG_THREADS, st->smem, s>>>(a);
+        st->fn<<<grid, st->threads, st->smem, s>>>(a);
         PMG_CUDA(cudaGetLastError());
         pm_grad_reduce_kernel<<<(st->n_blocks * 32 + 255) / 256, 256, 0, s>>>(scratch_dev, grid, st->n_blocks, st->d_meta, gout_dev);
         PMG_CUDA(cudaGetLastError());

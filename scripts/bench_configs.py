@@ -136,7 +136,63 @@ def config5(S=50_000, G=500, N=60):
                 bytes_per_conformation=24 * N + 32 * G, hbm_GB_s=S * (24 * N + 32 * G) / (ms * 1e-3) / 1e9)
 
 
+def config6(which="lig60", S=100_000):
+    """Analytic gradient: forward pass (E, F, residuals, MM force tiles) + pm_grad, against the evaluations a 2-point
+    finite-difference gradient would need (n_slots + 1 forward passes of the same kernel, batched)."""
+    if which == "aniline":
+        golden = os.path.join(REPO, "tests", "golden")
+        engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(golden, "aniline.prmtop"),
+                            crd_file=os.path.join(golden, "aniline.inpcrd"))
+        x0 = np.asarray(engine.get_positions(), dtype=np.float64).reshape(-1, 3)
+    else:
+        mm, x0 = make_ligand(60)
+        engine = B200Engine(system=mm)
+    topo = engine.device_topology()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.from_numpy(x0).cuda()[None] + 0.005 * torch.randn((S,) + x0.shape, dtype=torch.float64, device="cuda", generator=g)
+    F = 50.0 * torch.randn((S,) + x0.shape, dtype=torch.float64, device="cuda", generator=g)
+    E = torch.randn(S, dtype=torch.float64, device="cuda", generator=g)
+    ens = DeviceEnsemble(topo, X, F, E)
+    base = engine.current_slots()
+    derived = topo.prepare(torch.from_numpy(base[None].copy()).cuda())
+    ca = torch.randn(S, dtype=torch.float64, device="cuda", generator=g)
+    cb = torch.rand(S, dtype=torch.float64, device="cuda", generator=g)
+    times = {}
+    for name, fn in (("forward", lambda: ens.evaluate(derived, with_forces=True, want_fres=True)),
+                     ("forward_with_force_tiles", lambda: ens.evaluate(derived, with_forces=True, want_fres=True, want_fmm=True))):
+        fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(5):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        times[name] = a.elapsed_time(b) / 5
+    fmm = out[2]
+    ens.term_gradient(derived, ca, cb, fmm[0])
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        ens.term_gradient(derived, ca, cb, fmm[0])
+    b.record()
+    torch.cuda.synchronize()
+    times["pm_grad"] = a.elapsed_time(b) / 5
+    n_terms = topo.n_bonds + topo.n_angles + topo.n_torsions + topo.n_pairs
+    return dict(config=6, workload="analytic gradient, %s, S=%d conformations, %d slots, %d terms" % (which, S, topo.n_slots, n_terms),
+                forward_ms=times["forward"], forward_with_force_tiles_ms=times["forward_with_force_tiles"], grad_ms=times["pm_grad"],
+                gradient_conformations_per_s=S / (times["pm_grad"] * 1e-3),
+                analytic_total_ms=times["forward_with_force_tiles"] + times["pm_grad"],
+                two_point_fd_ms=times["forward"] * (topo.n_slots + 1),
+                speedup_vs_fd=times["forward"] * (topo.n_slots + 1) / (times["forward_with_force_tiles"] + times["pm_grad"]))
+
+
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
+    if 6 in which:
+        which = [c for c in which if c != 6]
+        print(json.dumps(config6("aniline", 1 << 20)), flush=True)
+        print(json.dumps(config6("lig60", 100_000)), flush=True)
     for c in which:
         print(json.dumps({3: config3, 4: config4, 5: config5}[c]()), flush=True)

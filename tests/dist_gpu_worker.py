@@ -1,7 +1,7 @@
 """
 Worker of tests/test_gpu_distributed.py: one process per GPU (NCCL).  Every rank evaluates the objective on its shard
 through ObjectiveFunction.f / f_batch (one allreduce per call) and, separately, on ALL conformations on its own GPU; the
-two must agree to 1e-12 relative, for uniform, Boltzmann and non-Boltzmann weights.
+two must agree to 1e-12 relative, for uniform, Boltzmann and non-Boltzmann weights; so must the analytic gradient.
 """
 import os
 import sys
@@ -66,6 +66,15 @@ def main():
         assert torch.equal(values, ref), "ranks disagree on the objective"
         if rank == 0:
             np.save(os.path.join(REPO, "gpurun_out", "dist_values_%s_w%d.npy" % (weighting, world)), values.cpu().numpy())
+        if weighting != "non_boltzmann":     # analytic gradient: one more sum-allreduce (of the term gradient)
+            v, g = of_shard.f_and_grad(trial[0].copy())
+            assert abs(v - got[0]) <= 1e-12 * abs(v)
+            gt = torch.from_numpy(g).cuda()
+            ref_g = gt.clone()
+            dist.broadcast(ref_g, src=0)
+            assert torch.equal(gt, ref_g), "ranks disagree on the gradient"
+            if rank == 0:
+                np.save(os.path.join(REPO, "gpurun_out", "dist_grad_%s_w%d.npy" % (weighting, world)), g)
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok" % rank)

@@ -26,8 +26,10 @@ def _run(world):
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(REPO, "tests", "dist_gpu_worker.py")]
     res = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=900)
     assert res.returncode == 0, res.stdout[-4000:]
-    return {w: np.load(os.path.join(REPO, "gpurun_out", "dist_values_%s_w%d.npy" % (w, world)))
-            for w in ("uniform", "boltzmann", "non_boltzmann")}
+    out = {w: np.load(os.path.join(REPO, "gpurun_out", "dist_values_%s_w%d.npy" % (w, world)))
+           for w in ("uniform", "boltzmann", "non_boltzmann")}
+    grads = {w: np.load(os.path.join(REPO, "gpurun_out", "dist_grad_%s_w%d.npy" % (w, world))) for w in ("uniform", "boltzmann")}
+    return out, grads
 
 
 def test_sharded_objective_equals_single_gpu():
@@ -35,8 +37,10 @@ def test_sharded_objective_equals_single_gpu():
     n_gpu = torch.cuda.device_count()
     if n_gpu < 2:
         pytest.skip("needs at least 2 GPUs")
-    single = _run(1)
-    multi = _run(2)
+    single, single_g = _run(1)
+    multi, multi_g = _run(2)
+    for w in single_g:   # analytic gradient: the shards' term gradients are summed by one allreduce
+        assert np.abs(single_g[w] - multi_g[w]).max() <= 1e-10 * np.abs(single_g[w]).max(), w
     for w in single:
         assert np.all(np.abs(single[w] - multi[w]) <= 1e-12 * np.abs(single[w])), (w, single[w], multi[w])
         # f and f_batch agree with each other

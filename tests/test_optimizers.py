@@ -4,6 +4,7 @@ finite-difference gradient-descent drivers must follow exactly the trajectory of
 stream, same decisions), using fewer launches.
 """
 import numpy as np
+import pytest
 
 from paramol_b200.Optimizers.optimizer import Optimizer
 from paramol_b200.Optimizers.monte_carlo import MonteCarlo
@@ -82,3 +83,55 @@ def test_optimizer_front_end_and_scipy():
     assert np.linalg.norm(np.asarray(x) - 1.0) < 1.0 and obj.f(x) < obj.f(np.zeros(6))
     assert str(opt) == "Instance of optimizer scipy."
     assert isinstance(Optimizer("monte_carlo", dict(n_blocks=1, max_iter=2, f_tol=1e-8, prob=0.25))._optimizer, MonteCarlo)
+
+
+class _Quadratic:
+    """Stand-in objective with the f / f_batch / f_and_grad / grad surface of ObjectiveFunction."""
+
+    def __init__(self, n=6):
+        rng = np.random.default_rng(4)
+        a = rng.normal(size=(n, n))
+        self.h = a @ a.T + n * np.eye(n)
+        self.c = rng.normal(size=n)
+        self.n_f = self.n_g = 0
+
+    def f(self, x):
+        self.n_f += 1
+        x = np.asarray(x, dtype=np.float64)
+        return float(0.5 * x @ self.h @ x - self.c @ x)
+
+    def f_batch(self, X):
+        return np.asarray([self.f(x) for x in np.atleast_2d(X)])
+
+    def f_and_grad(self, x):
+        self.n_g += 1
+        x = np.asarray(x, dtype=np.float64)
+        return float(0.5 * x @ self.h @ x - self.c @ x), self.h @ x - self.c
+
+    def grad(self, x):
+        return self.f_and_grad(x)[1]
+
+
+def test_scipy_optimizer_analytic_jacobian():
+    from paramol_b200.Optimizers.scipy_optimizers import ScipyOptimizer
+    obj = _Quadratic()
+    x = ScipyOptimizer(method="BFGS", jac="analytic", options=dict(gtol=1e-10)).run_optimization(obj.f, np.zeros(6))
+    assert np.abs(x - np.linalg.solve(obj.h, obj.c)).max() < 1e-8
+    assert obj.n_f == 0 and obj.n_g > 0                     # scipy never differenced f
+    with pytest.raises(ValueError):
+        ScipyOptimizer(method="BFGS", jac="analytic").run_optimization(lambda v: float(v @ v), np.zeros(3))
+    # the reference's default settings still work unchanged
+    x2 = ScipyOptimizer(method="BFGS", jac="2-point", options=dict(gtol=1e-8)).run_optimization(obj.f, np.zeros(6))
+    assert np.abs(x2 - x).max() < 1e-5
+
+
+def test_gradient_descent_analytic_matches_two_point():
+    from paramol_b200.Optimizers.gradient_descent import GradientDescent
+    obj = _Quadratic()
+    kw = dict(max_iter=30, derivative_calculation="always", g_tol=1e-12, f_tol=1e-14, dx=1e-6, derivative_h=0.02)
+    xa = GradientDescent(derivative_type="analytic", **kw).run_optimization(obj.f, np.zeros(6))
+    xf = GradientDescent(derivative_type="2-point", **kw).run_optimization(obj.f, np.zeros(6))
+    # the reference's 2-point quotient is (f+ - f-)/dx, i.e. twice the derivative: same path with half the step length
+    xh = GradientDescent(derivative_type="analytic", **dict(kw, derivative_h=0.04)).run_optimization(obj.f, np.zeros(6))
+    assert np.abs(xh - xf).max() < 1e-5
+    assert obj.f(xa) < obj.f(np.zeros(6))
