@@ -393,7 +393,7 @@ def run_ours(args):
         "objective_evals_per_s": args.steps / t_dev,
         "roofline": {"bound": "fp64", "kernel": "pm_ef_kernel<true>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak, "traffic": traffic,
-                     "peak_source": "DFMA peak measured live by pm_measure_fma_peak on this GPU",
+                     "peak_source": "FP64 pipe peak measured live by pm_measure_fma_peak on this GPU (DFMA with a uniform addend = DMMA rate; 3-register-operand DFMA streams reach 0.92 of it)",
                      "flops_per_conformation": flops_conf, "kernel_ms": 1e3 * t_kernel,
                      "kernel_share_of_step": t_kernel * args.steps / t_dev, "launch": info,
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
