@@ -170,6 +170,25 @@ int pm_grad(pm_handle h, const double *derived_dev, const double *coord_tiles_de
             const double *fref_tiles_dev, long n_conf, const double *coef_e_dev, const double *coef_f_dev, double *gout_dev,
             double *scratch_dev, void *stream);
 
+/* ---- delta evaluation ---------------------------------------------------------------------------------- */
+/* Energies (and force residuals) of n_vec trial vectors that differ from a stored BASE vector in a few terms each, as the
+ * single-parameter moves of the reference's Monte Carlo / simulated annealing do (ParaMol/Optimizers/monte_carlo.py:89-100,
+ * simulated_annealing.py:90-131; the reference re-evaluates everything, Objective_function/objective_function.py:231-359).
+ *   E_s(p) = e_base[s] + sum_affected (E_t(new) - E_t(old));   fres_s(p) = res_base[s] + the change caused by the force deltas.
+ * Proposal p owns entries prop_ptr[p] .. prop_ptr[p+1]-1; an entry is 12 ints: (kind 0 bond / 1 angle / 2 torsion / 3 pair,
+ * offset of the term in the derived table, periodicity, 0), the term's atoms (4), and for each of them its index into the
+ * proposal's list of affected atoms atom_list[atom_ptr[p] ..] (at most max_loc <= pm_delta_max_local_atoms() of them).
+ * derived_base_dev [n_derived] and derived_dev [n_vec][n_derived] come from pm_prepare_params.  fbase_tiles_dev = the MM
+ * forces of the base vector in tile layout (NULL: energies only; then res_base_dev / fres_dev are unused).
+ * commit = 1 (n_vec = 1): the proposal is folded into e_base, res_base and fbase_tiles instead (accepted move).
+ * pm_derived_layout: out5 = offsets of bonds, angles, torsions, pairs in the derived table and the pair stride. */
+int pm_delta_max_local_atoms(void);
+int pm_derived_layout(pm_handle h, int *out5);
+int pm_delta_eval(pm_handle h, const double *derived_base_dev, const double *derived_dev, int n_vec, const int *prop_ptr_dev,
+                  const int *entries_dev, const int *atom_ptr_dev, const int *atom_list_dev, int max_loc,
+                  const double *coord_tiles_dev, const double *fref_tiles_dev, double *fbase_tiles_dev, double *e_base_dev,
+                  double *res_base_dev, long n_conf, double *emm_dev, double *fres_dev, int commit, void *stream);
+
 /* ---- LLS (K3) ------------------------------------------------------------------------------------- */
 /* Internal coordinates q[S][n_terms] with the conventions of ParaMol/Utils/geometry.py:4-107: kind 0 distance(a0,a1),
  * 1 angle at a1 (arccos of the clipped cosine), 2 dihedral a0-a1-a2-a3 (atan2 form).  atoms [n_terms][4] int32 device. */

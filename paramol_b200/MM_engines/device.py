@@ -210,6 +210,95 @@ class DeviceTopology:
         g[self.off_exception:] = gexc.ravel()
         return g
 
+    # ---- delta evaluation (pm_delta_eval) --------------------------------------------------------------
+    def _delta_maps(self):
+        if getattr(self, "_dmaps", None) is None:
+            if getattr(self, "_pairs_cache", None) is None:
+                self._pairs_cache = self.pairs()
+            pm = self._pairs_cache
+            lay = (ctypes.c_int * 5)()
+            _lib.check(self._L.pm_derived_layout(self._h, lay), "pm_derived_layout")
+            plain = [[] for _ in range(self.n_atoms)]
+            of_exc = {}
+            for q, (i, j, e) in enumerate(pm.tolist()):
+                if e < 0:
+                    plain[i].append(q)
+                    plain[j].append(q)
+                else:
+                    of_exc[e] = q
+            self._dmaps = dict(pairs=pm, plain=plain, of_exc=of_exc, doff=list(lay)[:4], pair_stride=int(lay[4]),
+                               max_loc=int(self._L.pm_delta_max_local_atoms()),
+                               n_terms=self.n_bonds + self.n_angles + self.n_torsions + self.n_pairs)
+        return self._dmaps
+
+    def delta_plan(self, base_slots, slots_rows, max_fraction=0.5):
+        """
+        Entry lists for ``pm_delta_eval``: which terms each row of ``slots_rows`` [P, n_slots] changes with respect to
+        ``base_slots`` (a bonded slot changes its term, a particle slot every plain pair of the atom, an exception slot its
+        pair).  Returns None when a row touches more than ``max_fraction`` of the terms or more atoms than the kernel's
+        per-proposal limit -- the caller then evaluates the batch in full.
+        """
+        m = self._delta_maps()
+        k = self._keep
+        rows = np.atleast_2d(np.asarray(slots_rows, dtype=np.float64))
+        base = np.asarray(base_slots, dtype=np.float64)
+        prop_ptr, atom_ptr, entries, atom_list = [0], [0], [], []
+        max_loc = 1
+        for row in rows:
+            changed = np.nonzero(row != base)[0]
+            terms = set()
+            for idx in changed.tolist():
+                if idx < self.off_angle:
+                    terms.add((0, (idx - self.off_bond) // 2))
+                elif idx < self.off_torsion:
+                    terms.add((1, (idx - self.off_angle) // 2))
+                elif idx < self.off_particle:
+                    terms.add((2, (idx - self.off_torsion) // 2))
+                elif idx < self.off_exception:
+                    terms.update((3, q) for q in m["plain"][(idx - self.off_particle) // 3])
+                else:
+                    q = m["of_exc"].get((idx - self.off_exception) // 3)
+                    if q is not None:
+                        terms.add((3, q))
+            if len(terms) > max_fraction * m["n_terms"]:
+                return None
+            terms = sorted(terms)
+            atoms = set()
+            for kind, t in terms:
+                if kind == 0:
+                    atoms.update(k["bond"][t].tolist())
+                elif kind == 1:
+                    atoms.update(k["angle"][t].tolist())
+                elif kind == 2:
+                    atoms.update(k["tors"][t].tolist())
+                else:
+                    atoms.update(m["pairs"][t, :2].tolist())
+            atoms = sorted(atoms)
+            if len(atoms) > m["max_loc"]:
+                return None
+            loc = {a: l for l, a in enumerate(atoms)}
+            for kind, t in terms:
+                if kind == 0:
+                    at, pofs, per = k["bond"][t].tolist() + [0, 0], m["doff"][0] + 2 * t, 0
+                elif kind == 1:
+                    at, pofs, per = k["angle"][t].tolist() + [0], m["doff"][1] + 2 * t, 0
+                elif kind == 2:
+                    at, pofs, per = k["tors"][t].tolist(), m["doff"][2] + 4 * t, int(k["tper"][t])
+                else:
+                    at, pofs, per = m["pairs"][t, :2].tolist() + [0, 0], m["doff"][3] + m["pair_stride"] * t, 0
+                n_at = (2, 3, 4, 2)[kind]
+                lo = [loc[a] for a in at[:n_at]] + [0] * (4 - n_at)
+                entries.append([kind, pofs, per, 0] + at + lo)
+            atom_list += atoms
+            prop_ptr.append(len(entries))
+            atom_ptr.append(len(atom_list))
+            max_loc = max(max_loc, len(atoms))
+        return dict(prop_ptr=np.asarray(prop_ptr, dtype=np.int32),
+                    entries=np.asarray(entries, dtype=np.int32).reshape(-1, 12) if entries else np.zeros((1, 12), dtype=np.int32),
+                    atom_ptr=np.asarray(atom_ptr, dtype=np.int32),
+                    atom_list=np.asarray(atom_list if atom_list else [0], dtype=np.int32), max_loc=int(max_loc),
+                    n_entries=len(entries))
+
     def prepare(self, slots_dev, derived_dev=None):
         """slots [P, n_slots] CUDA float64 -> derived [P, n_derived]."""
         torch = _torch()
@@ -263,6 +352,7 @@ class DeviceEnsemble:
         self.weights = None            # CUDA [S] or None (= 1)
         self._scratch = None
         self._buffers = {}
+        self.delta_base = None
 
     def _to_device(self, a, pinned=False):
         torch = _torch()
@@ -346,6 +436,47 @@ class DeviceEnsemble:
                                                partials.data_ptr(), self._scratch.data_ptr(), _stream_ptr(self.device)),
                    "pm_reduce_objective")
         return partials
+
+    # ---- delta evaluation ---------------------------------------------------------------------------------
+    def set_delta_base(self, slots_row, derived_row, emm_row, fres_row, fmm_tiles_row):
+        """Keep copies of the per-conformation results of ONE fully evaluated vector as the base of later delta evaluations."""
+        self.delta_base = dict(slots=np.array(slots_row, dtype=np.float64, copy=True), derived=derived_row.reshape(-1).clone(),
+                               emm=emm_row.reshape(-1).clone(),
+                               fres=None if fres_row is None else fres_row.reshape(-1).clone(),
+                               fmm=None if fmm_tiles_row is None else fmm_tiles_row.reshape(-1).clone(), n_commits=0)
+        return self.delta_base
+
+    def _delta_call(self, plan, derived, emm, fres, commit):
+        torch = _torch()
+        topo, b = self.topology, self.delta_base
+        dev = [torch.from_numpy(plan[key]).to(self.device) for key in ("prop_ptr", "entries", "atom_ptr", "atom_list")]
+        with_f = b["fmm"] is not None
+        _lib.check(topo._L.pm_delta_eval(topo._h, b["derived"].data_ptr(), derived.data_ptr(), int(derived.shape[0]),
+                                         dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(),
+                                         plan["max_loc"], self.coord_tiles.data_ptr(),
+                                         self.fref_tiles.data_ptr() if with_f else None,
+                                         b["fmm"].data_ptr() if with_f else None, b["emm"].data_ptr(),
+                                         b["fres"].data_ptr() if with_f else None, self.n_conf,
+                                         emm.data_ptr() if emm is not None else None,
+                                         fres.data_ptr() if fres is not None else None, int(commit),
+                                         _stream_ptr(self.device)), "pm_delta_eval")
+
+    def delta_evaluate(self, plan, derived):
+        """(emm [P,S], fres [P,S] or None) of the rows described by ``plan`` (:meth:`DeviceTopology.delta_plan`) relative to
+        the stored base; same meaning as the outputs of :meth:`evaluate`."""
+        n_vec = int(derived.shape[0])
+        emm = self._buf("emm", (n_vec, self.n_conf))
+        fres = self._buf("fres", (n_vec, self.n_conf)) if self.delta_base["fmm"] is not None else None
+        self._delta_call(plan, derived, emm, fres, 0)
+        return emm, fres
+
+    def delta_commit(self, plan, slots_row, derived_row):
+        """Fold ONE proposal (an accepted move) into the base arrays."""
+        self._delta_call(plan, derived_row, None, None, 1)
+        b = self.delta_base
+        b["slots"] = np.array(slots_row, dtype=np.float64, copy=True)
+        b["derived"] = derived_row.reshape(-1).clone()
+        b["n_commits"] += 1
 
     def term_gradient(self, derived_row, coef_e=None, coef_f=None, fmm_tiles=None):
         """
