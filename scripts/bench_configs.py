@@ -188,6 +188,64 @@ def config6(which="lig60", S=100_000):
                 speedup_vs_fd=times["forward"] * (topo.n_slots + 1) / (times["forward_with_force_tiles"] + times["pm_grad"]))
 
 
+def config7(S=1 << 20, batch=64, rounds=6):
+    """Monte Carlo-style batches through the public API: `batch` proposals per f_batch call, each the current vector with ONE
+    displaced parameter (ParaMol/Optimizers/monte_carlo.py:89-100), aniline, S conformations, ENERGY + FORCE + L2; every
+    round "accepts" one proposal so that the next batch is built on a new vector.  Full evaluation vs delta evaluation."""
+    from paramol_b200.Objective_function.objective_function import ObjectiveFunction
+    from paramol_b200.Objective_function.Properties.energy_property import EnergyProperty
+    from paramol_b200.Objective_function.Properties.force_property import ForceProperty
+    from paramol_b200.Objective_function.Properties.regularization import Regularization
+    from paramol_b200.Utils.netcdf_lite import read_paramol_data
+    from paramol_b200.Utils.synthetic import perturbed_conformations
+    golden = os.path.join(REPO, "tests", "golden")
+    X10, _, _ = read_paramol_data(os.path.join(golden, "aniline_10_struct.nc"))
+    X = perturbed_conformations(X10, S, sigma=0.005, seed=1234)
+    rng = np.random.default_rng(5)
+    E_ref, F_ref = rng.normal(-43000.0, 5.0, S), rng.normal(0, 50.0, (S, 14, 3))
+    out = {}
+    for delta in (False, True):
+        engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(golden, "aniline.prmtop"),
+                            crd_file=os.path.join(golden, "aniline.inpcrd"))
+        system = ParaMolSystem("aniline", engine, 14, ref_coordinates=X, ref_energies=E_ref, ref_forces=F_ref)
+        system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
+        ps = ParameterSpace()
+        _, x0 = ps.get_optimizable_parameters([system])
+        x0 = np.asarray(x0, dtype=np.float64)
+        ps.calculate_prior_widths("arithmetic")
+        e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type="components")
+        e_prop.calculate_variance()
+        f_prop.calculate_variance()
+        of = ObjectiveFunction(None, ps, [e_prop, f_prop, Regularization(x0.copy(), ps.prior_widths, "L2")], [system],
+                               checkpoint_freq=10 ** 9, delta_evaluation=delta)
+        r2 = np.random.default_rng(9)
+        x = x0.copy()
+        of.f(x)
+        vals = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(rounds):
+            trial = np.repeat(x[None], batch, 0)
+            which = r2.choice(len(x), batch, replace=False)
+            trial[np.arange(batch), which] *= 1.0 + 0.01 * r2.uniform(-1, 1, batch)
+            v = of.f_batch(trial)
+            vals.append(v)
+            x = trial[int(np.argmin(v))].copy()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["delta" if delta else "full"] = dict(seconds=dt, objective_evals_per_s=rounds * batch / dt, values=np.concatenate(vals),
+                                                 delta_rows=of.n_delta_rows)
+        del of, system, engine
+        torch.cuda.empty_cache()
+    err = float(np.abs(out["delta"]["values"] - out["full"]["values"]).max() / np.abs(out["full"]["values"]).max())
+    return dict(config=7, workload="Monte Carlo batches: aniline, S=%d conformations, %d single-parameter proposals per f_batch, %d batches, "
+                "through ObjectiveFunction.f_batch (host vectors in, values out)" % (S, batch, rounds),
+                full_objective_evals_per_s=out["full"]["objective_evals_per_s"],
+                delta_objective_evals_per_s=out["delta"]["objective_evals_per_s"],
+                speedup=out["delta"]["objective_evals_per_s"] / out["full"]["objective_evals_per_s"],
+                delta_rows=out["delta"]["delta_rows"], max_rel_difference=err)
+
+
 if __name__ == "__main__":
     which = [int(a) for a in sys.argv[1:]] or [3, 4, 5]
     if 6 in which:
@@ -195,4 +253,4 @@ if __name__ == "__main__":
         print(json.dumps(config6("aniline", 1 << 20)), flush=True)
         print(json.dumps(config6("lig60", 100_000)), flush=True)
     for c in which:
-        print(json.dumps({3: config3, 4: config4, 5: config5}[c]()), flush=True)
+        print(json.dumps({3: config3, 4: config4, 5: config5, 7: config7}[c]()), flush=True)
