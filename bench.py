@@ -15,7 +15,7 @@ Printed JSON line (rank 0):
              (pm_prepare_params + pm_eval + pm_reduce_objective + allreduce per step, CUDA-event timed)
   e2e        the same metric through the public API ``ObjectiveFunction.f(x)`` with a HOST parameter vector: numpy
              plumbing, pinned H2D of the slot row, kernels, allreduce, D2H of the partial sums, every step
-  roofline   dominant kernel pm_ef_kernel<true>: algorithmic FP64 flops / CUDA-event kernel time against the DFMA peak
+  roofline   dominant kernel (pm_ef_spec_kernel for small molecules, else pm_ef_kernel<true>): algorithmic FP64 flops / CUDA-event kernel time against the DFMA peak
              measured live on this GPU (the kernel is FP64-pipe bound); ``hbm`` holds the same kernel
              against the measured copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline  the FP64 CPU oracle (oracle/oracle.c, OpenMP over conformations, all host cores) on a bounded sample
@@ -391,7 +391,9 @@ def run_ours(args):
                                 "note": "one-time pinned-host -> HBM staging of the conformation tiles, outside the step"}},
         "gpu_launches": 4 * args.steps,
         "objective_evals_per_s": args.steps / t_dev,
-        "roofline": {"bound": "fp64", "kernel": "pm_ef_kernel<true>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp64", "kernel": ("pm_ef_spec_kernel (topology-specialised code generated for this molecule, csrc/specialize.py)"
+                                                 if getattr(topo, "specialized", False) else "pm_ef_kernel<true>"),
+                     "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak, "traffic": traffic,
                      "peak_source": "FP64 pipe peak measured live by pm_measure_fma_peak on this GPU (DFMA with a uniform addend = DMMA rate; 3-register-operand DFMA streams reach 0.92 of it)",
                      "flops_per_conformation": flops_conf, "kernel_ms": 1e3 * t_kernel,

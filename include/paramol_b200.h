@@ -153,6 +153,17 @@ int pm_resp_assemble(int n_atoms, const double *coords_dev, const double *grid_d
 int pm_esp_potential(int n_atoms, const double *coords_dev, const double *grid_dev, const double *charges_dev,
                      long n_conf, int n_grid, double *vmm_dev, void *stream);
 
+/* ---- topology-specialised E+F kernel ------------------------------------------------------------------- */
+/* pm_set_specialized installs a cubin image holding `pm_ef_spec_kernel` and `__constant__ double spec_tab[]`, generated for
+ * exactly this topology by paramol_b200/csrc/specialize.py (the topology as straight-line code); pm_eval / pm_eval_ex then use
+ * it for full E+F evaluations (mode 0, with_forces = 1) and the generic kernel for everything else.  Same inputs, same
+ * outputs, same reference code replaced as pm_eval.  image = NULL removes it.  Needs pm_conf_per_tile(h) == 32.
+ * pm_topology_pairs (host only, no CUDA call): the pair list in derived-table order for a given conformations-per-tile value,
+ * so that the source can be generated and compiled before a GPU is present. */
+int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps);
+int pm_has_specialized(pm_handle h);
+int pm_topology_pairs(const pm_topology *topo, int cpw, int *n_pairs, int *out_pairs);
+
 /* ---- analytic parameter gradient ---------------------------------------------------------------------- */
 /* d f / d p for ONE parameter vector, where f = sum_s [ g(E_s) + b_s sum_a (F_sa - Fref_sa)^T M_a (F_sa - Fref_sa) ]:
  * the caller passes a_s = d f / d E_s (coef_e_dev [S], or NULL when the objective has no energy part) and b_s (coef_f_dev [S],

@@ -40,6 +40,50 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(index).cuda_stream)
 
 
+def _pm_topology(mm_system):
+    """(PmTopology, arrays it points into) for an :obj:`MMSystem`.  Exceptions whose initial chargeProd and epsilon are both
+    zero are pure exclusions; every other exception is a scaled 1-4 interaction."""
+    s = mm_system
+    keep = dict(
+        bond=np.ascontiguousarray(s.bond_idx, dtype=np.int32).reshape(-1, 2),
+        angle=np.ascontiguousarray(s.angle_idx, dtype=np.int32).reshape(-1, 3),
+        tors=np.ascontiguousarray(s.torsion_idx, dtype=np.int32).reshape(-1, 4),
+        tper=np.ascontiguousarray(s.torsion_per, dtype=np.int32).reshape(-1),
+        exc=np.ascontiguousarray(s.exception_idx, dtype=np.int32).reshape(-1, 2),
+    )
+    par = np.asarray(s.exception_par, dtype=np.float64).reshape(-1, 3)
+    keep["act"] = np.ascontiguousarray(((par[:, 0] != 0.0) | (par[:, 2] != 0.0)).astype(np.int32))
+    k = keep
+    topo = PmTopology(int(s.n_atoms),
+                      len(k["bond"]), _iptr(k["bond"]),
+                      len(k["angle"]), _iptr(k["angle"]),
+                      len(k["tors"]), _iptr(k["tors"]), _iptr(k["tper"]),
+                      len(k["exc"]), _iptr(k["exc"]), _iptr(k["act"]),
+                      0 if s.nonbonded_method == "NoCutoff" else 1,
+                      float(s.cutoff), float(s.rf_dielectric), float(s.one_4pi_eps0))
+    return topo, keep
+
+
+def prebuild_specialized(mm_system):
+    """Generate and compile (into the in-tree cache) the topology-specialised kernel of ``mm_system`` WITHOUT a GPU: the pair
+    list comes from the host-only ``pm_topology_pairs``.  Returns the image size in bytes, or 0 when the molecule is not
+    eligible.  ``DeviceTopology`` finds the cached image later by the hash of the same source."""
+    from ..csrc import specialize
+    if mm_system.nonbonded_method != "NoCutoff":
+        return 0
+    warps = specialize.choose_warps(int(mm_system.n_atoms))
+    if warps is None:
+        return 0
+    L = _lib.lib()
+    topo, keep = _pm_topology(mm_system)
+    n = ctypes.c_int()
+    _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), None), "pm_topology_pairs")
+    pairs = np.zeros((max(n.value, 1), 3), dtype=np.int32)
+    _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), _iptr(pairs)), "pm_topology_pairs")
+    image = specialize.image_for(int(mm_system.n_atoms), keep["bond"], keep["angle"], keep["tors"], keep["tper"], pairs[:n.value], warps)
+    return len(image)
+
+
 class DeviceTopology:
     """
     One ``pm_handle``: the topology "program" of a molecule on one GPU.
@@ -63,24 +107,9 @@ class DeviceTopology:
         s = mm_system
         self.n_atoms = int(s.n_atoms)
         self.k_coul = float(s.one_4pi_eps0)
-        self._keep = dict(
-            bond=np.ascontiguousarray(s.bond_idx, dtype=np.int32).reshape(-1, 2),
-            angle=np.ascontiguousarray(s.angle_idx, dtype=np.int32).reshape(-1, 3),
-            tors=np.ascontiguousarray(s.torsion_idx, dtype=np.int32).reshape(-1, 4),
-            tper=np.ascontiguousarray(s.torsion_per, dtype=np.int32).reshape(-1),
-            exc=np.ascontiguousarray(s.exception_idx, dtype=np.int32).reshape(-1, 2),
-        )
-        par = np.asarray(s.exception_par, dtype=np.float64).reshape(-1, 3)
-        self.exception_active = np.ascontiguousarray(((par[:, 0] != 0.0) | (par[:, 2] != 0.0)).astype(np.int32))
-        self._keep["act"] = self.exception_active
+        topo, self._keep = _pm_topology(s)
+        self.exception_active = self._keep["act"]
         k = self._keep
-        topo = PmTopology(self.n_atoms,
-                          len(k["bond"]), _iptr(k["bond"]),
-                          len(k["angle"]), _iptr(k["angle"]),
-                          len(k["tors"]), _iptr(k["tors"]), _iptr(k["tper"]),
-                          len(k["exc"]), _iptr(k["exc"]), _iptr(k["act"]),
-                          0 if s.nonbonded_method == "NoCutoff" else 1,
-                          float(s.cutoff), float(s.rf_dielectric), float(s.one_4pi_eps0))
         h = ctypes.c_void_p()
         _lib.check(L.pm_create(ctypes.byref(topo), self.device, ctypes.byref(h)), "pm_create")
         self._h = h
@@ -99,6 +128,34 @@ class DeviceTopology:
         self.off_particle = self.off_torsion + 2 * self.n_torsions
         self.off_exception = self.off_particle + 3 * self.n_atoms
         assert self.off_exception + 3 * self.n_exceptions == self.n_slots
+        self.specialized = False
+        self._maybe_specialize(s)
+
+    def _maybe_specialize(self, mm_system):
+        """
+        Small molecules: install a topology-specialised E+F kernel (``csrc/specialize.py``, ``pm_set_specialized``).  Controlled by
+        ``PARAMOL_B200_SPECIALIZE`` ("0" off, anything else / unset: automatic).  If the compiler is not available the generic
+        kernel stays in place -- both are the CUDA path; nothing falls back to the CPU.
+        """
+        import os
+        if os.environ.get("PARAMOL_B200_SPECIALIZE", "auto") == "0" or mm_system.nonbonded_method != "NoCutoff":
+            return
+        if self.conf_per_tile != 32:
+            return
+        from ..csrc import specialize
+        warps = specialize.choose_warps(self.n_atoms)
+        if warps is None:
+            return
+        k = self._keep
+        try:
+            image = specialize.image_for(self.n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], self.pairs(), warps)
+        except RuntimeError as exc:
+            import logging
+            logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
+            return
+        buf = ctypes.create_string_buffer(image, len(image))
+        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps), "pm_set_specialized")
+        self.specialized = True
 
     def __del__(self):
         try:

@@ -55,6 +55,14 @@ struct pm_handle_s {
     std::vector<int> bond_idx, angle_idx, torsion_idx, torsion_per;
     void *grad_state;               // owned by pm_grad_kernels.cu
     void (*grad_free)(void *);
+    void *spec_state;               // owned by pm_spec.cu: a topology-specialised E+F kernel, or null
+    void (*spec_free)(void *);
 };
 
 int pm_fail_msg(const std::string &msg);  // sets pm_last_error(), returns 1 (pm_kernels.cu)
+
+// pm_spec.cu
+int pm_spec_metric_changed(pm_handle h);
+int pm_spec_launch_info(pm_handle h, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel is installed
+int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
+                 double *fres, double *fmm_t, cudaStream_t stream);

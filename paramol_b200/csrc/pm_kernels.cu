@@ -824,6 +824,21 @@ extern "C" int pm_program_check(const pm_topology *t, int cpw, int *stats10) {
     return 0;
 }
 
+// Host-only: the interacting pair list (i, j, exception or -1) in derived-table order for a given CPW (no CUDA call).
+extern "C" int pm_topology_pairs(const pm_topology *t, int cpw, int *n_pairs, int *out_pairs) {
+    if (!t || !n_pairs) return pm_fail("pm_topology_pairs: null argument");
+    if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_topology_pairs: cpw must be 32, 16, 8 or 4");
+    std::vector<int> cls;
+    if (pm_classify(t, cls)) return 1;
+    PmHostProgram p;
+    if (!pm_build_program(t->n_atoms, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+                          t->torsion_per, cls, p))
+        return pm_fail("pm_topology_pairs: degenerate bonded term (repeated atom)");
+    *n_pairs = p.n_pairs;
+    if (out_pairs) memcpy(out_pairs, p.pair_map.data(), sizeof(int) * p.pair_map.size());
+    return 0;
+}
+
 extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     if (!t || !out) return pm_fail("pm_create: null argument");
     if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_create: n_atoms out of range");
@@ -890,6 +905,8 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     h->rf = rf;
     h->grad_state = nullptr;
     h->grad_free = nullptr;
+    h->spec_state = nullptr;
+    h->spec_free = nullptr;
     h->bond_idx.assign(t->bond_idx, t->bond_idx + 2 * (size_t)t->n_bonds);
     h->angle_idx.assign(t->angle_idx, t->angle_idx + 3 * (size_t)t->n_angles);
     h->torsion_idx.assign(t->torsion_idx, t->torsion_idx + 4 * (size_t)t->n_torsions);
@@ -1006,6 +1023,7 @@ extern "C" int pm_destroy(pm_handle h) {
     cudaFree(h->d_pair_map);
     cudaFree(h->d_acos);
     if (h->grad_state && h->grad_free) h->grad_free(h->grad_state);
+    if (h->spec_state && h->spec_free) h->spec_free(h->spec_state);
     delete h;
     return 0;
 }
@@ -1028,6 +1046,7 @@ extern "C" int pm_launch_info(pm_handle h, int with_forces, int *grid, int *bloc
     if (block) *block = h->warps[wf] * 32;
     if (smem_bytes) *smem_bytes = (int)h->smem_total[wf];
     if (warps_per_cta) *warps_per_cta = h->warps[wf];
+    if (wf) pm_spec_launch_info(h, block, smem_bytes, warps_per_cta);  // full E+F evaluations run the specialised kernel if present
     return 0;
 }
 extern "C" int pm_program_info(pm_handle h, int *out10) {
@@ -1043,6 +1062,7 @@ extern "C" int pm_set_force_metric(pm_handle h, const double *metric_host) {
     if (!h || !metric_host) return pm_fail("pm_set_force_metric: null argument");
     PM_CUDA(cudaSetDevice(h->device));
     PM_CUDA(cudaMemcpy(h->d_metric, metric_host, sizeof(double) * 9 * h->prog.n_atoms, cudaMemcpyHostToDevice));
+    if (pm_spec_metric_changed(h)) return 1;
     return 0;
 }
 
@@ -1089,6 +1109,9 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
     if (mode < 0 || mode > 2) return pm_fail("pm_eval_ex: mode must be 0 (all terms), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
     if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval_ex: mode 2 needs the cached nonbonded arrays");
     PM_CUDA(cudaSetDevice(h->device));
+    if (h->spec_state && mode == 0 && with_forces)  // full E+F evaluation of a small molecule: the topology-specialised kernel
+        return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
+                            (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
     const int warps = h->warps[wf];

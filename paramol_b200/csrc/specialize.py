@@ -1,0 +1,415 @@
+# -*- coding: utf-8 -*-
+"""
+Topology-specialised E+F kernel generator.
+
+The generic kernel ``pm_ef_kernel`` (pm_kernels.cu) interprets a topology "program": every atom index, parameter offset
+and loop bound is data.  For a given molecule all of that is known when the handle is created, so this module emits a CUDA
+kernel in which the topology is CODE: straight-line blocks with immediate shared-memory offsets, the derived parameter
+table in ``__constant__`` memory (parameters are direct constant-bank operands of the FP64 instructions), forces accumulated in registers (small molecules) or in the shared force tile with immediate offsets, and
+one big basic block per conformation that lets ptxas interleave independent terms to cover the 8-cycle DFMA latency.
+The arithmetic (trig-free torsions, table acos, c12/c6 pairs, the residual epilogue) is that of the generic kernel, term by
+term, so results agree to rounding (measured: 5e-16 relative on E, F and the residual).
+
+Same scope as the generic kernel for: one lane per conformation (CPW = 32), NoCutoff, full evaluation (mode 0).
+"""
+import numpy as np
+
+
+def _d3(name):
+    return "%s.x, %s.y, %s.z" % (name, name, name)
+
+
+class KernelSource:
+    def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers=True, name="pm_ef_spec_kernel",
+                 x_in_registers=False, fence_every=0, sync_every=0):
+        """
+        bonds [nb,2], angles [na,3], torsions [nt,4], tors_per [nt], pairs [np,3] = (i, j, exception or -1) in the
+        order of the derived table (pm_get_pairs).  Derived layout: bonds (r0,k) | angles (t0,k) | torsions
+        (k, kn, cos, sin) | pairs (c12, c6, Kqq).
+        """
+        self.N = int(n_atoms)
+        self.bonds = [tuple(int(v) for v in b) for b in np.asarray(bonds).reshape(-1, 2)]
+        self.angles = [tuple(int(v) for v in a) for a in np.asarray(angles).reshape(-1, 3)]
+        self.torsions = [tuple(int(v) for v in t) for t in np.asarray(torsions).reshape(-1, 4)]
+        self.tors_per = [int(v) for v in np.asarray(tors_per).reshape(-1)]
+        self.pairs = [tuple(int(v) for v in p) for p in np.asarray(pairs).reshape(-1, 3)]
+        self.f_reg = bool(f_in_registers)
+        self.x_reg = bool(x_in_registers)
+        self.fence_every = int(fence_every)
+        self.sync_every = int(sync_every)
+        self._blocks = 0
+        self.name = name
+        self.off_bond = 0
+        self.off_angle = 2 * len(self.bonds)
+        self.off_tors = self.off_angle + 2 * len(self.angles)
+        self.off_pair = self.off_tors + 4 * len(self.torsions)
+        self.n_derived = self.off_pair + 3 * len(self.pairs)
+        self.lines = []
+        self._uid = 0
+
+    # ---- emission helpers -----------------------------------------------------------------------
+    def emit(self, text):
+        self.lines.append(text)
+
+    def uid(self):
+        self._uid += 1
+        return self._uid
+
+    def P(self, off):
+        return "spec_tab[%d]" % off
+
+    def X(self, atom):
+        return ("X%d" % atom) if self.x_reg else ("PMX(%d)" % atom)
+
+    def end_block(self):
+        """Close a star / axis / pair block; every ``fence_every`` blocks a compiler-level memory fence keeps ptxas from
+        hoisting the loads of all later blocks to the top (which costs more registers than the interleaving gains)."""
+        self.emit("}")
+        self._blocks += 1
+        if self.sync_every and self._blocks % self.sync_every == 0:
+            # keeps the warps of the CTA within the same stretch of this (instruction-cache sized) straight-line code, so that a
+            # fetched line serves all of them; the trip count of the tile loop is uniform per CTA for that reason
+            self.emit("__syncthreads();")
+        elif self.fence_every and self._blocks % self.fence_every == 0:
+            self.emit('asm volatile("" ::: "memory");')
+
+    def addf(self, atom, expr_vec, sign="+"):
+        if self.f_reg:
+            self.emit("F%d.x %s= %s.x; F%d.y %s= %s.y; F%d.z %s= %s.z;" % (atom, sign, expr_vec, atom, sign, expr_vec, atom, sign, expr_vec))
+        else:
+            self.emit("PMF_%s(%d, %s);" % ("ADD" if sign == "+" else "SUB", atom, expr_vec))
+
+    # ---- stars: bonds + angles around a centre ---------------------------------------------------
+    def gen_stars(self):
+        N = self.N
+        nbrs = [[] for _ in range(N)]
+        bond_of = {}
+        for t, (i, j) in enumerate(self.bonds):
+            bond_of[(i, j)] = t
+            bond_of[(j, i)] = t
+        angle_at = [[] for _ in range(N)]
+        for t, (a, b, c) in enumerate(self.angles):
+            angle_at[b].append((t, a, c))
+        done_bond = set()
+        # geometry neighbours of a centre: every atom it shares a bond or an angle with
+        for c in range(N):
+            need = []
+            for (i, j) in self.bonds:
+                if i == c and j not in need:
+                    need.append(j)
+                if j == c and i not in need:
+                    need.append(i)
+            for (_, a, b) in angle_at[c]:
+                for v in (a, b):
+                    if v not in need:
+                        need.append(v)
+            own = [n for n in need if (c, n) in bond_of and bond_of[(c, n)] not in done_bond]
+            if not own and not angle_at[c]:
+                continue
+            used = set(own)
+            for (_, a, b) in angle_at[c]:
+                used.update((a, b))
+            need = [n for n in need if n in used]
+            self.emit("{  // star %d" % c)
+            self.emit("const pm_d3 xc = %s;" % self.X(c))
+            self.emit("pm_d3 fc = pm_d3{0.0, 0.0, 0.0};")
+            for n in need:
+                self.emit("const pm_d3 d%d = pm_sub(xc, %s); const double q%d = pm_dot(d%d, d%d); const double i%d = pm_rsqrt(q%d);"
+                          % (n, self.X(n), n, n, n, n, n))
+                self.emit("pm_d3 f%d = pm_d3{0.0, 0.0, 0.0};" % n)
+            for n in own:
+                t = bond_of[(c, n)]
+                done_bond.add(t)
+                o = self.off_bond + 2 * t
+                self.emit("{ const double dl = fma(q%d, i%d, -%s); const double kd = %s * dl; e_bond = fma(0.5 * kd, dl, e_bond);"
+                          " const double g = kd * i%d; pm_axpy(f%d, g, d%d); pm_axpy(fc, -g, d%d); }" % (n, n, self.P(o), self.P(o + 1), n, n, n, n))
+            for (t, a, b) in angle_at[c]:
+                o = self.off_angle + 2 * t
+                # d0 = x_centre - x_a, d1 = x_centre - x_b  (ReferenceAngleBondIxn; see pm_delta_kernels.cu for the same algebra)
+                self.emit("{ const pm_d3 pc = pm_cross(d%d, d%d); const double pp2 = pm_dot(pc, pc); const double i01 = i%d * i%d;" % (a, b, a, b))
+                self.emit("  const double ip = pm_rsqrt(fmax(pp2, 1.0e-12)); const double th = pm_acos_cs(pm_dot(d%d, d%d) * i01, pp2 * ip * i01, s_acos);" % (a, b))
+                self.emit("  const double dl = th - %s; const double dd = %s * dl; e_angle = fma(0.5 * dd, dl, e_angle);" % (self.P(o), self.P(o + 1)))
+                self.emit("  const double ta = dd * ip * (i%d * i%d), tc = -dd * ip * (i%d * i%d);" % (a, a, b, b))
+                self.emit("  const pm_d3 c0 = pm_cross(d%d, pc), c2 = pm_cross(d%d, pc);" % (a, b))
+                self.emit("  pm_axpy(f%d, ta, c0); pm_axpy(f%d, tc, c2); pm_axpy(fc, -ta, c0); pm_axpy(fc, -tc, c2); }" % (a, b))
+            self.addf(c, "fc")
+            for n in need:
+                self.addf(n, "f%d" % n)
+            self.end_block()
+        assert len(done_bond) == len(self.bonds)
+
+    # ---- axes: all torsions around j-k -----------------------------------------------------------
+    def gen_axes(self):
+        axes = {}
+        for t, (i, j, k, l) in enumerate(self.torsions):
+            if (k, j) in axes:                      # same axis, opposite orientation: phi(l,k,j,i) = phi(i,j,k,l)
+                axes[(k, j)].append((t, l, i))
+            else:
+                axes.setdefault((j, k), []).append((t, i, l))
+        for (j, k), terms in axes.items():
+            subs_i = sorted({i for (_, i, _) in terms})
+            subs_l = sorted({l for (_, _, l) in terms})
+            self.emit("{  // axis %d-%d" % (j, k))
+            self.emit("const pm_d3 xj = %s, xk = %s; const pm_d3 d1 = pm_sub(xk, xj); const double bb = pm_dot(d1, d1);" % (self.X(j), self.X(k)))
+            self.emit("const double rbb = pm_rsqrt(bb); const double nb = bb * rbb, ibb = rbb * rbb;")
+            self.emit("pm_d3 fj = pm_d3{0.0, 0.0, 0.0}, fk = pm_d3{0.0, 0.0, 0.0};")
+            for i in subs_i:
+                self.emit("const pm_d3 a%d = pm_sub(%s, xj); const pm_d3 u%d = pm_cross(a%d, d1); const double m%d = pm_dot(u%d, u%d);"
+                          " const double s%d = pm_rsqrt(m%d); const double g%d = pm_dot(a%d, d1) * ibb; pm_d3 fi%d = pm_d3{0.0, 0.0, 0.0};"
+                          % (i, self.X(i), i, i, i, i, i, i, i, i, i, i))
+            for l in subs_l:
+                self.emit("const pm_d3 b%d = pm_sub(xk, %s); const pm_d3 w%d = pm_cross(d1, b%d); const double n%d = pm_dot(w%d, w%d);"
+                          " const double t%d = pm_rsqrt(n%d); const double h%d = pm_dot(b%d, d1) * ibb; pm_d3 fl%d = pm_d3{0.0, 0.0, 0.0};"
+                          % (l, self.X(l), l, l, l, l, l, l, l, l, l, l))
+            cells = {}
+            for (t, i, l) in terms:
+                cells.setdefault((i, l), []).append(t)
+            for (i, l), ts in cells.items():
+                ts = sorted(ts, key=lambda t: self.tors_per[t])
+                self.emit("{ const double i12 = s%d * t%d; const double cphi = pm_dot(u%d, w%d) * i12, sphi = nb * pm_dot(a%d, w%d) * i12;" % (i, l, i, l, i, l))
+                self.emit("  double cn = 1.0, sn = 0.0, dd = 0.0;")
+                cur = 0
+                for t in ts:
+                    per = self.tors_per[t]
+                    while cur < per:
+                        self.emit("  { const double tt = cn * cphi - sn * sphi; sn = fma(sn, cphi, cn * sphi); cn = tt; }")
+                        cur += 1
+                    o = self.off_tors + 4 * t
+                    self.emit("  e_tors += %s * (1.0 + fma(cn, %s, sn * %s)); dd -= %s * fma(sn, %s, -(cn * %s));"
+                              % (self.P(o), self.P(o + 2), self.P(o + 3), self.P(o + 1), self.P(o + 2), self.P(o + 3)))
+                # F_0 = -dd |d1| c1 / n1, F_3 = dd |d1| c2 / n2, F_1 = (ff1-1) F_0 - ff2 F_3, F_2 = (ff2-1) F_3 - ff1 F_0
+                self.emit("  const double z0 = -dd * nb * (s%d * s%d), z3 = dd * nb * (t%d * t%d);" % (i, i, l, l))
+                self.emit("  const pm_d3 f0 = pm_d3{z0 * u%d.x, z0 * u%d.y, z0 * u%d.z}, f3 = pm_d3{z3 * w%d.x, z3 * w%d.y, z3 * w%d.z};" % (i, i, i, l, l, l))
+                self.emit("  pm_axpy(fi%d, 1.0, f0); pm_axpy(fl%d, 1.0, f3);" % (i, l))
+                self.emit("  pm_axpy(fj, g%d - 1.0, f0); pm_axpy(fj, -h%d, f3); pm_axpy(fk, h%d - 1.0, f3); pm_axpy(fk, -g%d, f0); }" % (i, l, l, i))
+            self.addf(j, "fj")
+            self.addf(k, "fk")
+            for i in subs_i:
+                self.addf(i, "fi%d" % i)
+            for l in subs_l:
+                self.addf(l, "fl%d" % l)
+            self.end_block()
+
+    # ---- pairs ---------------------------------------------------------------------------------
+    def gen_pairs(self):
+        by_i = {}
+        for q, (i, j, _) in enumerate(self.pairs):
+            by_i.setdefault(i, []).append((q, j))
+        for i, lst in by_i.items():
+            self.emit("{  // pairs of atom %d" % i)
+            self.emit("const pm_d3 xi = %s; pm_d3 fi = pm_d3{0.0, 0.0, 0.0};" % self.X(i))
+            for (q, j) in lst:
+                o = self.off_pair + 3 * q
+                self.emit("{ const pm_d3 d = pm_sub(xi, %s); const double rinv = pm_rsqrt(pm_dot(d, d)); const double u = rinv * rinv; const double u3 = u * u * u;" % self.X(j))
+                self.emit("  const double a = %s * u3; const double b = a - %s; const double cq = %s * rinv; e_nb = fma(b, u3, e_nb); e_nb += cq;" % (self.P(o), self.P(o + 1), self.P(o + 2)))
+                self.emit("  const double g = fma(6.0 * u3, a + b, cq) * u; const pm_d3 fv = pm_d3{g * d.x, g * d.y, g * d.z}; pm_axpy(fi, g, d);")
+                self.addf(j, "fv", "-")
+                self.emit("}")
+            self.addf(i, "fi")
+            self.end_block()
+
+    # ---- the kernel ----------------------------------------------------------------------------
+    def source(self, warps):
+        N = self.N
+        self.lines = []
+        self._blocks = 0
+        self.gen_stars()
+        self.gen_axes()
+        self.gen_pairs()
+        body = "\n            ".join(self.lines)
+        f_decl = "\n            ".join("pm_d3 F%d = pm_d3{0.0, 0.0, 0.0};" % a for a in range(N)) if self.f_reg else \
+            "for (int k = lane; k < TILE_D; k += 32) fs[k] = 0.0; __syncwarp();"
+        res_lines = []
+        for a in range(N):
+            if self.f_reg:
+                fx, fy, fz = "F%d.x" % a, "F%d.y" % a, "F%d.z" % a
+            else:
+                fx, fy, fz = "fs[%d * 32 + lane]" % (3 * a), "fs[%d * 32 + lane]" % (3 * a + 1), "fs[%d * 32 + lane]" % (3 * a + 2)
+            res_lines.append("{ const double dx = %s - fr[%d * 32], dy = %s - fr[%d * 32], dz = %s - fr[%d * 32];" % (fx, 3 * a, fy, 3 * a + 1, fz, 3 * a + 2))
+            m = ["spec_tab[SPEC_ND + %d]" % (9 * a + q) for q in range(9)]
+            res_lines.append("  const double t0 = fma(dz, %s, fma(dy, %s, dx * %s)), t1 = fma(dz, %s, fma(dy, %s, dx * %s)), t2 = fma(dz, %s, fma(dy, %s, dx * %s));"
+                             % (m[6], m[3], m[0], m[7], m[4], m[1], m[8], m[5], m[2]))
+            res_lines.append("  res += fma(t2, dz, fma(t1, dy, t0 * dx)); }")
+        res = "\n                ".join(res_lines)
+        if self.f_reg:
+            fout = "\n                ".join("fo[%d * 32] = F%d.x; fo[%d * 32] = F%d.y; fo[%d * 32] = F%d.z;" % (3 * a, a, 3 * a + 1, a, 3 * a + 2, a) for a in range(N))
+        else:
+            fout = "for (int k = 0; k < %d; ++k) fo[k * 32] = fs[k * 32 + lane];" % (3 * N)
+        if self.x_reg:
+            x_load = "const double *xg = xt + (size_t)tile * TILE_D + lane;\n        " + "\n        ".join(
+                "const pm_d3 X%d = pm_d3{xg[%d * 32], xg[%d * 32], xg[%d * 32]};" % (a, 3 * a, 3 * a + 1, 3 * a + 2) for a in range(N))
+        else:
+            x_load = ""
+        return _TEMPLATE.format(name=self.name, N=N, ND=max(self.n_derived, 1), W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
+                                f_tile=0 if self.f_reg else 1, x_tile=0 if self.x_reg else 1, x_load=x_load)
+
+
+_TEMPLATE = r'''// generated by paramol_b200/csrc/specialize.py -- do not edit
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pm_device.cuh"
+
+#define SPEC_N {N}
+#define SPEC_ND {ND}
+#define TILE_D (3 * SPEC_N * 32)
+#define PMX(a) pm_d3{{xc_base[(3 * (a)) * 32], xc_base[(3 * (a) + 1) * 32], xc_base[(3 * (a) + 2) * 32]}}
+#define PMF_ADD(a, v) do {{ fc_base[(3 * (a)) * 32] += (v).x; fc_base[(3 * (a) + 1) * 32] += (v).y; fc_base[(3 * (a) + 2) * 32] += (v).z; }} while (0)
+#define PMF_SUB(a, v) do {{ fc_base[(3 * (a)) * 32] -= (v).x; fc_base[(3 * (a) + 1) * 32] -= (v).y; fc_base[(3 * (a) + 2) * 32] -= (v).z; }} while (0)
+
+// derived table of the parameter vector being evaluated (pm_prepare_params layout), then the 9 N force-metric entries; the
+// host copies them here before the launch, so every parameter is a constant-bank operand with an immediate offset
+__constant__ double spec_tab[SPEC_ND + 9 * SPEC_N];
+
+extern "C" __global__ void __launch_bounds__({W} * 32, 1)
+    {name}(const double2 *__restrict__ acos_tab, const double *__restrict__ xt,
+           const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm, double *__restrict__ fres,
+           double *__restrict__ fmm_t) {{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
+    size_t off = ((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127;
+    const size_t per_warp = 128 + (size_t)TILE_D * sizeof(double) * ({f_tile} + {x_tile});
+    unsigned char *wbase = smem_raw + off + per_warp * warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
+    double *xs = reinterpret_cast<double *>(wbase + 128);
+    double *fs = xs + ({x_tile} ? TILE_D : 0);
+    (void)fs;
+    for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = acos_tab[i];
+    if (lane == 0) {{
+        pm_mbar_init(bar, 1);
+        pm_fence_mbar_init();
+    }}
+    __syncthreads();
+    uint32_t parity = 0;
+    const long warp_stride = (long)gridDim.x * n_warps;
+    // uniform trip count per CTA (the body may contain CTA barriers): a warp without a tile of its own repeats the last tile
+    // of the problem and stores nothing
+    const long first_cta = (long)blockIdx.x * n_warps;
+    const long n_iter = first_cta < n_tiles ? (n_tiles - first_cta + warp_stride - 1) / warp_stride : 0;
+    for (long it = 0; it < n_iter; ++it) {{
+        long tile = first_cta + warp + it * warp_stride;
+        const bool live = tile < n_tiles;
+        if (!live) tile = n_tiles - 1;
+        if (lane == 0) {{
+            if ({x_tile}) {{
+                pm_fence_proxy_async();
+                pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
+                pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+            }}
+            if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+            if (tile + warp_stride < n_tiles) pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+        }}
+        {x_load}
+        {f_decl}
+        if ({x_tile}) {{
+            pm_mbar_wait(bar, parity);
+            parity ^= 1;
+        }}
+        __syncwarp();
+        const double *xc_base = xs + lane;
+        double *fc_base = fs + lane;
+        (void)fc_base;
+        double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
+        {{
+            {body}
+        }}
+        const long sconf = tile * 32 + lane;
+        const double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
+        double res = 0.0;
+        if (fres != nullptr) {{
+            const double *fr = fref_t + (size_t)tile * TILE_D + lane;
+            {{
+                {res}
+            }}
+        }}
+        if (live && sconf < n_conf) {{
+            emm[sconf] = e_total;
+            if (fres != nullptr) fres[sconf] = res;
+        }}
+        if (live && fmm_t != nullptr) {{
+            double *fo = fmm_t + (size_t)tile * TILE_D + lane;
+            {{
+                {fout}
+            }}
+        }}
+        __syncwarp();
+    }}
+}}
+'''
+
+
+def generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=True, name="pm_ef_spec_kernel",
+             x_in_registers=False, fence_every=0, sync_every=0):
+    return KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers, name, x_in_registers,
+                        fence_every, sync_every).source(warps)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# compile + cache
+# ---------------------------------------------------------------------------------------------------------------------
+MAX_SMEM = 227 * 1024
+FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fences -> 168 registers, no spills, fastest
+SYNC_EVERY = 0
+MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
+MAX_WARPS = 10
+
+
+def choose_warps(n_atoms):
+    """Warps per CTA of the specialised kernel (coordinate + force tile of 32 conformations per warp), or None when too
+    few fit for it to beat the generic kernel."""
+    import math
+    tile = 3 * n_atoms * 32 * 8
+    table = ((257 * 16 + 127) // 128) * 128
+    warps = min(MAX_WARPS, int(math.floor((MAX_SMEM - table) / (128 + 2 * tile))))
+    return warps if warps >= MIN_WARPS else None
+
+
+def _nvcc():
+    import os
+    import shutil
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def cache_dir():
+    import os
+    d = os.environ.get("PARAMOL_B200_SPEC_CACHE") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_spec_cache")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def compile_image(source):
+    """nvcc -cubin for sm_100a, cached in-tree by the hash of the source (the cache travels with the repository snapshot, so
+    a molecule compiled once -- e.g. by ``__graft_entry__.build()`` -- is not compiled again on the GPU box)."""
+    import hashlib
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "pm_device.cuh"), "rb") as fh:
+        key = hashlib.sha256(source.encode() + fh.read()).hexdigest()[:24]
+    path = os.path.join(cache_dir(), key + ".cubin")
+    if not os.path.exists(path):
+        nvcc = _nvcc()
+        if nvcc is None:
+            raise RuntimeError("nvcc not found: cannot compile the topology-specialised kernel")
+        src = os.path.join(cache_dir(), key + ".cu")
+        with open(src, "w") as fh:
+            fh.write(source)
+        tmp = path + ".tmp%d" % os.getpid()
+        res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-I", here,
+                              src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on the specialised kernel:\n" + res.stdout[-2000:])
+        os.replace(tmp, path)
+    with open(path, "rb") as fh:
+        return fh.read()
+
+
+def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs, warps):
+    import os
+    fence = int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY))
+    sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
+    return compile_image(generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=False,
+                                  x_in_registers=False, fence_every=fence, sync_every=sync))

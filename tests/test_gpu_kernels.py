@@ -162,3 +162,45 @@ def test_fma_peak_probe():
     fl, ms = ctypes.c_double(), ctypes.c_double()
     _lib.check(L.pm_measure_fma_peak(0, 1, 2000, ctypes.byref(fl), ctypes.byref(ms)))
     assert fl.value > 1e12  # a B200 sustains tens of TFLOP/s of DFMA
+
+
+@pytest.mark.parametrize("n_atoms", [5, 12, 15, 16])
+def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
+    """The topology-specialised kernel (csrc/specialize.py, installed automatically for small molecules) against the generic
+    program-interpreting kernel on the same tiles: energies, residuals and forces to 1e-13, several parameter vectors per
+    call, a partial last tile, non-trivial metric; energy-only calls keep using the generic kernel."""
+    import torch
+    from paramol_b200.MM_engines.b200_engine import B200Engine
+    from paramol_b200.MM_engines.device import DeviceEnsemble, DeviceTopology
+    from paramol_b200.Utils.synthetic import make_ligand
+    mm, x0 = make_ligand(n_atoms)
+    monkeypatch.setenv("PM_CPW", "32")
+    monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "0")
+    generic = DeviceTopology(mm)
+    monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "auto")
+    spec = DeviceTopology(mm)
+    assert not generic.specialized and spec.specialized
+    rng = np.random.default_rng(n_atoms)
+    n_conf = 32 * 7 + 5
+    X = x0[None] + rng.normal(0, 0.01, (n_conf,) + x0.shape)
+    F = rng.normal(0, 50.0, X.shape)
+    metric = np.tile(np.eye(3).ravel(), (n_atoms, 1)) * rng.uniform(0.5, 2.0, (n_atoms, 1))
+    metric[:, 1] += 0.1
+    base = B200Engine(system=mm).current_slots() if False else generic.slots_from_system(mm)
+    rows = base[None] * (1.0 + 0.02 * rng.uniform(-1, 1, (3, len(base))))
+    out = []
+    for topo in (generic, spec):
+        topo.set_force_metric(metric)
+        ens = DeviceEnsemble(topo, X, F, np.zeros(n_conf))
+        der = topo.prepare(torch.from_numpy(rows).cuda())
+        emm, fres, fmm = ens.evaluate(der, with_forces=True, want_fres=True, want_fmm=True)
+        forces = ens.forces_from_tiles(fmm)
+        e_only = ens.evaluate(der, with_forces=False, want_fres=False)[0].clone()
+        out.append((emm.clone(), fres.clone(), forces.clone(), e_only))
+    for a, b in zip(out[0], out[1]):
+        assert (a - b).abs().max().item() <= 1e-13 * a.abs().max().item()
+    # the metric can change after the kernel was installed
+    spec.set_force_metric(2.0 * metric)
+    ens = DeviceEnsemble(spec, X, F, np.zeros(n_conf))
+    fres2 = ens.evaluate(spec.prepare(torch.from_numpy(rows).cuda()), with_forces=True, want_fres=True)[1]
+    assert (fres2 - 2.0 * out[1][1]).abs().max().item() <= 1e-12 * out[1][1].abs().max().item()
