@@ -1,9 +1,8 @@
 #!/usr/bin/env python
-"""cProfile of ObjectiveFunction.f on a small ensemble (host-side overhead per call)."""
-import cProfile, pstats, os, sys, io
-import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
+"""cProfile of ObjectiveFunction.f on the headline workload (host-side overhead per call): `python scripts/profile_f.py [S]`."""
+import cProfile, os, pstats, sys, time
+import numpy as np, torch
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, REPO)
 from paramol_b200.MM_engines.b200_engine import B200Engine
 from paramol_b200.System.system import ParaMolSystem
 from paramol_b200.Parameter_space.parameter_space import ParameterSpace
@@ -13,26 +12,26 @@ from paramol_b200.Objective_function.Properties.force_property import ForcePrope
 from paramol_b200.Objective_function.Properties.regularization import Regularization
 from paramol_b200.Utils.netcdf_lite import read_paramol_data
 from paramol_b200.Utils.synthetic import perturbed_conformations
-G = "tests/golden/"
-e = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=G + "aniline.prmtop", crd_file=G + "aniline.inpcrd")
-s = ParaMolSystem("aniline", e, 14)
-s.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True, opt_charges=True, opt_lj=True, opt_sc=True)
-X10 = read_paramol_data(G + "aniline_10_struct.nc")[0]
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-s.ref_coordinates = perturbed_conformations(X10, n); s.n_structures = n
-rng = np.random.default_rng(0)
-s.ref_energies = rng.normal(0, 5, n); s.ref_forces = rng.normal(0, 100, (n, 14, 3))
-ps = ParameterSpace(); _, x0 = ps.get_optimizable_parameters([s]); x0 = np.asarray(x0)
-ep, fp = EnergyProperty([s]), ForceProperty([s]); ep.calculate_variance(); fp.calculate_variance()
-ps.calculate_prior_widths("default")
-rp = Regularization(x0.copy(), ps.prior_widths, "L2")
-of = ObjectiveFunction(None, ps, [ep, fp, rp], [s], checkpoint_freq=10 ** 12)
-for _ in range(20): of.f(x0.copy())
-import time
-t0 = time.perf_counter()
-for _ in range(500): of.f(x0.copy())
-print("us per f() call (S=%d): %.1f" % (n, 1e6 * (time.perf_counter() - t0) / 500))
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+G = os.path.join(REPO, "tests", "golden")
+X10, _, _ = read_paramol_data(os.path.join(G, "aniline_10_struct.nc"))
+X = perturbed_conformations(X10, S, sigma=0.005, seed=1234)
+rng = np.random.default_rng(5)
+engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(G, "aniline.prmtop"), crd_file=os.path.join(G, "aniline.inpcrd"))
+system = ParaMolSystem("aniline", engine, 14, ref_coordinates=X, ref_energies=rng.normal(-43000.0, 5.0, S), ref_forces=rng.normal(0, 50.0, (S, 14, 3)))
+system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True, opt_charges=True, opt_lj=True, opt_sc=True)
+ps = ParameterSpace(); _, x0 = ps.get_optimizable_parameters([system]); x0 = np.asarray(x0, float)
+ps.calculate_prior_widths("arithmetic")
+e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type="components")
+e_prop.calculate_variance(); f_prop.calculate_variance()
+of = ObjectiveFunction(None, ps, [e_prop, f_prop, Regularization(x0.copy(), ps.prior_widths, "L2")], [system], checkpoint_freq=10**9)
+trial = [x0 * (1 + 0.01 * rng.uniform(-1, 1, len(x0))) for _ in range(300)]
+for x in trial[:20]: of.f(x)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for x in trial: of.f(x)
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / len(trial)
+print("f: %.1f us per call (%.3e conf/s)" % (dt * 1e6, S / dt))
 pr = cProfile.Profile(); pr.enable()
-for _ in range(500): of.f(x0.copy())
+for x in trial: of.f(x)
 pr.disable()
-st = io.StringIO(); pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(22); print(st.getvalue()[:4500])
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
