@@ -30,6 +30,49 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
+def config1(n_calls=300):
+    """BASELINE config 1: the repository's own small case -- aniline, the 10 stored conformations, ENERGY + FORCE + L2 -- where
+    one objective evaluation is pure latency; reported as microseconds per `ObjectiveFunction.f` call with host vectors."""
+    from paramol_b200.Objective_function.objective_function import ObjectiveFunction
+    from paramol_b200.Objective_function.Properties.energy_property import EnergyProperty
+    from paramol_b200.Objective_function.Properties.force_property import ForceProperty
+    from paramol_b200.Objective_function.Properties.regularization import Regularization
+    golden = os.path.join(REPO, "tests", "golden")
+    engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(golden, "aniline.prmtop"),
+                        crd_file=os.path.join(golden, "aniline.inpcrd"))
+    system = ParaMolSystem("aniline", engine, 14)
+    system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True, opt_charges=True, opt_lj=True, opt_sc=True)
+    system.read_data(os.path.join(golden, "aniline_10_struct.nc"))
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    x0 = np.asarray(x0, dtype=np.float64)
+    ps.calculate_prior_widths("arithmetic")
+    out = {}
+    for term in ("components", "norm"):
+        e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type=term)
+        e_prop.calculate_variance()
+        f_prop.calculate_variance()
+        of = ObjectiveFunction(None, ps, [e_prop, f_prop, Regularization(x0.copy(), ps.prior_widths, "L2")], [system], checkpoint_freq=10 ** 9)
+        rng = np.random.default_rng(0)
+        trial = [x0 * (1.0 + 0.01 * rng.uniform(-1, 1, len(x0))) for _ in range(n_calls)]
+        for x in trial[:20]:
+            of.f(x)
+        t0 = time.perf_counter()
+        vals = [of.f(x) for x in trial]
+        dt = (time.perf_counter() - t0) / n_calls
+        t0 = time.perf_counter()
+        of.f_batch(np.stack(trial))
+        db = (time.perf_counter() - t0) / n_calls
+        vg = of.f_and_grad(trial[0])
+        t0 = time.perf_counter()
+        for x in trial[:100]:
+            of.f_and_grad(x)
+        dg = (time.perf_counter() - t0) / 100
+        out[term] = dict(us_per_f=dt * 1e6, us_per_vector_in_f_batch=db * 1e6, us_per_f_and_grad=dg * 1e6, f_first=vals[0])
+    return dict(config=1, workload="aniline, the 10 stored conformations, ENERGY + FORCE + L2, 232 parameters, host vectors in / value out",
+                **{k + "_" + kk: vv for k, v in out.items() for kk, vv in v.items()})
+
+
 def config3(P=256, S=100_000):
     mm, x0 = make_ligand(60)
     engine = B200Engine(system=mm)
@@ -253,4 +296,4 @@ if __name__ == "__main__":
         print(json.dumps(config6("aniline", 1 << 20)), flush=True)
         print(json.dumps(config6("lig60", 100_000)), flush=True)
     for c in which:
-        print(json.dumps({3: config3, 4: config4, 5: config5, 7: config7}[c]()), flush=True)
+        print(json.dumps({1: config1, 3: config3, 4: config4, 5: config5, 7: config7}[c]()), flush=True)
