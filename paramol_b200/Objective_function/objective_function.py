@@ -23,6 +23,7 @@ to the host through ``ParaMolSystem.get_*_ensemble`` and reduced by the numpy pr
 parity tests of the seam, not for speed.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -80,6 +81,7 @@ class ObjectiveFunction:
         self._fused = bool(fused)
         self._cache_nonbonded = bool(cache_nonbonded)
         self._delta = bool(delta_evaluation)
+        self._graphs = os.environ.get("PARAMOL_B200_GRAPHS", "1") != "0"
         self.n_delta_rows = 0
         self._total_n_batches = None
         self._batch_lims = None
@@ -485,6 +487,37 @@ class ObjectiveFunction:
         self.n_delta_rows += slots.shape[0]
         return ens.delta_evaluate(plan, derived)
 
+    def _capture_graph(self, st, ens):
+        """CUDA graph of one single-vector evaluation of ``ens``: pinned slots -> device, ``pm_prepare_params``, the E(+F)
+        kernel, ``pm_reduce_objective``, partial sums -> pinned host.  The graph owns its buffers."""
+        import torch
+        topo = ens.topology
+        g = dict(pin_in=torch.empty((1, topo.n_slots), dtype=torch.float64).pin_memory(),
+                 slots_dev=torch.empty((1, topo.n_slots), dtype=torch.float64, device=ens.device),
+                 derived=torch.empty((1, topo.n_derived), dtype=torch.float64, device=ens.device),
+                 pin_out=torch.empty((1, NPARTIAL), dtype=torch.float64).pin_memory(), bufs={})
+        saved_bufs, saved_scratch = ens._buffers, ens._scratch
+        ens._buffers, ens._scratch = g["bufs"], None
+        try:
+            # allocate the graph's private buffers eagerly (same shapes as the capture will ask for), then capture
+            g["slots_dev"].copy_(g["pin_in"])
+            topo.prepare(g["slots_dev"], g["derived"])
+            emm, fres, _ = ens.evaluate(g["derived"], with_forces=st["need_f"], want_fres=st["need_f"])
+            ens.reduce(emm, fres, d_shift=st["d_shift"])
+            g["scratch"] = ens._scratch
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["slots_dev"].copy_(g["pin_in"], non_blocking=True)
+                topo.prepare(g["slots_dev"], g["derived"])
+                emm, fres, _ = ens.evaluate(g["derived"], with_forces=st["need_f"], want_fres=st["need_f"])
+                part = ens.reduce(emm, fres, d_shift=st["d_shift"])
+                g["pin_out"].copy_(part, non_blocking=True)
+            g["graph"] = graph
+        finally:
+            ens._buffers, ens._scratch = saved_bufs, saved_scratch
+        return g
+
     def _evaluate_fused(self, slots_per_system, X, set_values):
         """
         slots_per_system: list over ``self.systems`` of float64 [P, n_slots]; X [P, P_opt] for the regularisation.
@@ -495,6 +528,9 @@ class ObjectiveFunction:
         e_prop, f_prop, r_prop = self._prop("ENERGY"), self._prop("FORCE"), self._prop("REGULARIZATION")
         partial_list = []
         states = []
+        use_graph = (n_vec == 1 and self._graphs and not self._delta and not self._cache_nonbonded
+                     and self._weighting_method.upper() != "NON_BOLTZMANN" and _dist.world_size() == 1)
+        graph_rows = {}
         for s_idx, (system, slots) in enumerate(zip(self.systems, slots_per_system)):
             st = self._system_state(s_idx, system)
             states.append(st)
@@ -502,6 +538,19 @@ class ObjectiveFunction:
                 partial_list.append(None)
                 continue
             ens = st["ens"]
+            if use_graph:
+                # single-vector calls (the optimiser's f(x)): upload, prepare, E+F kernel, reduction and download replayed as
+                # ONE CUDA graph; the first calls run eagerly (they allocate and warm up what the capture then pins)
+                st["eager_calls"] = st.get("eager_calls", 0) + 1
+                if "graph" not in st and st["eager_calls"] > 2:
+                    st["graph"] = self._capture_graph(st, ens)
+                if "graph" in st:
+                    g = st["graph"]
+                    g["pin_in"].copy_(torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64)))
+                    g["graph"].replay()
+                    graph_rows[s_idx] = g["pin_out"]
+                    partial_list.append("graph")
+                    continue
             host = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64))
             pin = st.get("pin")
             if pin is None or tuple(pin.shape) != tuple(host.shape):
@@ -532,17 +581,23 @@ class ObjectiveFunction:
                 partial_list.append(torch.cat(rows, dim=0))
             else:
                 partial_list.append(ens.reduce(emm, fres, d_shift=st["d_shift"]))
-        live = [p for p in partial_list if p is not None]
+        live = [p for p in partial_list if p is not None and not isinstance(p, str)]
         values = np.zeros(n_vec)
-        if live:
-            stacked = live[0].unsqueeze(0) if len(live) == 1 else torch.stack(live, dim=0)  # [n_live, P, 8]
-            _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective
-            host_partials = stacked.cpu().numpy()
+        if live or graph_rows:
+            host_partials = None
+            if live:
+                stacked = live[0].unsqueeze(0) if len(live) == 1 else torch.stack(live, dim=0)  # [n_live, P, 8]
+                _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective
+                host_partials = stacked.cpu().numpy()
+            if graph_rows:
+                torch.cuda.current_stream().synchronize()
             k = 0
             per_system = []
-            for p in partial_list:
+            for i, p in enumerate(partial_list):
                 if p is None:
                     per_system.append(None)
+                elif isinstance(p, str):
+                    per_system.append(graph_rows[i].numpy().copy())
                 else:
                     per_system.append(host_partials[k] * 1.0)
                     k += 1
