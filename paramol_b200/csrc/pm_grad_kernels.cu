@@ -47,8 +47,11 @@ struct PmGradState {
     int n_gout;          // doubles in the gradient output: 2 nb + 2 na + 2 nt + 3 np
     int4 *d_atoms;       // [n_blocks * 32]
     int4 *d_meta;        // [n_blocks * 32] = (kind or -1 for padding, offset in the derived table, periodicity, offset in gout)
+    int n_items;         // work items = (block, slice of the tile's conformations); = n_blocks unless blocks are split
+    int4 *d_items;       // [n_items] = (block, slice index, number of slices of that block, 0), grouped by warp
+    int *d_warp_ptr;     // [warps + 1] into d_items
     int cpt;             // conformations per CTA tile
-    int threads;         // 32 x min(8, n_blocks): a small molecule has fewer blocks of terms than a full CTA has warps
+    int threads;         // 32 x warps
     size_t smem;
     int grid_max;
     int minb;
@@ -60,16 +63,20 @@ static void pm_grad_free(void *p) {
     if (!st) return;
     cudaFree(st->d_atoms);
     cudaFree(st->d_meta);
+    cudaFree(st->d_items);
+    cudaFree(st->d_warp_ptr);
     delete st;
 }
 
 struct PmGradArgs {
-    int n_atoms, cpw, cpt, n_blocks;
+    int n_atoms, cpw, cpt, n_blocks, n_items;
+    const int4 *items;
+    const int *warp_ptr;
     long n_conf, n_tiles;  // n_tiles = CTA tiles of cpt conformations
     const int4 *atoms, *meta;
     const double *derived, *x_tiles, *fmm_tiles, *fref_tiles, *metric, *coef_e, *coef_f;
     const double2 *acos_tab;
-    double *partial;  // [gridDim.x][n_blocks][4][32]
+    double *partial;  // [gridDim.x][n_items][4][32]
 };
 
 __device__ __forceinline__ void pmg_load(const double *__restrict__ s, pm_d3 &x, pm_d3 &l) {
@@ -85,9 +92,9 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
     const int N = g.n_atoms, CPT = g.cpt;
     double *tile = sm;                       // [CPT][N][6]
     double *ca = tile + (size_t)CPT * N * 6;  // [CPT] energy coefficients
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long tile_d = (long)3 * N * g.cpw;
-    double *my_partial = g.partial + (size_t)blockIdx.x * g.n_blocks * 128;
+    double *my_partial = g.partial + (size_t)blockIdx.x * g.n_items * 128;
 
     for (long t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
         const long c0 = t * CPT;
@@ -118,10 +125,13 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
         for (int c = tid; c < nc; c += blockDim.x) ca[c] = g.coef_e ? g.coef_e[c0 + c] : 0.0;
         __syncthreads();
 
-        for (int blk = warp; blk < g.n_blocks; blk += W) {
+        for (int item = g.warp_ptr[warp]; item < g.warp_ptr[warp + 1]; ++item) {
+            const int4 it4 = g.items[item];  // (block, slice, slices of the block): this warp does conformations [cb, ce) of the tile
+            const int blk = it4.x;
+            const int cb = (int)((long)nc * it4.y / it4.z), ce = (int)((long)nc * (it4.y + 1) / it4.z);
             const int4 at = g.atoms[blk * 32 + lane], me = g.meta[blk * 32 + lane];
             const int kind = __shfl_sync(0xffffffffu, me.x, 0);  // uniform per block (lane 0 is never padding)
-            double *pp = my_partial + (size_t)blk * 128 + lane;
+            double *pp = my_partial + (size_t)item * 128 + lane;
             double p0 = pp[0], p1 = pp[32], p2 = pp[64];  // requested now, needed after the loop
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
             if (me.x >= 0) {
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
                 if (kind == PMG_PAIR) {
                     const double *si = tile + at.x * 6, *sj = tile + at.y * 6;
 #pragma unroll 2
-                    for (int c = 0; c < nc; ++c) {
+                    for (int c = cb; c < ce; ++c) {
                         pm_d3 xi, li, xj, lj;
                         pmg_load(si + c * stride, xi, li);
                         pmg_load(sj + c * stride, xj, lj);
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
                 } else if (kind == PMG_BOND) {
                     const double r0 = dp[0], k = dp[1];
                     const double *si = tile + at.x * 6, *sj = tile + at.y * 6;
-                    for (int c = 0; c < nc; ++c) {
+                    for (int c = cb; c < ce; ++c) {
                         pm_d3 xi, li, xj, lj;
                         pmg_load(si + c * stride, xi, li);
                         pmg_load(sj + c * stride, xj, lj);
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
                 } else if (kind == PMG_ANGLE) {
                     const double t0 = dp[0], k = dp[1];
                     const double *sa = tile + at.x * 6, *sb = tile + at.y * 6, *sc = tile + at.z * 6;
-                    for (int c = 0; c < nc; ++c) {
+                    for (int c = cb; c < ce; ++c) {
                         pm_d3 xa, la, xb, lb, xc, lc;
                         pmg_load(sa + c * stride, xa, la);
                         pmg_load(sb + c * stride, xb, lb);
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
                     const int per = me.z;
                     const double n = (double)per;
                     const double *s0 = tile + at.x * 6, *s1 = tile + at.y * 6, *s2 = tile + at.z * 6, *s3 = tile + at.w * 6;
-                    for (int c = 0; c < nc; ++c) {
+                    for (int c = cb; c < ce; ++c) {
                         pm_d3 x0, l0, x1, l1, x2, l2, x3, l3;
                         pmg_load(s0 + c * stride, x0, l0);
                         pmg_load(s1 + c * stride, x1, l1);
@@ -228,9 +238,9 @@ __global__ void __launch_bounds__(PMG_THREADS, MINB) pm_grad_kernel(const PmGrad
     }
 }
 
-// gout[meta.w + q] = sum over CTAs (fixed order) of the lane's partial sums
-__global__ void pm_grad_reduce_kernel(const double *__restrict__ partial, int n_cta, int n_blocks, const int4 *__restrict__ meta,
-                                      double *__restrict__ gout) {
+// gout[meta.w + q] = sum over CTAs and over the slices of the term's block (fixed order) of the lane's partial sums
+__global__ void pm_grad_reduce_kernel(const double *__restrict__ partial, int n_cta, int n_blocks, int n_items,
+                                      const int4 *__restrict__ items, const int4 *__restrict__ meta, double *__restrict__ gout) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_blocks * 32) return;
     const int4 me = meta[e];
@@ -239,7 +249,10 @@ __global__ void pm_grad_reduce_kernel(const double *__restrict__ partial, int n_
     const int nq = me.x == PMG_PAIR ? 3 : 2;
     for (int q = 0; q < nq; ++q) {
         double s = 0.0;
-        for (int c = 0; c < n_cta; ++c) s += partial[((size_t)c * n_blocks + blk) * 128 + q * 32 + lane];
+        for (int item = 0; item < n_items; ++item) {
+            if (items[item].x != blk) continue;
+            for (int c = 0; c < n_cta; ++c) s += partial[((size_t)c * n_items + item) * 128 + q * 32 + lane];
+        }
         gout[me.w + q] = s;
     }
 }
@@ -288,8 +301,52 @@ static PmGradState *pm_grad_state(pm_handle h) {
     st->n_gout = go_pair + 3 * g.n_pairs;
     st->d_atoms = nullptr;
     st->d_meta = nullptr;
-    const int warps = std::min(PMG_THREADS / 32, std::max(st->n_blocks, 2));
+    // Work items.  A block costs (terms' relative cost) x (conformations of the tile); small molecules have only a handful of
+    // blocks of very different cost (aniline: 2 torsion, 1 angle, 1 bond, 2 pair blocks), so blocks are cut into slices of the
+    // tile's conformations until no item exceeds the per-warp share, and the items are dealt to the warps longest first.
+    const int warps = std::min(PMG_THREADS / 32, std::max(st->n_blocks, 4));
     st->threads = 32 * warps;
+    {
+        static const double kind_cost[4] = {1.0, 2.0, 3.4, 1.15};  // bond, angle, torsion, pair (instructions per term, relative)
+        std::vector<double> bcost(st->n_blocks);
+        double total = 0.0;
+        for (int b = 0; b < st->n_blocks; ++b) {
+            bcost[b] = kind_cost[meta[(size_t)b * 32].x];
+            total += bcost[b];
+        }
+        const double share = total / warps;
+        struct Item { int blk, slice, n_slices; double cost; };
+        std::vector<Item> items;
+        for (int b = 0; b < st->n_blocks; ++b) {
+            int ns = st->n_blocks >= 4 * warps ? 1 : (int)ceil(bcost[b] / share - 1e-9);
+            ns = std::max(1, std::min(ns, 8));
+            for (int j = 0; j < ns; ++j) items.push_back({b, j, ns, bcost[b] / ns});
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
+        std::vector<std::vector<Item>> per_warp(warps);
+        std::vector<double> load(warps, 0.0);
+        for (const Item &it : items) {
+            int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            per_warp[w].push_back(it);
+            load[w] += it.cost;
+        }
+        std::vector<int4> flat;
+        std::vector<int> wptr(1, 0);
+        for (int w = 0; w < warps; ++w) {
+            for (const Item &it : per_warp[w]) flat.push_back(make_int4(it.blk, it.slice, it.n_slices, 0));
+            wptr.push_back((int)flat.size());
+        }
+        st->n_items = (int)flat.size();
+        st->d_items = nullptr;
+        st->d_warp_ptr = nullptr;
+        if (cudaMalloc(&st->d_items, sizeof(int4) * std::max<size_t>(flat.size(), 1)) != cudaSuccess ||
+            cudaMalloc(&st->d_warp_ptr, sizeof(int) * wptr.size()) != cudaSuccess) {
+            pm_grad_free(st);
+            return nullptr;
+        }
+        cudaMemcpy(st->d_items, flat.data(), sizeof(int4) * flat.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(st->d_warp_ptr, wptr.data(), sizeof(int) * wptr.size(), cudaMemcpyHostToDevice);
+    }
     const int ctas_per_sm = std::max(2, std::min(6, (16 + warps - 1) / warps));  // aim at >= 16 resident warps per SM
     const size_t smem_cap = std::min<size_t>((size_t)200 * 1024 / ctas_per_sm, PMG_MAX_SMEM);
     st->cpt = 128;  // long tiles amortise the per-tile staging, barrier and partial-sum update of small molecules
@@ -330,7 +387,7 @@ extern "C" long pm_grad_scratch_doubles(pm_handle h) {
     cudaSetDevice(h->device);
     PmGradState *st = pm_grad_state(h);
     if (!st) return -1;
-    return (long)st->grid_max * st->n_blocks * 128;
+    return (long)st->grid_max * st->n_items * 128;
 }
 
 extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coord_tiles_dev, const double *fmm_tiles_dev,
@@ -350,6 +407,9 @@ extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coo
     a.cpw = h->prog.cpw;
     a.cpt = st->cpt;
     a.n_blocks = st->n_blocks;
+    a.n_items = st->n_items;
+    a.items = st->d_items;
+    a.warp_ptr = st->d_warp_ptr;
     a.n_conf = n_conf;
     a.n_tiles = (n_conf + st->cpt - 1) / st->cpt;
     a.atoms = st->d_atoms;
@@ -364,11 +424,12 @@ extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coo
     a.coef_f = coef_f_dev;
     a.partial = scratch_dev;
     const int grid = (int)std::min<long>(st->grid_max, a.n_tiles);
-    PMG_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * (size_t)grid * st->n_blocks * 128, s));
+    PMG_CUDA(cudaMemsetAsync(scratch_dev, 0, sizeof(double) * (size_t)grid * st->n_items * 128, s));
     if (st->n_blocks > 0) {
         st->fn<<<grid, st->threads, st->smem, s>>>(a);
         PMG_CUDA(cudaGetLastError());
-        pm_grad_reduce_kernel<<<(st->n_blocks * 32 + 255) / 256, 256, 0, s>>>(scratch_dev, grid, st->n_blocks, st->d_meta, gout_dev);
+        pm_grad_reduce_kernel<<<(st->n_blocks * 32 + 255) / 256, 256, 0, s>>>(scratch_dev, grid, st->n_blocks, st->n_items, st->d_items, st->d_meta,
+                                                                              gout_dev);
         PMG_CUDA(cudaGetLastError());
     }
     return 0;
