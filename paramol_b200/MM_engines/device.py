@@ -154,7 +154,8 @@ class DeviceTopology:
             logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
             return
         buf = ctypes.create_string_buffer(image, len(image))
-        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps), "pm_set_specialized")
+        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, specialize.choose_warps_energy(self.n_atoms) or 0),
+                   "pm_set_specialized")
         self.specialized = True
 
     def __del__(self):

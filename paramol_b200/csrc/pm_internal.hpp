@@ -63,6 +63,7 @@ int pm_fail_msg(const std::string &msg);  // sets pm_last_error(), returns 1 (pm
 
 // pm_spec.cu
 int pm_spec_metric_changed(pm_handle h);
-int pm_spec_launch_info(pm_handle h, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel is installed
+int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel serves that mode
+int pm_spec_can_eval(pm_handle h, int with_forces);
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
-                 double *fres, double *fmm_t, cudaStream_t stream);
+                 double *fres, double *fmm_t, int with_forces, cudaStream_t stream);

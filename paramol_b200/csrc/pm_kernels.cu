@@ -1046,7 +1046,7 @@ extern "C" int pm_launch_info(pm_handle h, int with_forces, int *grid, int *bloc
     if (block) *block = h->warps[wf] * 32;
     if (smem_bytes) *smem_bytes = (int)h->smem_total[wf];
     if (warps_per_cta) *warps_per_cta = h->warps[wf];
-    if (wf) pm_spec_launch_info(h, block, smem_bytes, warps_per_cta);  // full E+F evaluations run the specialised kernel if present
+    pm_spec_launch_info(h, wf, block, smem_bytes, warps_per_cta);  // full evaluations run the specialised kernels if present
     return 0;
 }
 extern "C" int pm_program_info(pm_handle h, int *out10) {
@@ -1109,9 +1109,9 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
     if (mode < 0 || mode > 2) return pm_fail("pm_eval_ex: mode must be 0 (all terms), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
     if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval_ex: mode 2 needs the cached nonbonded arrays");
     PM_CUDA(cudaSetDevice(h->device));
-    if (h->spec_state && mode == 0 && with_forces)  // full E+F evaluation of a small molecule: the topology-specialised kernel
+    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0))  // full evaluation of a small molecule: the topology-specialised kernels
         return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
-                            (cudaStream_t)stream);
+                            with_forces ? 1 : 0, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
     const int warps = h->warps[wf];

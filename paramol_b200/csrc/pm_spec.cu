@@ -22,10 +22,11 @@
 
 struct PmSpecState {
     cudaLibrary_t lib;
-    cudaKernel_t kernel;
+    cudaKernel_t kernel;    // pm_ef_spec_kernel: energies, forces, residual
+    cudaKernel_t kernel_e;  // pm_e_spec_kernel: energies only (null when the image has none)
     double *tab_dev;  // __constant__ spec_tab[n_derived + 9 N]: derived table of the vector being evaluated, then the metric
-    int warps;
-    size_t smem;
+    int warps, warps_e;
+    size_t smem, smem_e;
 };
 
 static void pm_spec_free(void *p) {
@@ -37,7 +38,7 @@ static void pm_spec_free(void *p) {
 
 extern "C" int pm_has_specialized(pm_handle h) { return h && h->spec_state ? 1 : 0; }
 
-extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps) {
+extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int warps_energy) {
     if (!h) return pm_fail_msg("pm_set_specialized: null handle");
     PMS_CUDA(cudaSetDevice(h->device));
     if (h->spec_state) {
@@ -71,17 +72,30 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
         pm_spec_free(st);
         return pm_fail_msg("pm_set_specialized: shared-memory request rejected");
     }
+    st->kernel_e = nullptr;
+    st->warps_e = 0;
+    st->smem_e = 0;
+    if (warps_energy > 0 && warps_energy <= 32 && cudaLibraryGetKernel(&st->kernel_e, st->lib, "pm_e_spec_kernel") == cudaSuccess) {
+        st->warps_e = warps_energy;
+        st->smem_e = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps_energy * (128 + tile);
+        if (st->smem_e > (size_t)h->max_smem ||
+            cudaFuncSetAttribute((const void *)st->kernel_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_e) != cudaSuccess)
+            st->kernel_e = nullptr;
+    } else {
+        st->kernel_e = nullptr;
+    }
+    cudaGetLastError();
     h->spec_state = st;
     h->spec_free = pm_spec_free;
     return pm_spec_metric_changed(h);
 }
 
-int pm_spec_launch_info(pm_handle h, int *block, int *smem_bytes, int *warps) {
+int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_bytes, int *warps) {
     PmSpecState *st = (PmSpecState *)h->spec_state;
-    if (!st) return 0;
-    if (block) *block = st->warps * 32;
-    if (smem_bytes) *smem_bytes = (int)st->smem;
-    if (warps) *warps = st->warps;
+    if (!st || (!with_forces && !st->kernel_e)) return 0;
+    if (block) *block = (with_forces ? st->warps : st->warps_e) * 32;
+    if (smem_bytes) *smem_bytes = (int)(with_forces ? st->smem : st->smem_e);
+    if (warps) *warps = with_forces ? st->warps : st->warps_e;
     return 1;
 }
 
@@ -93,14 +107,22 @@ int pm_spec_metric_changed(pm_handle h) {
     return 0;
 }
 
-int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf,
-                 double *emm, double *fres, double *fmm_t, cudaStream_t stream) {
+int pm_spec_can_eval(pm_handle h, int with_forces) {
     PmSpecState *st = (PmSpecState *)h->spec_state;
+    return st && (with_forces || st->kernel_e) ? 1 : 0;
+}
+
+int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf,
+                 double *emm, double *fres, double *fmm_t, int with_forces, cudaStream_t stream) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    const cudaKernel_t kernel = with_forces ? st->kernel : st->kernel_e;
+    const int warps = with_forces ? st->warps : st->warps_e;
+    const size_t smem = with_forces ? st->smem : st->smem_e;
     const size_t nd = (size_t)h->prog.doff_pair + 3 * (size_t)h->prog.n_pairs;
     long n_tiles = (n_conf + 31) / 32;
     const long tile_d = (long)3 * h->prog.n_atoms * 32;
     long grid = h->n_sm;
-    if (grid * st->warps > n_tiles) grid = (n_tiles + st->warps - 1) / st->warps;
+    if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
     if (grid < 1) grid = 1;
     const double2 *acos_tab = h->d_acos;
     for (int p = 0; p < n_vec; ++p) {
@@ -109,7 +131,7 @@ int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double
         double *e_p = emm + (size_t)p * n_conf, *r_p = fres ? fres + (size_t)p * n_conf : nullptr;
         double *f_p = fmm_t ? fmm_t + (size_t)p * n_tiles * tile_d : nullptr;
         void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p};
-        PMS_CUDA(cudaLaunchKernel((const void *)st->kernel, dim3((unsigned)grid), dim3(st->warps * 32), args, st->smem, stream));
+        PMS_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
     }
     return 0;
 }

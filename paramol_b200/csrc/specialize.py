@@ -21,7 +21,7 @@ def _d3(name):
 
 class KernelSource:
     def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers=True, name="pm_ef_spec_kernel",
-                 x_in_registers=False, fence_every=0, sync_every=0):
+                 x_in_registers=False, fence_every=0, sync_every=0, with_forces=True):
         """
         bonds [nb,2], angles [na,3], torsions [nt,4], tors_per [nt], pairs [np,3] = (i, j, exception or -1) in the
         order of the derived table (pm_get_pairs).  Derived layout: bonds (r0,k) | angles (t0,k) | torsions
@@ -37,6 +37,7 @@ class KernelSource:
         self.x_reg = bool(x_in_registers)
         self.fence_every = int(fence_every)
         self.sync_every = int(sync_every)
+        self.wf = bool(with_forces)
         self._blocks = 0
         self.name = name
         self.off_bond = 0
@@ -62,8 +63,8 @@ class KernelSource:
         return ("X%d" % atom) if self.x_reg else ("PMX(%d)" % atom)
 
     def end_block(self):
-        """Close a star / axis / pair block; every ``fence_every`` blocks a compiler-level memory fence keeps ptxas from
-        hoisting the loads of all later blocks to the top (which costs more registers than the interleaving gains)."""
+        """Close a star / axis / pair block; every ``fence_every`` blocks a warp-level fence keeps ptxas from hoisting the
+        loads of all later blocks to the top (which costs more registers than the interleaving gains)."""
         self.emit("}")
         self._blocks += 1
         if self.sync_every and self._blocks % self.sync_every == 0:
@@ -71,9 +72,13 @@ class KernelSource:
             # fetched line serves all of them; the trip count of the tile loop is uniform per CTA for that reason
             self.emit("__syncthreads();")
         elif self.fence_every and self._blocks % self.fence_every == 0:
-            self.emit('asm volatile("" ::: "memory");')
+            # a fence ptxas honours (an empty asm with a memory clobber only constrains NVVM; without stores between them, as in
+            # the energy-only kernel, ptxas still hoists every coordinate load to the top and spills)
+            self.emit("__syncwarp();")
 
     def addf(self, atom, expr_vec, sign="+"):
+        if not self.wf:
+            return
         if self.f_reg:
             self.emit("F%d.x %s= %s.x; F%d.y %s= %s.y; F%d.z %s= %s.z;" % (atom, sign, expr_vec, atom, sign, expr_vec, atom, sign, expr_vec))
         else:
@@ -112,26 +117,31 @@ class KernelSource:
             need = [n for n in need if n in used]
             self.emit("{  // star %d" % c)
             self.emit("const pm_d3 xc = %s;" % self.X(c))
-            self.emit("pm_d3 fc = pm_d3{0.0, 0.0, 0.0};")
+            if self.wf:
+                self.emit("pm_d3 fc = pm_d3{0.0, 0.0, 0.0};")
             for n in need:
                 self.emit("const pm_d3 d%d = pm_sub(xc, %s); const double q%d = pm_dot(d%d, d%d); const double i%d = pm_rsqrt(q%d);"
                           % (n, self.X(n), n, n, n, n, n))
-                self.emit("pm_d3 f%d = pm_d3{0.0, 0.0, 0.0};" % n)
+                if self.wf:
+                    self.emit("pm_d3 f%d = pm_d3{0.0, 0.0, 0.0};" % n)
             for n in own:
                 t = bond_of[(c, n)]
                 done_bond.add(t)
                 o = self.off_bond + 2 * t
-                self.emit("{ const double dl = fma(q%d, i%d, -%s); const double kd = %s * dl; e_bond = fma(0.5 * kd, dl, e_bond);"
-                          " const double g = kd * i%d; pm_axpy(f%d, g, d%d); pm_axpy(fc, -g, d%d); }" % (n, n, self.P(o), self.P(o + 1), n, n, n, n))
+                self.emit("{ const double dl = fma(q%d, i%d, -%s); const double kd = %s * dl; e_bond = fma(0.5 * kd, dl, e_bond);" % (n, n, self.P(o), self.P(o + 1))
+                          + (" const double g = kd * i%d; pm_axpy(f%d, g, d%d); pm_axpy(fc, -g, d%d); }" % (n, n, n, n) if self.wf else " }"))
             for (t, a, b) in angle_at[c]:
                 o = self.off_angle + 2 * t
                 # d0 = x_centre - x_a, d1 = x_centre - x_b  (ReferenceAngleBondIxn; see pm_delta_kernels.cu for the same algebra)
                 self.emit("{ const pm_d3 pc = pm_cross(d%d, d%d); const double pp2 = pm_dot(pc, pc); const double i01 = i%d * i%d;" % (a, b, a, b))
                 self.emit("  const double ip = pm_rsqrt(fmax(pp2, 1.0e-12)); const double th = pm_acos_cs(pm_dot(d%d, d%d) * i01, pp2 * ip * i01, s_acos);" % (a, b))
                 self.emit("  const double dl = th - %s; const double dd = %s * dl; e_angle = fma(0.5 * dd, dl, e_angle);" % (self.P(o), self.P(o + 1)))
-                self.emit("  const double ta = dd * ip * (i%d * i%d), tc = -dd * ip * (i%d * i%d);" % (a, a, b, b))
-                self.emit("  const pm_d3 c0 = pm_cross(d%d, pc), c2 = pm_cross(d%d, pc);" % (a, b))
-                self.emit("  pm_axpy(f%d, ta, c0); pm_axpy(f%d, tc, c2); pm_axpy(fc, -ta, c0); pm_axpy(fc, -tc, c2); }" % (a, b))
+                if self.wf:
+                    self.emit("  const double ta = dd * ip * (i%d * i%d), tc = -dd * ip * (i%d * i%d);" % (a, a, b, b))
+                    self.emit("  const pm_d3 c0 = pm_cross(d%d, pc), c2 = pm_cross(d%d, pc);" % (a, b))
+                    self.emit("  pm_axpy(f%d, ta, c0); pm_axpy(f%d, tc, c2); pm_axpy(fc, -ta, c0); pm_axpy(fc, -tc, c2); }" % (a, b))
+                else:
+                    self.emit("}")
             self.addf(c, "fc")
             for n in need:
                 self.addf(n, "f%d" % n)
@@ -152,15 +162,16 @@ class KernelSource:
             self.emit("{  // axis %d-%d" % (j, k))
             self.emit("const pm_d3 xj = %s, xk = %s; const pm_d3 d1 = pm_sub(xk, xj); const double bb = pm_dot(d1, d1);" % (self.X(j), self.X(k)))
             self.emit("const double rbb = pm_rsqrt(bb); const double nb = bb * rbb, ibb = rbb * rbb;")
-            self.emit("pm_d3 fj = pm_d3{0.0, 0.0, 0.0}, fk = pm_d3{0.0, 0.0, 0.0};")
+            if self.wf:
+                self.emit("pm_d3 fj = pm_d3{0.0, 0.0, 0.0}, fk = pm_d3{0.0, 0.0, 0.0};")
             for i in subs_i:
                 self.emit("const pm_d3 a%d = pm_sub(%s, xj); const pm_d3 u%d = pm_cross(a%d, d1); const double m%d = pm_dot(u%d, u%d);"
-                          " const double s%d = pm_rsqrt(m%d); const double g%d = pm_dot(a%d, d1) * ibb; pm_d3 fi%d = pm_d3{0.0, 0.0, 0.0};"
-                          % (i, self.X(i), i, i, i, i, i, i, i, i, i, i))
+                          " const double s%d = pm_rsqrt(m%d);" % (i, self.X(i), i, i, i, i, i, i, i)
+                          + (" const double g%d = pm_dot(a%d, d1) * ibb; pm_d3 fi%d = pm_d3{0.0, 0.0, 0.0};" % (i, i, i) if self.wf else ""))
             for l in subs_l:
                 self.emit("const pm_d3 b%d = pm_sub(xk, %s); const pm_d3 w%d = pm_cross(d1, b%d); const double n%d = pm_dot(w%d, w%d);"
-                          " const double t%d = pm_rsqrt(n%d); const double h%d = pm_dot(b%d, d1) * ibb; pm_d3 fl%d = pm_d3{0.0, 0.0, 0.0};"
-                          % (l, self.X(l), l, l, l, l, l, l, l, l, l, l))
+                          " const double t%d = pm_rsqrt(n%d);" % (l, self.X(l), l, l, l, l, l, l, l)
+                          + (" const double h%d = pm_dot(b%d, d1) * ibb; pm_d3 fl%d = pm_d3{0.0, 0.0, 0.0};" % (l, l, l) if self.wf else ""))
             cells = {}
             for (t, i, l) in terms:
                 cells.setdefault((i, l), []).append(t)
@@ -175,13 +186,16 @@ class KernelSource:
                         self.emit("  { const double tt = cn * cphi - sn * sphi; sn = fma(sn, cphi, cn * sphi); cn = tt; }")
                         cur += 1
                     o = self.off_tors + 4 * t
-                    self.emit("  e_tors += %s * (1.0 + fma(cn, %s, sn * %s)); dd -= %s * fma(sn, %s, -(cn * %s));"
-                              % (self.P(o), self.P(o + 2), self.P(o + 3), self.P(o + 1), self.P(o + 2), self.P(o + 3)))
+                    self.emit("  e_tors += %s * (1.0 + fma(cn, %s, sn * %s));" % (self.P(o), self.P(o + 2), self.P(o + 3))
+                              + (" dd -= %s * fma(sn, %s, -(cn * %s));" % (self.P(o + 1), self.P(o + 2), self.P(o + 3)) if self.wf else ""))
                 # F_0 = -dd |d1| c1 / n1, F_3 = dd |d1| c2 / n2, F_1 = (ff1-1) F_0 - ff2 F_3, F_2 = (ff2-1) F_3 - ff1 F_0
-                self.emit("  const double z0 = -dd * nb * (s%d * s%d), z3 = dd * nb * (t%d * t%d);" % (i, i, l, l))
-                self.emit("  const pm_d3 f0 = pm_d3{z0 * u%d.x, z0 * u%d.y, z0 * u%d.z}, f3 = pm_d3{z3 * w%d.x, z3 * w%d.y, z3 * w%d.z};" % (i, i, i, l, l, l))
-                self.emit("  pm_axpy(fi%d, 1.0, f0); pm_axpy(fl%d, 1.0, f3);" % (i, l))
-                self.emit("  pm_axpy(fj, g%d - 1.0, f0); pm_axpy(fj, -h%d, f3); pm_axpy(fk, h%d - 1.0, f3); pm_axpy(fk, -g%d, f0); }" % (i, l, l, i))
+                if self.wf:
+                    self.emit("  const double z0 = -dd * nb * (s%d * s%d), z3 = dd * nb * (t%d * t%d);" % (i, i, l, l))
+                    self.emit("  const pm_d3 f0 = pm_d3{z0 * u%d.x, z0 * u%d.y, z0 * u%d.z}, f3 = pm_d3{z3 * w%d.x, z3 * w%d.y, z3 * w%d.z};" % (i, i, i, l, l, l))
+                    self.emit("  pm_axpy(fi%d, 1.0, f0); pm_axpy(fl%d, 1.0, f3);" % (i, l))
+                    self.emit("  pm_axpy(fj, g%d - 1.0, f0); pm_axpy(fj, -h%d, f3); pm_axpy(fk, h%d - 1.0, f3); pm_axpy(fk, -g%d, f0); }" % (i, l, l, i))
+                else:
+                    self.emit("  (void)dd; }")
             self.addf(j, "fj")
             self.addf(k, "fk")
             for i in subs_i:
@@ -197,19 +211,20 @@ class KernelSource:
             by_i.setdefault(i, []).append((q, j))
         for i, lst in by_i.items():
             self.emit("{  // pairs of atom %d" % i)
-            self.emit("const pm_d3 xi = %s; pm_d3 fi = pm_d3{0.0, 0.0, 0.0};" % self.X(i))
+            self.emit("const pm_d3 xi = %s;" % self.X(i) + (" pm_d3 fi = pm_d3{0.0, 0.0, 0.0};" if self.wf else ""))
             for (q, j) in lst:
                 o = self.off_pair + 3 * q
                 self.emit("{ const pm_d3 d = pm_sub(xi, %s); const double rinv = pm_rsqrt(pm_dot(d, d)); const double u = rinv * rinv; const double u3 = u * u * u;" % self.X(j))
                 self.emit("  const double a = %s * u3; const double b = a - %s; const double cq = %s * rinv; e_nb = fma(b, u3, e_nb); e_nb += cq;" % (self.P(o), self.P(o + 1), self.P(o + 2)))
-                self.emit("  const double g = fma(6.0 * u3, a + b, cq) * u; const pm_d3 fv = pm_d3{g * d.x, g * d.y, g * d.z}; pm_axpy(fi, g, d);")
+                if self.wf:
+                    self.emit("  const double g = fma(6.0 * u3, a + b, cq) * u; const pm_d3 fv = pm_d3{g * d.x, g * d.y, g * d.z}; pm_axpy(fi, g, d);")
                 self.addf(j, "fv", "-")
                 self.emit("}")
             self.addf(i, "fi")
             self.end_block()
 
     # ---- the kernel ----------------------------------------------------------------------------
-    def source(self, warps):
+    def source(self, warps, with_header=True):
         N = self.N
         self.lines = []
         self._blocks = 0
@@ -219,6 +234,8 @@ class KernelSource:
         body = "\n            ".join(self.lines)
         f_decl = "\n            ".join("pm_d3 F%d = pm_d3{0.0, 0.0, 0.0};" % a for a in range(N)) if self.f_reg else \
             "for (int k = lane; k < TILE_D; k += 32) fs[k] = 0.0; __syncwarp();"
+        if not self.wf:
+            f_decl = ""
         res_lines = []
         for a in range(N):
             if self.f_reg:
@@ -230,8 +247,10 @@ class KernelSource:
             res_lines.append("  const double t0 = fma(dz, %s, fma(dy, %s, dx * %s)), t1 = fma(dz, %s, fma(dy, %s, dx * %s)), t2 = fma(dz, %s, fma(dy, %s, dx * %s));"
                              % (m[6], m[3], m[0], m[7], m[4], m[1], m[8], m[5], m[2]))
             res_lines.append("  res += fma(t2, dz, fma(t1, dy, t0 * dx)); }")
-        res = "\n                ".join(res_lines)
-        if self.f_reg:
+        res = "\n                ".join(res_lines) if self.wf else ""
+        if not self.wf:
+            fout = ""
+        elif self.f_reg:
             fout = "\n                ".join("fo[%d * 32] = F%d.x; fo[%d * 32] = F%d.y; fo[%d * 32] = F%d.z;" % (3 * a, a, 3 * a + 1, a, 3 * a + 2, a) for a in range(N))
         else:
             fout = "for (int k = 0; k < %d; ++k) fo[k * 32] = fs[k * 32 + lane];" % (3 * N)
@@ -240,11 +259,12 @@ class KernelSource:
                 "const pm_d3 X%d = pm_d3{xg[%d * 32], xg[%d * 32], xg[%d * 32]};" % (a, 3 * a, 3 * a + 1, 3 * a + 2) for a in range(N))
         else:
             x_load = ""
-        return _TEMPLATE.format(name=self.name, N=N, ND=max(self.n_derived, 1), W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
-                                f_tile=0 if self.f_reg else 1, x_tile=0 if self.x_reg else 1, x_load=x_load)
+        kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
+                                f_tile=0 if (self.f_reg or not self.wf) else 1, x_tile=0 if self.x_reg else 1, x_load=x_load)
+        return kernel if not with_header else _HEADER.format(N=N, ND=max(self.n_derived, 1)) + kernel
 
 
-_TEMPLATE = r'''// generated by paramol_b200/csrc/specialize.py -- do not edit
+_HEADER = r'''// generated by paramol_b200/csrc/specialize.py -- do not edit
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pm_device.cuh"
@@ -259,7 +279,9 @@ _TEMPLATE = r'''// generated by paramol_b200/csrc/specialize.py -- do not edit
 // derived table of the parameter vector being evaluated (pm_prepare_params layout), then the 9 N force-metric entries; the
 // host copies them here before the launch, so every parameter is a constant-bank operand with an immediate offset
 __constant__ double spec_tab[SPEC_ND + 9 * SPEC_N];
+'''
 
+_KERNEL = r'''
 extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     {name}(const double2 *__restrict__ acos_tab, const double *__restrict__ xt,
            const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm, double *__restrict__ fres,
@@ -339,9 +361,9 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
 
 
 def generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=True, name="pm_ef_spec_kernel",
-             x_in_registers=False, fence_every=0, sync_every=0):
+             x_in_registers=False, fence_every=0, sync_every=0, with_forces=True):
     return KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers, name, x_in_registers,
-                        fence_every, sync_every).source(warps)
+                        fence_every, sync_every, with_forces).source(warps)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -352,6 +374,7 @@ FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fen
 SYNC_EVERY = 0
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
+MAX_WARPS_ENERGY = 16   # 128 registers, no spills
 
 
 def choose_warps(n_atoms):
@@ -407,9 +430,25 @@ def compile_image(source):
         return fh.read()
 
 
+def choose_warps_energy(n_atoms):
+    """Warps per CTA of the energy-only specialised kernel (coordinate tile only)."""
+    import math
+    tile = 3 * n_atoms * 32 * 8
+    table = ((257 * 16 + 127) // 128) * 128
+    warps = min(MAX_WARPS_ENERGY, int(math.floor((MAX_SMEM - table) / (128 + tile))))
+    return warps if warps >= MIN_WARPS else None
+
+
 def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs, warps):
+    """One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual; ``warps`` per CTA) and ``pm_e_spec_kernel`` (energies
+    only; ``choose_warps_energy`` per CTA) sharing ``spec_tab``."""
     import os
     fence = int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY))
     sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
-    return compile_image(generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=False,
-                                  x_in_registers=False, fence_every=fence, sync_every=sync))
+    src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=False, x_in_registers=False,
+                   fence_every=fence, sync_every=sync)
+    we = choose_warps_energy(n_atoms)
+    if we is not None:
+        src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, fence, 0,
+                            with_forces=False).source(we, with_header=False)
+    return compile_image(src)

@@ -30,3 +30,10 @@ b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 20
 print("%s S=%d specialized=%s fence=%s sync=%s : %.4f ms  %.1f Mconf/s  %s" % (name, S, topo.specialized, os.environ.get("PM_SPEC_FENCE", "-"),
       os.environ.get("PM_SPEC_SYNC", "-"), ms, S / ms / 1e3, topo.launch_info(True)))
+for _ in range(3): ens.evaluate(der, with_forces=False, want_fres=False)
+torch.cuda.synchronize()
+a.record()
+for _ in range(20): ens.evaluate(der, with_forces=False, want_fres=False)
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 20
+print("   energy only: %.4f ms  %.1f Mconf/s  %s" % (ms, S / ms / 1e3, topo.launch_info(False)))
