@@ -80,7 +80,7 @@ def prebuild_specialized(mm_system):
     _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), None), "pm_topology_pairs")
     pairs = np.zeros((max(n.value, 1), 3), dtype=np.int32)
     _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), _iptr(pairs)), "pm_topology_pairs")
-    image = specialize.image_for(int(mm_system.n_atoms), keep["bond"], keep["angle"], keep["tors"], keep["tper"], pairs[:n.value], warps)
+    image, _, _ = specialize.image_for(int(mm_system.n_atoms), keep["bond"], keep["angle"], keep["tors"], keep["tper"], pairs[:n.value], warps)
     return len(image)
 
 
@@ -148,13 +148,13 @@ class DeviceTopology:
             return
         k = self._keep
         try:
-            image = specialize.image_for(self.n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], self.pairs(), warps)
+            image, warps, tiles = specialize.image_for(self.n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], self.pairs(), warps)
         except RuntimeError as exc:
             import logging
             logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
             return
         buf = ctypes.create_string_buffer(image, len(image))
-        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, specialize.choose_warps_energy(self.n_atoms) or 0),
+        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, specialize.choose_warps_energy(self.n_atoms) or 0),
                    "pm_set_specialized")
         self.specialized = True
 

@@ -38,7 +38,7 @@ static void pm_spec_free(void *p) {
 
 extern "C" int pm_has_specialized(pm_handle h) { return h && h->spec_state ? 1 : 0; }
 
-extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int warps_energy) {
+extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int tiles_per_warp, int warps_energy) {
     if (!h) return pm_fail_msg("pm_set_specialized: null handle");
     PMS_CUDA(cudaSetDevice(h->device));
     if (h->spec_state) {
@@ -47,7 +47,7 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     }
     if (!image || n_bytes <= 0) return 0;  // NULL image: back to the generic kernel
     if (h->rf || h->prog.cpw != 32) return pm_fail_msg("pm_set_specialized: needs a NoCutoff topology with 32 conformations per tile");
-    if (warps < 1 || warps > 32) return pm_fail_msg("pm_set_specialized: bad warp count");
+    if (warps < 1 || warps > 32 || tiles_per_warp < 1 || tiles_per_warp > 2) return pm_fail_msg("pm_set_specialized: bad warp / tile count");
     PmSpecState *st = new PmSpecState();
     if (cudaLibraryLoadData(&st->lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
         delete st;
@@ -65,7 +65,7 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     st->tab_dev = (double *)tab;
     st->warps = warps;
     const size_t tile = (size_t)3 * h->prog.n_atoms * 32 * sizeof(double);
-    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps * (128 + 2 * tile);
+    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps * (128 + (size_t)tiles_per_warp * tile);
     if (st->smem > (size_t)h->max_smem ||
         cudaFuncSetAttribute((const void *)st->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess) {
         cudaGetLastError();

@@ -403,9 +403,10 @@ def cache_dir():
     return d
 
 
-def compile_image(source):
+def compile_image(source, want_report=False):
     """nvcc -cubin for sm_100a, cached in-tree by the hash of the source (the cache travels with the repository snapshot, so
-    a molecule compiled once -- e.g. by ``__graft_entry__.build()`` -- is not compiled again on the GPU box)."""
+    a molecule compiled once -- e.g. by ``__graft_entry__.build()`` -- is not compiled again on the GPU box).  With
+    ``want_report`` also returns the ptxas resource report (kept next to the image)."""
     import hashlib
     import os
     import subprocess
@@ -413,7 +414,7 @@ def compile_image(source):
     with open(os.path.join(here, "pm_device.cuh"), "rb") as fh:
         key = hashlib.sha256(source.encode() + fh.read()).hexdigest()[:24]
     path = os.path.join(cache_dir(), key + ".cubin")
-    if not os.path.exists(path):
+    if not os.path.exists(path) or not os.path.exists(path + ".txt"):
         nvcc = _nvcc()
         if nvcc is None:
             raise RuntimeError("nvcc not found: cannot compile the topology-specialised kernel")
@@ -421,13 +422,31 @@ def compile_image(source):
         with open(src, "w") as fh:
             fh.write(source)
         tmp = path + ".tmp%d" % os.getpid()
-        res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-I", here,
-                              src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+        res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v",
+                              "-I", here, src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed on the specialised kernel:\n" + res.stdout[-2000:])
+        with open(tmp + ".txt", "w") as fh:
+            fh.write(res.stdout)
+        os.replace(tmp + ".txt", path + ".txt")
         os.replace(tmp, path)
     with open(path, "rb") as fh:
-        return fh.read()
+        image = fh.read()
+    if want_report:
+        with open(path + ".txt") as fh:
+            return image, fh.read()
+    return image
+
+
+def _spills(report, kernel):
+    """Bytes of spill stores ptxas reports for ``kernel`` (0 when it fits its register budget)."""
+    lines = report.splitlines()
+    for i, line in enumerate(lines):
+        if "Compiling entry function '%s'" % kernel in line:
+            for nxt in lines[i + 1:i + 4]:
+                if "spill stores" in nxt:
+                    return int(nxt.split("bytes stack frame,")[1].split("bytes spill stores")[0])
+    return -1
 
 
 def choose_warps_energy(n_atoms):
@@ -439,16 +458,37 @@ def choose_warps_energy(n_atoms):
     return warps if warps >= MIN_WARPS else None
 
 
+F_REG_WARPS = 8       # forces in registers: 255 registers per thread
+F_REG_MAX_SPILL = 512  # bytes of spill stores tolerated (aniline at fence 6: 204 bytes, still the fastest)
+F_REG_FENCE = 6       # measured on B200 (aniline, 8 warps): 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms (spills)
+
+
 def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs, warps):
-    """One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual; ``warps`` per CTA) and ``pm_e_spec_kernel`` (energies
-    only; ``choose_warps_energy`` per CTA) sharing ``spec_tab``."""
+    """
+    One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual) and ``pm_e_spec_kernel`` (energies only;
+    ``choose_warps_energy`` warps per CTA) sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp).
+
+    Two shapes of the E+F kernel are tried: forces in REGISTERS (3 N doubles per lane, 8 warps, no force tile: 11 % fewer
+    instructions and no shared-memory read-modify-write chains; aniline 0.632 ms) is kept when ptxas reports (almost) no spills;
+    otherwise forces live in the shared force tile (``warps`` warps, 168 registers; aniline 0.704 ms).
+    """
     import os
-    fence = int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY))
     sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
-    src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=False, x_in_registers=False,
-                   fence_every=fence, sync_every=sync)
     we = choose_warps_energy(n_atoms)
-    if we is not None:
-        src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, fence, 0,
-                            with_forces=False).source(we, with_header=False)
-    return compile_image(src)
+
+    def build(f_reg, w, fence):
+        src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
+                       fence_every=fence, sync_every=sync)
+        if we is not None:
+            src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY, 0,
+                                with_forces=False).source(we, with_header=False)
+        return compile_image(src, want_report=True)
+
+    mode = os.environ.get("PM_SPEC_FREG", "auto")
+    if mode != "0":
+        image, report = build(True, int(os.environ.get("PM_SPEC_WARPS", F_REG_WARPS)), int(os.environ.get("PM_SPEC_FENCE", F_REG_FENCE)))
+        if 0 <= _spills(report, "pm_ef_spec_kernel") <= F_REG_MAX_SPILL or mode == "1":
+            return image, int(os.environ.get("PM_SPEC_WARPS", F_REG_WARPS)), 1
+    w = int(os.environ.get("PM_SPEC_WARPS", warps))
+    image, _ = build(False, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
+    return image, w, 2
