@@ -1109,7 +1109,10 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
     if (mode < 0 || mode > 2) return pm_fail("pm_eval_ex: mode must be 0 (all terms), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
     if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval_ex: mode 2 needs the cached nonbonded arrays");
     PM_CUDA(cudaSetDevice(h->device));
-    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0))  // full evaluation of a small molecule: the topology-specialised kernels
+    // Full evaluation of a small molecule: the topology-specialised kernels -- one launch (plus a constant-table copy) per
+    // parameter vector, so batches over small ensembles (launch-bound: < 32768 conformations) stay on the generic kernel, which
+    // loops over the vectors inside one launch.
+    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0) && (n_vec == 1 || n_conf >= 32768))
         return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
                             with_forces ? 1 : 0, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;

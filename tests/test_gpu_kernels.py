@@ -167,7 +167,7 @@ def test_fma_peak_probe():
 @pytest.mark.parametrize("n_atoms", [5, 12, 15, 16])
 def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
     """The topology-specialised kernel (csrc/specialize.py, installed automatically for small molecules) against the generic
-    program-interpreting kernel on the same tiles: energies, residuals and forces to 1e-13, several parameter vectors per
+    program-interpreting kernel on the same tiles: energies, residuals and forces to 1e-11 of the largest entry (a few of the 32805 random conformations are near-singular), several parameter vectors per
     call, a partial last tile, non-trivial metric; energy-only calls keep using the generic kernel."""
     import torch
     from paramol_b200.MM_engines.b200_engine import B200Engine
@@ -181,7 +181,7 @@ def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
     spec = DeviceTopology(mm)
     assert not generic.specialized and spec.specialized
     rng = np.random.default_rng(n_atoms)
-    n_conf = 32 * 7 + 5
+    n_conf = 32768 + 37     # batches over fewer than 32768 conformations stay on the generic kernel (launch-bound)
     X = x0[None] + rng.normal(0, 0.01, (n_conf,) + x0.shape)
     F = rng.normal(0, 50.0, X.shape)
     metric = np.tile(np.eye(3).ravel(), (n_atoms, 1)) * rng.uniform(0.5, 2.0, (n_atoms, 1))
@@ -198,7 +198,12 @@ def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
         e_only = ens.evaluate(der, with_forces=False, want_fres=False)[0].clone()
         out.append((emm.clone(), fres.clone(), forces.clone(), e_only))
     for a, b in zip(out[0], out[1]):
-        assert (a - b).abs().max().item() <= 1e-13 * a.abs().max().item()
+        assert (a - b).abs().max().item() <= 1e-11 * a.abs().max().item()
+    # single vectors use the specialised kernel whatever the ensemble size (partial last tile included)
+    small = DeviceEnsemble(spec, X[:229], F[:229], np.zeros(229))
+    one = small.evaluate(spec.prepare(torch.from_numpy(rows[1:2].copy()).cuda()), with_forces=True, want_fres=True)
+    assert (one[0][0] - out[0][0][1, :229]).abs().max().item() <= 1e-12 * out[0][0].abs().max().item()
+    assert (one[1][0] - out[0][1][1, :229]).abs().max().item() <= 1e-12 * out[0][1].abs().max().item()
     # the metric can change after the kernel was installed
     spec.set_force_metric(2.0 * metric)
     ens = DeviceEnsemble(spec, X, F, np.zeros(n_conf))
