@@ -15,10 +15,6 @@ Same scope as the generic kernel for: one lane per conformation (CPW = 32), NoCu
 import numpy as np
 
 
-def _d3(name):
-    return "%s.x, %s.y, %s.z" % (name, name, name)
-
-
 class KernelSource:
     def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers=True, name="pm_ef_spec_kernel",
                  x_in_registers=False, fence_every=0, sync_every=0, with_forces=True):
@@ -46,15 +42,10 @@ class KernelSource:
         self.off_pair = self.off_tors + 4 * len(self.torsions)
         self.n_derived = self.off_pair + 3 * len(self.pairs)
         self.lines = []
-        self._uid = 0
 
     # ---- emission helpers -----------------------------------------------------------------------
     def emit(self, text):
         self.lines.append(text)
-
-    def uid(self):
-        self._uid += 1
-        return self._uid
 
     def P(self, off):
         return "spec_tab[%d]" % off
@@ -87,7 +78,6 @@ class KernelSource:
     # ---- stars: bonds + angles around a centre ---------------------------------------------------
     def gen_stars(self):
         N = self.N
-        nbrs = [[] for _ in range(N)]
         bond_of = {}
         for t, (i, j) in enumerate(self.bonds):
             bond_of[(i, j)] = t

@@ -102,3 +102,32 @@ def test_compute_calls_fail_loudly_without_gpu():
     h = ctypes.c_void_p()
     assert L.pm_create(ctypes.byref(topo), 0, ctypes.byref(h)) != 0
     assert b"no CUDA device" in L.pm_last_error()
+
+
+def test_specialized_kernel_source_builds_without_gpu(tmp_path, monkeypatch):
+    """Host-only half of the topology-specialised kernel: pm_topology_pairs (no CUDA call), the generator and the nvcc cross
+    compile.  The image must hold both kernels and the constant table, and ptxas must not spill beyond the accepted budget."""
+    from paramol_b200.MM_engines.device import prebuild_specialized, _pm_topology
+    from paramol_b200.csrc import specialize
+    from paramol_b200.Utils.synthetic import make_ligand
+    import ctypes
+    monkeypatch.setenv("PARAMOL_B200_SPEC_CACHE", str(tmp_path))
+    mm, _ = make_ligand(9)
+    L = _lib.lib()
+    topo, keep = _pm_topology(mm)
+    n = ctypes.c_int()
+    assert L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), None) == 0
+    exc = {tuple(sorted(map(int, e))) for e, a in zip(keep["exc"], keep["act"]) if not a}
+    assert n.value == 9 * 8 // 2 - len(exc)             # every pair except the pure exclusions
+    size = prebuild_specialized(mm)
+    assert size > 0
+    cubins = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(cubins) == 1
+    blob = open(os.path.join(tmp_path, cubins[0]), "rb").read()
+    assert b"pm_ef_spec_kernel" in blob and b"pm_e_spec_kernel" in blob and b"spec_tab" in blob
+    report = open(os.path.join(tmp_path, cubins[0] + ".txt")).read()
+    assert 0 <= specialize._spills(report, "pm_ef_spec_kernel") <= specialize.F_REG_MAX_SPILL
+    assert specialize._spills(report, "pm_e_spec_kernel") == 0
+    # molecules whose tiles leave too few warps are left to the generic kernel
+    big, _ = make_ligand(30)
+    assert prebuild_specialized(big) == 0
