@@ -29,7 +29,9 @@ class KernelSource:
         self.torsions = [tuple(int(v) for v in t) for t in np.asarray(torsions).reshape(-1, 4)]
         self.tors_per = [int(v) for v in np.asarray(tors_per).reshape(-1)]
         self.pairs = [tuple(int(v) for v in p) for p in np.asarray(pairs).reshape(-1, 3)]
-        self.f_reg = bool(f_in_registers)
+        # forces in registers: True (all atoms), False (none: shared force tile) or an iterable of atom indices (the rest go to the tile)
+        self.f_reg_atoms = set(range(int(n_atoms))) if f_in_registers is True else set(int(a) for a in (f_in_registers or ()))
+        self.f_reg = len(self.f_reg_atoms) == int(n_atoms)
         self.x_reg = bool(x_in_registers)
         self.fence_every = int(fence_every)
         self.sync_every = int(sync_every)
@@ -70,7 +72,7 @@ class KernelSource:
     def addf(self, atom, expr_vec, sign="+"):
         if not self.wf:
             return
-        if self.f_reg:
+        if atom in self.f_reg_atoms:
             self.emit("F%d.x %s= %s.x; F%d.y %s= %s.y; F%d.z %s= %s.z;" % (atom, sign, expr_vec, atom, sign, expr_vec, atom, sign, expr_vec))
         else:
             self.emit("PMF_%s(%d, %s);" % ("ADD" if sign == "+" else "SUB", atom, expr_vec))
@@ -222,13 +224,14 @@ class KernelSource:
         self.gen_axes()
         self.gen_pairs()
         body = "\n            ".join(self.lines)
-        f_decl = "\n            ".join("pm_d3 F%d = pm_d3{0.0, 0.0, 0.0};" % a for a in range(N)) if self.f_reg else \
-            "for (int k = lane; k < TILE_D; k += 32) fs[k] = 0.0; __syncwarp();"
+        f_decl = "\n            ".join("pm_d3 F%d = pm_d3{0.0, 0.0, 0.0};" % a for a in sorted(self.f_reg_atoms))
+        if not self.f_reg:
+            f_decl += "\n            for (int k = lane; k < TILE_D; k += 32) fs[k] = 0.0; __syncwarp();"
         if not self.wf:
             f_decl = ""
         res_lines = []
         for a in range(N):
-            if self.f_reg:
+            if a in self.f_reg_atoms:
                 fx, fy, fz = "F%d.x" % a, "F%d.y" % a, "F%d.z" % a
             else:
                 fx, fy, fz = "fs[%d * 32 + lane]" % (3 * a), "fs[%d * 32 + lane]" % (3 * a + 1), "fs[%d * 32 + lane]" % (3 * a + 2)
@@ -240,10 +243,11 @@ class KernelSource:
         res = "\n                ".join(res_lines) if self.wf else ""
         if not self.wf:
             fout = ""
-        elif self.f_reg:
-            fout = "\n                ".join("fo[%d * 32] = F%d.x; fo[%d * 32] = F%d.y; fo[%d * 32] = F%d.z;" % (3 * a, a, 3 * a + 1, a, 3 * a + 2, a) for a in range(N))
         else:
-            fout = "for (int k = 0; k < %d; ++k) fo[k * 32] = fs[k * 32 + lane];" % (3 * N)
+            fout = "\n                ".join(
+                ("fo[%d * 32] = F%d.x; fo[%d * 32] = F%d.y; fo[%d * 32] = F%d.z;" % (3 * a, a, 3 * a + 1, a, 3 * a + 2, a)) if a in self.f_reg_atoms else
+                ("fo[%d * 32] = fs[%d * 32 + lane]; fo[%d * 32] = fs[%d * 32 + lane]; fo[%d * 32] = fs[%d * 32 + lane];"
+                 % (3 * a, 3 * a, 3 * a + 1, 3 * a + 1, 3 * a + 2, 3 * a + 2)) for a in range(N))
         if self.x_reg:
             x_load = "const double *xg = xt + (size_t)tile * TILE_D + lane;\n        " + "\n        ".join(
                 "const pm_d3 X%d = pm_d3{xg[%d * 32], xg[%d * 32], xg[%d * 32]};" % (a, 3 * a, 3 * a + 1, 3 * a + 2) for a in range(N))
@@ -475,6 +479,16 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs, warps):
         return compile_image(src, want_report=True)
 
     mode = os.environ.get("PM_SPEC_FREG", "auto")
+    if mode.startswith("top"):   # experiment: only the k busiest atoms in registers, the others in the force tile
+        k = int(mode[3:])
+        count = np.zeros(n_atoms)
+        for arr in (bonds, angles, torsions):
+            for a in np.asarray(arr).ravel():
+                count[int(a)] += 1
+        keep = [int(a) for a in np.argsort(-count, kind="stable")[:k]]
+        w = int(os.environ.get("PM_SPEC_WARPS", warps))
+        image, _ = build(keep, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
+        return image, w, 2
     if mode != "0":
         image, report = build(True, int(os.environ.get("PM_SPEC_WARPS", F_REG_WARPS)), int(os.environ.get("PM_SPEC_FENCE", F_REG_FENCE)))
         if 0 <= _spills(report, "pm_ef_spec_kernel") <= F_REG_MAX_SPILL or mode == "1":
