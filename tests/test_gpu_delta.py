@@ -150,3 +150,38 @@ def test_monte_carlo_trajectory_with_delta_evaluation(golden_dir, tmp_path, monk
     assert np.abs(results[0][0] - results[1][0]).max() <= 1e-12 * np.abs(results[0][0]).max()
     assert abs(results[0][1] - results[1][1]) <= 1e-10 * abs(results[0][1])
     assert results[0][2] == 0 and results[1][2] > 0
+
+
+def test_delta_evaluation_two_systems(golden_dir, tmp_path, monkeypatch):
+    """Two systems with their own bases: single-parameter rows of f_batch through pm_delta_eval for both, values equal to full
+    evaluations."""
+    monkeypatch.chdir(tmp_path)
+    built = []
+    for delta in (True, False):
+        systems = []
+        for k in range(2):
+            engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(golden_dir, "aniline.prmtop"),
+                                crd_file=os.path.join(golden_dir, "aniline.inpcrd"))
+            system = ParaMolSystem(name="aniline%d" % k, engine=engine, n_atoms=14)
+            system.force_field.create_force_field(ff_file=None, opt_bonds=True, opt_angles=True, opt_torsions=True)
+            system.read_data(os.path.join(golden_dir, "aniline_10_struct.nc"))
+            if k == 1:
+                system.ref_energies = np.asarray(system.ref_energies) + np.linspace(-2, 2, system.n_structures)
+            systems.append(system)
+        ps = ParameterSpace()
+        _, x0 = ps.get_optimizable_parameters(systems)
+        e_prop = EnergyProperty(systems, weight=1.0)
+        e_prop.calculate_variance()
+        f_prop = ForceProperty(systems, term_type="norm", weight=1.0)
+        f_prop.calculate_variance()
+        built.append((ObjectiveFunction(None, ps, [e_prop, f_prop], systems, weighting_method="uniform", delta_evaluation=delta, **SETTINGS),
+                      np.asarray(x0, dtype=np.float64)))
+    (of_d, x0), (of_f, _) = built
+    rng = np.random.default_rng(4)
+    assert abs(of_d.f(x0) - of_f.f(x0)) <= 1e-12
+    trial = np.repeat(x0[None], 16, 0)
+    which = rng.choice(len(x0), 16, replace=False)
+    trial[np.arange(16), which] *= 1.0 + 0.02 * rng.uniform(-1, 1, 16)
+    got, want = of_d.f_batch(trial), of_f.f_batch(trial)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    assert of_d.n_delta_rows == 32      # 16 rows x 2 systems

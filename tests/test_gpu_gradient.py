@@ -180,3 +180,41 @@ def test_non_boltzmann_is_refused(kwargs_dict, golden_dir):
                                            systems=[system], weighting_method="non_boltzmann", **SETTINGS)
     with pytest.raises(NotImplementedError):
         objective_function.f_and_grad(np.asarray(x0))
+
+
+def test_gradient_with_esp_property(kwargs_dict, golden_dir, tmp_path, monkeypatch):
+    """ENERGY + ESP: the charge derivatives of the ESP quadratic form (2 (A q - B)) reach the gradient through the particle
+    slots, together with the energy part, and agree with central differences."""
+    from paramol_b200.MM_engines.resp import RESP
+    from paramol_b200.Objective_function.Properties.esp_property import ESPProperty
+    monkeypatch.chdir(tmp_path)
+    engine = B200Engine(True, **kwargs_dict)
+    system = ParaMolSystem(name="aniline", engine=engine, n_atoms=14)
+    d = np.load(os.path.join(golden_dir, "aniline_esp.npz"))
+    rng = np.random.default_rng(2)
+    sel = rng.choice(len(d["esp"]), 2000, replace=False)
+    system.ref_coordinates = [d["conformation"], d["conformation"] + rng.normal(0, 0.01, (14, 3))]
+    system.ref_esp_grid = [d["grid"][sel], d["grid"][sel[:1500]]]
+    system.ref_esp = [d["esp"][sel], d["esp"][sel[:1500]]]
+    system.ref_energies = np.array([float(d["energy"]), float(d["energy"]) + 3.0])
+    system.n_structures = 2
+    system.force_field.create_force_field(opt_charges=True, opt_bonds=True)
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    x0 = np.asarray(x0, dtype=np.float64)
+    system.resp_engine = RESP(0, False, "L2", 1.0, 0.01, "uniform", 300.0)
+    system.resp_engine.set_initial_charges(system.force_field.force_field)
+    system.resp_engine.set_charges(system.force_field.force_field)
+    system.resp_engine.calculate_inverse_distances(system)
+    esp_prop = ESPProperty([system], weight=1.5)
+    esp_prop.calculate_variance()
+    e_prop = EnergyProperty([system], weight=0.8)
+    e_prop.calculate_variance()
+    of = ObjectiveFunction(None, ps, [e_prop, esp_prop], [system], weighting_method="uniform", **SETTINGS)
+    x = x0 * (1.0 + 0.01 * rng.uniform(-1, 1, len(x0))) + 1e-3 * rng.uniform(-1, 1, len(x0))
+    value, grad = of.f_and_grad(x)
+    assert abs(value - of.f_batch(x[None])[0]) <= 1e-10 * abs(value)
+    fd = _central_differences(of, x)
+    assert np.abs(grad - fd).max() <= 2e-6 * np.abs(fd).max()
+    charge = np.asarray([p.param_key == "charge" for p in ps.optimizable_parameters])
+    assert np.abs(grad[charge]).max() > 0 and np.abs(grad[~charge]).max() > 0
