@@ -10,6 +10,7 @@ This is the layer that replaces the ``context.setPositions -> context.getState``
 ``ParaMol/System/system.py:324-354`` and ``ParaMol/Objective_function/cpu_objective_function.py:67-108``.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -68,20 +69,9 @@ def prebuild_specialized(mm_system):
     """Generate and compile (into the in-tree cache) the topology-specialised kernel of ``mm_system`` WITHOUT a GPU: the pair
     list comes from the host-only ``pm_topology_pairs``.  Returns the image size in bytes, or 0 when the molecule is not
     eligible.  ``DeviceTopology`` finds the cached image later by the hash of the same source."""
-    from ..csrc import specialize
-    if mm_system.nonbonded_method != "NoCutoff":
-        return 0
-    warps = specialize.choose_warps(int(mm_system.n_atoms))
-    if warps is None:
-        return 0
-    L = _lib.lib()
-    topo, keep = _pm_topology(mm_system)
-    n = ctypes.c_int()
-    _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), None), "pm_topology_pairs")
-    pairs = np.zeros((max(n.value, 1), 3), dtype=np.int32)
-    _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), _iptr(pairs)), "pm_topology_pairs")
-    image, _, _ = specialize.image_for(int(mm_system.n_atoms), keep["bond"], keep["angle"], keep["tors"], keep["tper"], pairs[:n.value], warps)
-    return len(image)
+    topo, _keep = _pm_topology(mm_system)
+    built = DeviceTopology._build_specialized(mm_system, topo)
+    return 0 if built is None else len(built[0])
 
 
 class DeviceTopology:
@@ -110,8 +100,21 @@ class DeviceTopology:
         topo, self._keep = _pm_topology(s)
         self.exception_active = self._keep["act"]
         k = self._keep
+        # Small molecules: a kernel generated for this topology (csrc/specialize.py).  It works on tiles of 32 conformations, so
+        # the image is built first (host-only pair list) and, if there is one, the handle is created with that tile shape.
+        built = self._build_specialized(s, topo)
         h = ctypes.c_void_p()
-        _lib.check(L.pm_create(ctypes.byref(topo), self.device, ctypes.byref(h)), "pm_create")
+        saved_cpw = os.environ.get("PM_CPW")
+        if built is not None:
+            os.environ["PM_CPW"] = "32"
+        try:
+            _lib.check(L.pm_create(ctypes.byref(topo), self.device, ctypes.byref(h)), "pm_create")
+        finally:
+            if built is not None:
+                if saved_cpw is None:
+                    os.environ.pop("PM_CPW", None)
+                else:
+                    os.environ["PM_CPW"] = saved_cpw
         self._h = h
         self._L = L
         self.n_bonds, self.n_angles, self.n_torsions, self.n_exceptions = (len(k["bond"]), len(k["angle"]),
@@ -129,34 +132,40 @@ class DeviceTopology:
         self.off_exception = self.off_particle + 3 * self.n_atoms
         assert self.off_exception + 3 * self.n_exceptions == self.n_slots
         self.specialized = False
-        self._maybe_specialize(s)
+        if built is not None and self.conf_per_tile == 32:
+            image, warps, tiles, warps_energy = built
+            buf = ctypes.create_string_buffer(image, len(image))
+            _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy), "pm_set_specialized")
+            self.specialized = True
 
-    def _maybe_specialize(self, mm_system):
+    @staticmethod
+    def _build_specialized(mm_system, topo):
         """
-        Small molecules: install a topology-specialised E+F kernel (``csrc/specialize.py``, ``pm_set_specialized``).  Controlled by
+        (image, warps, tiles per warp, energy warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
         ``PARAMOL_B200_SPECIALIZE`` ("0" off, anything else / unset: automatic).  If the compiler is not available the generic
         kernel stays in place -- both are the CUDA path; nothing falls back to the CPU.
         """
-        import os
         if os.environ.get("PARAMOL_B200_SPECIALIZE", "auto") == "0" or mm_system.nonbonded_method != "NoCutoff":
-            return
-        if self.conf_per_tile != 32:
-            return
+            return None
         from ..csrc import specialize
-        warps = specialize.choose_warps(self.n_atoms)
-        if warps is None:
-            return
-        k = self._keep
+        n_atoms = int(mm_system.n_atoms)
+        if not specialize.eligible(n_atoms):
+            return None
+        L = _lib.lib()
+        n = ctypes.c_int()
+        _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), None), "pm_topology_pairs")
+        pairs = np.zeros((max(n.value, 1), 3), dtype=np.int32)
+        _lib.check(L.pm_topology_pairs(ctypes.byref(topo), 32, ctypes.byref(n), _iptr(pairs)), "pm_topology_pairs")
+        k = dict(bond=np.ascontiguousarray(mm_system.bond_idx, dtype=np.int32).reshape(-1, 2),
+                 angle=np.ascontiguousarray(mm_system.angle_idx, dtype=np.int32).reshape(-1, 3),
+                 tors=np.ascontiguousarray(mm_system.torsion_idx, dtype=np.int32).reshape(-1, 4),
+                 tper=np.ascontiguousarray(mm_system.torsion_per, dtype=np.int32).reshape(-1))
         try:
-            image, warps, tiles = specialize.image_for(self.n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], self.pairs(), warps)
+            return specialize.image_for(n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], pairs[:n.value])
         except RuntimeError as exc:
             import logging
             logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
-            return
-        buf = ctypes.create_string_buffer(image, len(image))
-        _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, specialize.choose_warps_energy(self.n_atoms) or 0),
-                   "pm_set_specialized")
-        self.specialized = True
+            return None
 
     def __del__(self):
         try:

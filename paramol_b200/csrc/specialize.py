@@ -453,46 +453,76 @@ def choose_warps_energy(n_atoms):
 
 
 F_REG_WARPS = 8       # forces in registers: 255 registers per thread
+F_REG_MIN_WARPS = 6
+F_REG_MAX_ATOMS = 20   # measured on B200 vs the team-mode interpreter: 18 atoms 1.28x, 20 atoms 1.24x, 24 atoms 0.89x (fits only
+                       # with a fence after every block); 28 atoms spill 1 KB at best
 F_REG_MAX_SPILL = 512  # bytes of spill stores tolerated (aniline at fence 6: 204 bytes, still the fastest)
-F_REG_FENCE = 6       # measured on B200 (aniline, 8 warps): 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms (spills)
 
 
-def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs, warps):
+def f_reg_fence(n_atoms):
+    """Blocks between scheduling fences for the forces-in-registers shape: the more atoms, the fewer registers are left for
+    interleaving (measured on B200: aniline 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms with spills; ptxas
+    reports: 20 atoms fit at 1-2, 24 atoms only at 1, 28 atoms not at all).  15-20 atoms use 2."""
+    return 6 if n_atoms <= 14 else 2
+
+
+def choose_warps_f_reg(n_atoms):
+    """Warps per CTA of the forces-in-registers shape (coordinate tile only in shared memory; 255 registers cap it at 8)."""
+    import math
+    if n_atoms > F_REG_MAX_ATOMS:
+        return None
+    tile = 3 * n_atoms * 32 * 8
+    table = ((257 * 16 + 127) // 128) * 128
+    warps = min(F_REG_WARPS, int(math.floor((MAX_SMEM - table) / (128 + tile))))
+    return warps if warps >= F_REG_MIN_WARPS else None
+
+
+def eligible(n_atoms):
+    return choose_warps_f_reg(n_atoms) is not None or choose_warps(n_atoms) is not None
+
+
+def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     """
-    One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual) and ``pm_e_spec_kernel`` (energies only;
-    ``choose_warps_energy`` warps per CTA) sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp).
+    One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual) and, when enough warps fit, ``pm_e_spec_kernel``
+    (energies only) sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp, warps_energy) or None when neither shape of
+    the E+F kernel suits the molecule.
 
-    Two shapes of the E+F kernel are tried: forces in REGISTERS (3 N doubles per lane, 8 warps, no force tile: 11 % fewer
-    instructions and no shared-memory read-modify-write chains; aniline 0.632 ms) is kept when ptxas reports (almost) no spills;
-    otherwise forces live in the shared force tile (``warps`` warps, 168 registers; aniline 0.704 ms).
+    Two shapes are tried: forces in REGISTERS (3 N doubles per lane, 8 warps, no force tile: fewer instructions and no
+    shared-memory read-modify-write chains; aniline 0.632 ms) is kept when ptxas reports (almost) no spills -- up to ~24 atoms;
+    otherwise forces live in the shared force tile (10 warps, 168 registers; aniline 0.704 ms) if at least 9 warps fit.
     """
     import os
     sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
-    we = choose_warps_energy(n_atoms)
+    we = choose_warps_energy(n_atoms) or 0
 
     def build(f_reg, w, fence):
         src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
                        fence_every=fence, sync_every=sync)
-        if we is not None:
+        if we:
             src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY, 0,
                                 with_forces=False).source(we, with_header=False)
         return compile_image(src, want_report=True)
 
     mode = os.environ.get("PM_SPEC_FREG", "auto")
-    if mode.startswith("top"):   # experiment: only the k busiest atoms in registers, the others in the force tile
+    w_tile = choose_warps(n_atoms)
+    if mode.startswith("top") and w_tile:   # experiment: only the k busiest atoms in registers, the others in the force tile
         k = int(mode[3:])
         count = np.zeros(n_atoms)
         for arr in (bonds, angles, torsions):
             for a in np.asarray(arr).ravel():
                 count[int(a)] += 1
         keep = [int(a) for a in np.argsort(-count, kind="stable")[:k]]
-        w = int(os.environ.get("PM_SPEC_WARPS", warps))
+        w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
         image, _ = build(keep, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-        return image, w, 2
-    if mode != "0":
-        image, report = build(True, int(os.environ.get("PM_SPEC_WARPS", F_REG_WARPS)), int(os.environ.get("PM_SPEC_FENCE", F_REG_FENCE)))
+        return image, w, 2, we
+    w_reg = choose_warps_f_reg(n_atoms)
+    if mode != "0" and w_reg:
+        w = int(os.environ.get("PM_SPEC_WARPS", w_reg))
+        image, report = build(True, w, int(os.environ.get("PM_SPEC_FENCE", f_reg_fence(n_atoms))))
         if 0 <= _spills(report, "pm_ef_spec_kernel") <= F_REG_MAX_SPILL or mode == "1":
-            return image, int(os.environ.get("PM_SPEC_WARPS", F_REG_WARPS)), 1
-    w = int(os.environ.get("PM_SPEC_WARPS", warps))
-    image, _ = build(False, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-    return image, w, 2
+            return image, w, 1, we
+    if w_tile:
+        w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
+        image, _ = build(False, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
+        return image, w, 2, we
+    return None
