@@ -514,6 +514,7 @@ class ObjectiveFunction:
                 part = ens.reduce(emm, fres, d_shift=st["d_shift"])
                 g["pin_out"].copy_(part, non_blocking=True)
             g["graph"] = graph
+            g["part_dev"] = part
         finally:
             ens._buffers, ens._scratch = saved_bufs, saved_scratch
         return g
@@ -529,7 +530,8 @@ class ObjectiveFunction:
         partial_list = []
         states = []
         use_graph = (n_vec == 1 and self._graphs and not self._delta and not self._cache_nonbonded
-                     and self._weighting_method.upper() != "NON_BOLTZMANN" and _dist.world_size() == 1)
+                     and self._weighting_method.upper() != "NON_BOLTZMANN")
+        multi_rank = _dist.world_size() > 1
         graph_rows = {}
         for s_idx, (system, slots) in enumerate(zip(self.systems, slots_per_system)):
             st = self._system_state(s_idx, system)
@@ -548,8 +550,11 @@ class ObjectiveFunction:
                     g = st["graph"]
                     g["pin_in"].copy_(torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64)))
                     g["graph"].replay()
-                    graph_rows[s_idx] = g["pin_out"]
-                    partial_list.append("graph")
+                    if multi_rank:   # the partial sums stay on the device for the allreduce
+                        partial_list.append(g["part_dev"])
+                    else:
+                        graph_rows[s_idx] = g["pin_out"]
+                        partial_list.append("graph")
                     continue
             host = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64))
             pin = st.get("pin")
