@@ -102,6 +102,7 @@ class B200Engine:
         self._device = device
         self._topo = None            # DeviceTopology, created lazily
         self._plan = None
+        self._slots_cache = None
         self._single = {}            # cached 1-conformation ensembles for get_potential_energy/get_forces
 
         if init_openmm:
@@ -197,7 +198,9 @@ class B200Engine:
         return self._topo
 
     def current_slots(self):
-        """Physical parameter table of the current MM system as one slots row."""
+        """Physical parameter table of the current MM system as one slots row (a fresh array)."""
+        if self._slots_cache is not None:   # left by load_slots; every other writer of the parameter arrays clears it
+            return self._slots_cache.copy()
         s = self.system
         return np.concatenate([s.bond_par.ravel(), s.angle_par.ravel(), s.torsion_par.ravel(), s.particle_par.ravel(),
                                s.exception_par.ravel()]).astype(np.float64)
@@ -225,6 +228,7 @@ class B200Engine:
 
     # ---- bonded parameters (reference :507-613) ---------------------------------------------------
     def set_harmonic_bond_force_parameters(self, ff_bond_terms):
+        self._slots_cache = None
         for k, _ in enumerate(self.forces_indexes["HarmonicBondForce"]):
             for bond_term in ff_bond_terms[k]:
                 self.system.bond_par[bond_term.idx, 0] = bond_term.parameters["bond_eq"].value
@@ -232,6 +236,7 @@ class B200Engine:
         return self.context
 
     def set_harmonic_angle_force_parameters(self, ff_angle_terms):
+        self._slots_cache = None
         for k, _ in enumerate(self.forces_indexes["HarmonicAngleForce"]):
             for angle_term in ff_angle_terms[k]:
                 self.system.angle_par[angle_term.idx, 0] = angle_term.parameters["angle_eq"].value
@@ -247,6 +252,7 @@ class B200Engine:
         return np.mod(phase, div)
 
     def set_periodic_torsion_force_parameters(self, ff_torsion_terms):
+        self._slots_cache = None
         for k, _ in enumerate(self.forces_indexes["PeriodicTorsionForce"]):
             for torsion_term in ff_torsion_terms[k]:
                 self.system.torsion_per[torsion_term.idx] = torsion_term.parameters["torsion_periodicity"].value
@@ -269,6 +275,7 @@ class B200Engine:
         Zeroes charges, sigmas and epsilons of all particles; interacting exceptions are set to 1e-16 as the
         reference does on the CPU/Reference platforms (:640-650) so that they stay "interacting".
         """
+        self._slots_cache = None
         s = self.system
         s.particle_par[:, :] = 0.0
         sel = (np.abs(s.exception_par[:, 0]) > 1e-16) & (s.exception_par[:, 2] > 1e-16)
@@ -277,6 +284,7 @@ class B200Engine:
 
     def set_nonbonded_parameters(self, force_field_optimizable):
         """The three-way branch of the reference (:661-756), including its quirks."""
+        self._slots_cache = None
         s = self.system
         if "NonbondedForce" in force_field_optimizable and "Scaling14" not in force_field_optimizable:
             nonbonded_force_terms = force_field_optimizable["NonbondedForce"]
@@ -317,6 +325,7 @@ class B200Engine:
         Adds, for every distinct torsion quadruple, the periodicities of ``periodicities`` that it does not
         have yet (with ``phase_default`` and ``v_default``).  The device topology is rebuilt on next use.
         """
+        self._slots_cache = None
         s = self.system
         new_idx, new_per, new_par = [], [], []
         prev_dihedral = None
@@ -512,6 +521,7 @@ class B200Engine:
         for arr in (s.bond_par, s.angle_par, s.torsion_par, s.particle_par, s.exception_par):
             arr[...] = np.asarray(slots_row[o:o + arr.size]).reshape(arr.shape)
             o += arr.size
+        self._slots_cache = np.array(slots_row, dtype=np.float64).reshape(-1)
 
     # ------------------------------------------------------------------------------------------
     #                                       PRIVATE METHODS
