@@ -255,7 +255,7 @@ class KernelSource:
             x_load = ""
         kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
                                 f_tile=0 if (self.f_reg or not self.wf) else 1, x_tile=0 if self.x_reg else 1, x_load=x_load)
-        return kernel if not with_header else _HEADER.format(N=N, ND=max(self.n_derived, 1)) + kernel
+        return kernel if not with_header else _HEADER.format(N=N, ND=self.n_derived) + kernel
 
 
 _HEADER = r'''// generated by paramol_b200/csrc/specialize.py -- do not edit
