@@ -133,15 +133,15 @@ class DeviceTopology:
         assert self.off_exception + 3 * self.n_exceptions == self.n_slots
         self.specialized = False
         if built is not None and self.conf_per_tile == 32:
-            image, warps, tiles, warps_energy = built
+            image, warps, tiles, warps_energy, warps_grad = built
             buf = ctypes.create_string_buffer(image, len(image))
-            _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy), "pm_set_specialized")
+            _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy, warps_grad), "pm_set_specialized")
             self.specialized = True
 
     @staticmethod
     def _build_specialized(mm_system, topo):
         """
-        (image, warps, tiles per warp, energy warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
+        (image, warps, tiles per warp, energy warps, gradient warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
         ``PARAMOL_B200_SPECIALIZE`` ("0" off, anything else / unset: automatic).  If the compiler is not available the generic
         kernel stays in place -- both are the CUDA path; nothing falls back to the CPU.
         """

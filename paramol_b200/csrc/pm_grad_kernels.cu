@@ -387,7 +387,7 @@ extern "C" long pm_grad_scratch_doubles(pm_handle h) {
     cudaSetDevice(h->device);
     PmGradState *st = pm_grad_state(h);
     if (!st) return -1;
-    return (long)st->grid_max * st->n_items * 128;
+    return std::max((long)st->grid_max * st->n_items * 128, pm_spec_grad_scratch(h));
 }
 
 extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coord_tiles_dev, const double *fmm_tiles_dev,
@@ -399,6 +399,9 @@ extern "C" int pm_grad(pm_handle h, const double *derived_dev, const double *coo
     if (coef_f_dev && (!fmm_tiles_dev || !fref_tiles_dev)) return pm_fail_msg("pm_grad: force coefficients need the MM and reference force tiles");
     if (h->rf) return pm_fail_msg("pm_grad: the cutoff / reaction-field nonbonded variant has no analytic gradient in this kernel generation");
     PMG_CUDA(cudaSetDevice(h->device));
+    if (pm_spec_can_grad(h))  // small molecule with a generated gradient kernel (csrc/specialize.py: GradKernelSource)
+        return pm_spec_grad(h, derived_dev, coord_tiles_dev, fmm_tiles_dev, fref_tiles_dev, n_conf, coef_e_dev, coef_f_dev, gout_dev,
+                            scratch_dev, (cudaStream_t)stream);
     PmGradState *st = pm_grad_state(h);
     if (!st) return pm_fail_msg("pm_grad: molecule too large for the gradient kernel's shared-memory tile");
     cudaStream_t s = (cudaStream_t)stream;

@@ -67,3 +67,7 @@ int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_byte
 int pm_spec_can_eval(pm_handle h, int with_forces);
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
                  double *fres, double *fmm_t, int with_forces, cudaStream_t stream);
+int pm_spec_can_grad(pm_handle h);
+long pm_spec_grad_scratch(pm_handle h);  // doubles
+int pm_spec_grad(pm_handle h, const double *derived_dev, const double *xt, const double *fmm_t, const double *fref_t, long n_conf,
+                 const double *coef_e, const double *coef_f, double *gout, double *scratch, cudaStream_t stream);

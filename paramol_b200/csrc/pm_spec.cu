@@ -24,9 +24,12 @@ struct PmSpecState {
     cudaLibrary_t lib;
     cudaKernel_t kernel;    // pm_ef_spec_kernel: energies, forces, residual
     cudaKernel_t kernel_e;  // pm_e_spec_kernel: energies only (null when the image has none)
+    cudaKernel_t kernel_g;  // pm_grad_spec_kernel + pm_grad_spec_reduce: analytic parameter gradient (null when absent)
+    cudaKernel_t kernel_gr;
     double *tab_dev;  // __constant__ spec_tab[n_derived + 9 N]: derived table of the vector being evaluated, then the metric
-    int warps, warps_e;
-    size_t smem, smem_e;
+    int warps, warps_e, warps_g;
+    int ngp;          // padded number of gradient quantities (rows of the partial array are ngp doubles)
+    size_t smem, smem_e, smem_g;
 };
 
 static void pm_spec_free(void *p) {
@@ -38,7 +41,8 @@ static void pm_spec_free(void *p) {
 
 extern "C" int pm_has_specialized(pm_handle h) { return h && h->spec_state ? 1 : 0; }
 
-extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int tiles_per_warp, int warps_energy) {
+extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int tiles_per_warp, int warps_energy,
+                                  int warps_grad) {
     if (!h) return pm_fail_msg("pm_set_specialized: null handle");
     PMS_CUDA(cudaSetDevice(h->device));
     if (h->spec_state) {
@@ -85,6 +89,32 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
         st->kernel_e = nullptr;
     }
     cudaGetLastError();
+    st->kernel_g = nullptr;
+    st->kernel_gr = nullptr;
+    st->warps_g = 0;
+    st->ngp = 0;
+    st->smem_g = 0;
+    if (warps_grad > 0 && warps_grad <= 32) {
+        void *info = nullptr;
+        size_t info_bytes = 0;
+        int host_info[2] = {0, 0};
+        if (cudaLibraryGetKernel(&st->kernel_g, st->lib, "pm_grad_spec_kernel") == cudaSuccess &&
+            cudaLibraryGetKernel(&st->kernel_gr, st->lib, "pm_grad_spec_reduce") == cudaSuccess &&
+            cudaLibraryGetGlobal(&info, &info_bytes, st->lib, "grad_info") == cudaSuccess && info_bytes == sizeof(host_info) &&
+            cudaMemcpy(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost) == cudaSuccess &&
+            host_info[1] == 2 * (h->prog.n_bonds + h->prog.n_angles + h->prog.n_torsions) + 3 * h->prog.n_pairs) {
+            st->warps_g = warps_grad;
+            st->ngp = host_info[0];
+            st->smem_g = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) +
+                         (size_t)warps_grad * (128 + 2 * tile + (size_t)st->ngp * sizeof(double));
+            if (st->smem_g > (size_t)h->max_smem ||
+                cudaFuncSetAttribute((const void *)st->kernel_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_g) != cudaSuccess)
+                st->kernel_g = nullptr;
+        } else {
+            st->kernel_g = nullptr;
+        }
+        cudaGetLastError();
+    }
     h->spec_state = st;
     h->spec_free = pm_spec_free;
     return pm_spec_metric_changed(h);
@@ -133,5 +163,36 @@ int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double
         void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p};
         PMS_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
     }
+    return 0;
+}
+
+// ---- generated analytic-gradient kernel ----------------------------------------------------------------------------
+int pm_spec_can_grad(pm_handle h) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    return st && st->kernel_g ? 1 : 0;
+}
+
+long pm_spec_grad_scratch(pm_handle h) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    if (!st || !st->kernel_g) return 0;
+    return (long)h->n_sm * st->warps_g * st->ngp;
+}
+
+int pm_spec_grad(pm_handle h, const double *derived_dev, const double *xt, const double *fmm_t, const double *fref_t, long n_conf,
+                 const double *coef_e, const double *coef_f, double *gout, double *scratch, cudaStream_t stream) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    const size_t nd = (size_t)h->prog.doff_pair + 3 * (size_t)h->prog.n_pairs;
+    long n_tiles = (n_conf + 31) / 32;
+    long grid = h->n_sm;
+    if (grid * st->warps_g > n_tiles) grid = (n_tiles + st->warps_g - 1) / st->warps_g;
+    if (grid < 1) grid = 1;
+    PMS_CUDA(cudaMemcpyAsync(st->tab_dev, derived_dev, sizeof(double) * nd, cudaMemcpyDeviceToDevice, stream));
+    const double2 *acos_tab = h->d_acos;
+    void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fmm_t, (void *)&fref_t, (void *)&coef_e, (void *)&coef_f, (void *)&n_conf,
+                    (void *)&n_tiles, (void *)&scratch};
+    PMS_CUDA(cudaLaunchKernel((const void *)st->kernel_g, dim3((unsigned)grid), dim3(st->warps_g * 32), args, st->smem_g, stream));
+    int n_rows = (int)grid * st->warps_g;
+    void *rargs[] = {(void *)&scratch, (void *)&n_rows, (void *)&gout};
+    PMS_CUDA(cudaLaunchKernel((const void *)st->kernel_gr, dim3((unsigned)((st->ngp + 127) / 128)), dim3(128), rargs, 0, stream));
     return 0;
 }

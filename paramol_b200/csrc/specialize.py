@@ -354,6 +354,277 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
 '''
 
 
+class GradKernelSource(KernelSource):
+    """
+    Generated ANALYTIC-GRADIENT kernel (``pm_grad_spec_kernel``): the same blocks as the E+F kernel, one conformation per lane,
+    but instead of forces every term produces its contributions to d f / d parameter (see pm_grad_kernels.cu for the algebra:
+    a_s dE/dp - (d2E/dq dp)(grad q . lambda)).  The per-lane quantities of 32 terms at a time are summed over the 32
+    conformations of the tile with a transposing butterfly (31 shuffle steps for 32 sums) and added to the warp's accumulators
+    in shared memory; a second generated kernel adds the warps' partials in a fixed order and scatters them to the gout layout
+    of ``pm_grad`` through ``grad_perm``.  Deterministic, no atomics.
+    """
+
+    def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=2):
+        KernelSource.__init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_grad_spec_kernel", False, fence_every, 0, True)
+        self.go_bond = 0
+        self.go_angle = 2 * len(self.bonds)
+        self.go_tors = self.go_angle + 2 * len(self.angles)
+        self.go_pair = self.go_tors + 2 * len(self.torsions)
+        self.n_gout = self.go_pair + 3 * len(self.pairs)
+        self.order = []   # gout index of every emitted quantity, in emission order
+
+    def L(self, atom):
+        return "PML(%d)" % atom
+
+    def quantity(self, gout_index, expr):
+        k = len(self.order) % 32
+        self.order.append(gout_index)
+        self.emit("Q[%d] = %s;" % (k, expr))
+        if k == 31:
+            self.flush()
+
+    def flush(self, final=False):
+        n = len(self.order)
+        if final:
+            k = n % 32
+            if k == 0:
+                return
+            for i in range(k, 32):
+                self.emit("Q[%d] = 0.0;" % i)
+                self.order.append(-1)
+            n = len(self.order)
+        self.emit("{ const double r_ = pmg_reduce32(Q, lane); acc[%d + lane] += r_; }" % (n - 32))
+
+    def gen_stars(self):
+        N = self.N
+        bond_of = {}
+        for t, (i, j) in enumerate(self.bonds):
+            bond_of[(i, j)] = t
+            bond_of[(j, i)] = t
+        angle_at = [[] for _ in range(N)]
+        for t, (a, b, c) in enumerate(self.angles):
+            angle_at[b].append((t, a, c))
+        done_bond = set()
+        for c in range(N):
+            need = []
+            for (i, j) in self.bonds:
+                if i == c and j not in need:
+                    need.append(j)
+                if j == c and i not in need:
+                    need.append(i)
+            for (_, a, b) in angle_at[c]:
+                for v in (a, b):
+                    if v not in need:
+                        need.append(v)
+            own = [n for n in need if (c, n) in bond_of and bond_of[(c, n)] not in done_bond]
+            if not own and not angle_at[c]:
+                continue
+            used = set(own)
+            for (_, a, b) in angle_at[c]:
+                used.update((a, b))
+            need = [n for n in need if n in used]
+            self.emit("{  // star %d" % c)
+            self.emit("const pm_d3 xc = %s, lc = %s;" % (self.X(c), self.L(c)))
+            for n in need:
+                self.emit("const pm_d3 d%d = pm_sub(xc, %s); const double q%d = pm_dot(d%d, d%d); const double i%d = pm_rsqrt(q%d);"
+                          " const pm_d3 m%d = pm_sub(lc, %s);" % (n, self.X(n), n, n, n, n, n, n, self.L(n)))
+            for n in own:
+                t = bond_of[(c, n)]
+                done_bond.add(t)
+                o = self.off_bond + 2 * t
+                self.emit("{ const double dl = fma(q%d, i%d, -%s); const double dr = i%d * pm_dot(d%d, m%d);" % (n, n, self.P(o), n, n, n))
+                self.quantity(self.go_bond + 2 * t, "%s * (dr - ae * dl)" % self.P(o + 1))
+                self.quantity(self.go_bond + 2 * t + 1, "dl * fma(0.5 * ae, dl, -dr)")
+                self.emit("}")
+            for (t, a, b) in angle_at[c]:
+                o = self.off_angle + 2 * t
+                self.emit("{ const pm_d3 pc = pm_cross(d%d, d%d); const double pp2 = pm_dot(pc, pc); const double i01 = i%d * i%d;" % (a, b, a, b))
+                self.emit("  const double ip = pm_rsqrt(fmax(pp2, 1.0e-12)); const double th = pm_acos_cs(pm_dot(d%d, d%d) * i01, pp2 * ip * i01, s_acos);" % (a, b))
+                self.emit("  const double dth = ip * ((i%d * i%d) * pm_dot(pm_cross(d%d, pc), m%d) - (i%d * i%d) * pm_dot(pm_cross(d%d, pc), m%d));"
+                          % (a, a, a, a, b, b, b, b))
+                self.emit("  const double dl = th - %s;" % self.P(o))
+                self.quantity(self.go_angle + 2 * t, "%s * (dth - ae * dl)" % self.P(o + 1))
+                self.quantity(self.go_angle + 2 * t + 1, "dl * fma(0.5 * ae, dl, -dth)")
+                self.emit("}")
+            self.end_block()
+        assert len(done_bond) == len(self.bonds)
+
+    def gen_axes(self):
+        axes = {}
+        for t, (i, j, k, l) in enumerate(self.torsions):
+            if (k, j) in axes:
+                axes[(k, j)].append((t, l, i))
+            else:
+                axes.setdefault((j, k), []).append((t, i, l))
+        for (j, k), terms in axes.items():
+            subs_i = sorted({i for (_, i, _) in terms})
+            subs_l = sorted({l for (_, _, l) in terms})
+            self.emit("{  // axis %d-%d" % (j, k))
+            self.emit("const pm_d3 xj = %s, xk = %s, lj = %s, lk = %s; const pm_d3 d1 = pm_sub(xk, xj); const double bb = pm_dot(d1, d1);"
+                      % (self.X(j), self.X(k), self.L(j), self.L(k)))
+            self.emit("const double rbb = pm_rsqrt(bb); const double nb = bb * rbb, ibb = rbb * rbb;")
+            for i in subs_i:
+                self.emit("const pm_d3 a%d = pm_sub(%s, xj); const pm_d3 u%d = pm_cross(a%d, d1); const double s%d = pm_rsqrt(pm_dot(u%d, u%d));"
+                          " const double g%d = pm_dot(a%d, d1) * ibb;" % (i, self.X(i), i, i, i, i, i, i, i))
+                # w0 = l_i + (ff1 - 1) l_j - ff1 l_k
+                self.emit("const pm_d3 li%d = %s; const pm_d3 v%d = pm_d3{li%d.x + (g%d - 1.0) * lj.x - g%d * lk.x, li%d.y + (g%d - 1.0) * lj.y - g%d * lk.y,"
+                          " li%d.z + (g%d - 1.0) * lj.z - g%d * lk.z}; const double p%d = pm_dot(u%d, v%d) * (s%d * s%d);"
+                          % (i, self.L(i), i, i, i, i, i, i, i, i, i, i, i, i, i, i, i))
+            for l in subs_l:
+                self.emit("const pm_d3 b%d = pm_sub(xk, %s); const pm_d3 w%d = pm_cross(d1, b%d); const double t%d = pm_rsqrt(pm_dot(w%d, w%d));"
+                          " const double h%d = pm_dot(b%d, d1) * ibb;" % (l, self.X(l), l, l, l, l, l, l, l))
+                # w3 = l_l - ff2 l_j + (ff2 - 1) l_k
+                self.emit("const pm_d3 ll%d = %s; const pm_d3 z%d = pm_d3{ll%d.x - h%d * lj.x + (h%d - 1.0) * lk.x, ll%d.y - h%d * lj.y + (h%d - 1.0) * lk.y,"
+                          " ll%d.z - h%d * lj.z + (h%d - 1.0) * lk.z}; const double r%d = pm_dot(w%d, z%d) * (t%d * t%d);"
+                          % (l, self.L(l), l, l, l, l, l, l, l, l, l, l, l, l, l, l, l))
+            cells = {}
+            for (t, i, l) in terms:
+                cells.setdefault((i, l), []).append(t)
+            for (i, l), ts in cells.items():
+                ts = sorted(ts, key=lambda t: self.tors_per[t])
+                self.emit("{ const double i12 = s%d * t%d; const double cphi = pm_dot(u%d, w%d) * i12, sphi = nb * pm_dot(a%d, w%d) * i12;" % (i, l, i, l, i, l))
+                self.emit("  const double dphi = nb * (p%d - r%d); double cn = 1.0, sn = 0.0;" % (i, l))
+                cur = 0
+                for t in ts:
+                    per = self.tors_per[t]
+                    while cur < per:
+                        self.emit("  { const double tt = cn * cphi - sn * sphi; sn = fma(sn, cphi, cn * sphi); cn = tt; }")
+                        cur += 1
+                    o = self.off_tors + 4 * t
+                    self.emit("  { const double cpsi = fma(cn, %s, sn * %s), spsi = fma(sn, %s, -(cn * %s));" % (self.P(o + 2), self.P(o + 3), self.P(o + 2), self.P(o + 3)))
+                    self.quantity(self.go_tors + 2 * t, "%s * (ae * spsi - %d.0 * cpsi * dphi)" % (self.P(o), per))
+                    self.quantity(self.go_tors + 2 * t + 1, "fma(ae, 1.0 + cpsi, %d.0 * spsi * dphi)" % per)
+                    self.emit("  }")
+                self.emit("}")
+            self.end_block()
+
+    def gen_pairs(self):
+        by_i = {}
+        for q, (i, j, _) in enumerate(self.pairs):
+            by_i.setdefault(i, []).append((q, j))
+        for i, lst in by_i.items():
+            self.emit("{  // pairs of atom %d" % i)
+            self.emit("const pm_d3 xi = %s, li = %s;" % (self.X(i), self.L(i)))
+            for (q, j) in lst:
+                self.emit("{ const pm_d3 d = pm_sub(xi, %s); const double rinv = pm_rsqrt(pm_dot(d, d)); const double u = rinv * rinv; const double u3 = u * u * u;"
+                          " const double us = u * pm_dot(d, pm_sub(li, %s));" % (self.X(j), self.L(j)))
+                self.quantity(self.go_pair + 3 * q, "(u3 * u3) * fma(12.0, us, ae)")
+                self.quantity(self.go_pair + 3 * q + 1, "-u3 * fma(6.0, us, ae)")
+                self.quantity(self.go_pair + 3 * q + 2, "rinv * (ae + us)")
+                self.emit("}")
+            self.end_block()
+
+    def source(self, warps):
+        N = self.N
+        self.lines = []
+        self._blocks = 0
+        self.order = []
+        self.gen_stars()
+        self.gen_axes()
+        self.gen_pairs()
+        self.flush(final=True)
+        body = "\n            ".join(self.lines)
+        lam = []
+        for a in range(N):
+            m = ["spec_tab[SPEC_ND + %d]" % (9 * a + q) for q in range(9)]
+            lam.append("{ const double dx = fm[%d * 32] - fr[%d * 32], dy = fm[%d * 32] - fr[%d * 32], dz = fm[%d * 32] - fr[%d * 32];"
+                       % (3 * a, 3 * a, 3 * a + 1, 3 * a + 1, 3 * a + 2, 3 * a + 2))
+            lam.append("  lc_base[%d * 32] = bf * ((%s + %s) * dx + (%s + %s) * dy + (%s + %s) * dz);" % (3 * a, m[0], m[0], m[1], m[3], m[2], m[6]))
+            lam.append("  lc_base[%d * 32] = bf * ((%s + %s) * dx + (%s + %s) * dy + (%s + %s) * dz);" % (3 * a + 1, m[3], m[1], m[4], m[4], m[5], m[7]))
+            lam.append("  lc_base[%d * 32] = bf * ((%s + %s) * dx + (%s + %s) * dy + (%s + %s) * dz); }" % (3 * a + 2, m[6], m[2], m[7], m[5], m[8], m[8]))
+        ngp = len(self.order)
+        perm = ", ".join(str(v) for v in self.order) if self.order else "-1"
+        return _GRAD_KERNEL.format(W=warps, body=body, lam="\n                ".join(lam), NGP=max(ngp, 32), perm=perm, NG=self.n_gout)
+
+
+_GRAD_KERNEL = r'''
+#define PML(a) pm_d3{{lc_base[(3 * (a)) * 32], lc_base[(3 * (a) + 1) * 32], lc_base[(3 * (a) + 2) * 32]}}
+#define SPEC_NGP {NGP}
+__constant__ int grad_perm[SPEC_NGP] = {{{perm}}};
+__constant__ int grad_info[2] = {{SPEC_NGP, {NG}}};
+
+// sums of Q[0..31] over the 32 lanes: lane l returns the total of Q[l] (transposing butterfly, 31 shuffle steps)
+__device__ __forceinline__ double pmg_reduce32(double (&q)[32], int lane) {{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {{
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {{
+            const double a = q[i], b = q[i + o];
+            const double send = up ? a : b, keep = up ? b : a;
+            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }}
+    }}
+    return q[0];
+}}
+
+extern "C" __global__ void __launch_bounds__({W} * 32, 1)
+    pm_grad_spec_kernel(const double2 *__restrict__ acos_tab, const double *__restrict__ xt, const double *__restrict__ fmm_t,
+                        const double *__restrict__ fref_t, const double *__restrict__ coef_e, const double *__restrict__ coef_f,
+                        long n_conf, long n_tiles, double *__restrict__ partial) {{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
+    size_t off = ((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127;
+    const size_t per_warp = 128 + (size_t)TILE_D * sizeof(double) * 2 + (size_t)SPEC_NGP * sizeof(double);
+    unsigned char *wbase = smem_raw + off + per_warp * warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
+    double *xs = reinterpret_cast<double *>(wbase + 128);
+    double *ls = xs + TILE_D;
+    double *acc = ls + TILE_D;
+    for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = acos_tab[i];
+    for (int i = lane; i < SPEC_NGP; i += 32) acc[i] = 0.0;
+    if (lane == 0) {{
+        pm_mbar_init(bar, 1);
+        pm_fence_mbar_init();
+    }}
+    __syncthreads();
+    uint32_t parity = 0;
+    const long warp_stride = (long)gridDim.x * n_warps;
+    for (long tile = (long)blockIdx.x * n_warps + warp; tile < n_tiles; tile += warp_stride) {{
+        if (lane == 0) {{
+            pm_fence_proxy_async();
+            pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
+            pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+        }}
+        const long sconf = tile * 32 + lane;
+        const bool valid = sconf < n_conf;
+        const double ae = (valid && coef_e != nullptr) ? coef_e[sconf] : 0.0;
+        const double bf = (valid && coef_f != nullptr) ? coef_f[sconf] : 0.0;
+        double *lc_base = ls + lane;
+        if (coef_f != nullptr) {{
+            const double *fm = fmm_t + (size_t)tile * TILE_D + lane, *fr = fref_t + (size_t)tile * TILE_D + lane;
+            {{
+                {lam}
+            }}
+        }} else {{
+            for (int k = 0; k < 3 * SPEC_N; ++k) lc_base[k * 32] = 0.0;
+        }}
+        pm_mbar_wait(bar, parity);
+        parity ^= 1;
+        __syncwarp();
+        const double *xc_base = xs + lane;
+        double Q[32];
+        {{
+            {body}
+        }}
+        __syncwarp();
+    }}
+    double *out = partial + ((size_t)blockIdx.x * n_warps + warp) * SPEC_NGP;
+    for (int i = lane; i < SPEC_NGP; i += 32) out[i] = acc[i];
+}}
+
+// gout[grad_perm[k]] = sum over the warps' partial rows (fixed order)
+extern "C" __global__ void pm_grad_spec_reduce(const double *__restrict__ partial, int n_rows, double *__restrict__ gout) {{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= SPEC_NGP || grad_perm[k] < 0) return;
+    double s = 0.0;
+    for (int r = 0; r < n_rows; ++r) s += partial[(size_t)r * SPEC_NGP + k];
+    gout[grad_perm[k]] = s;
+}}
+'''
+
+
 def generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_registers=True, name="pm_ef_spec_kernel",
              x_in_registers=False, fence_every=0, sync_every=0, with_forces=True):
     return KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, f_in_registers, name, x_in_registers,
@@ -443,6 +714,16 @@ def _spills(report, kernel):
     return -1
 
 
+def choose_warps_grad(n_atoms, n_gout):
+    """Warps per CTA of the generated gradient kernel (coordinate tile + lambda tile + the warp's accumulators), or 0."""
+    import math
+    tile = 3 * n_atoms * 32 * 8
+    table = ((257 * 16 + 127) // 128) * 128
+    ngp = max(32, (n_gout + 31) // 32 * 32)
+    warps = min(MAX_WARPS, int(math.floor((MAX_SMEM - table) / (128 + 2 * tile + 8 * ngp))))
+    return warps if warps >= 6 else 0
+
+
 def choose_warps_energy(n_atoms):
     """Warps per CTA of the energy-only specialised kernel (coordinate tile only)."""
     import math
@@ -484,7 +765,8 @@ def eligible(n_atoms):
 def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     """
     One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual) and, when enough warps fit, ``pm_e_spec_kernel``
-    (energies only) sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp, warps_energy) or None when neither shape of
+    (energies only) and the gradient kernels sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp, warps_energy,
+    warps_grad) or None when neither shape of
     the E+F kernel suits the molecule.
 
     Two shapes are tried: forces in REGISTERS (3 N doubles per lane, 8 warps, no force tile: fewer instructions and no
@@ -495,12 +777,18 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
     we = choose_warps_energy(n_atoms) or 0
 
+    grad = GradKernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=FENCE_EVERY) \
+        if os.environ.get("PM_SPEC_GRAD", "1") != "0" else None
+    wg = choose_warps_grad(n_atoms, grad.n_gout) if grad is not None else 0
+
     def build(f_reg, w, fence):
         src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
                        fence_every=fence, sync_every=sync)
         if we:
             src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY, 0,
                                 with_forces=False).source(we, with_header=False)
+        if wg:
+            src += grad.source(wg)
         return compile_image(src, want_report=True)
 
     mode = os.environ.get("PM_SPEC_FREG", "auto")
@@ -514,15 +802,15 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
         keep = [int(a) for a in np.argsort(-count, kind="stable")[:k]]
         w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
         image, _ = build(keep, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-        return image, w, 2, we
+        return image, w, 2, we, wg
     w_reg = choose_warps_f_reg(n_atoms)
     if mode != "0" and w_reg:
         w = int(os.environ.get("PM_SPEC_WARPS", w_reg))
         image, report = build(True, w, int(os.environ.get("PM_SPEC_FENCE", f_reg_fence(n_atoms))))
         if 0 <= _spills(report, "pm_ef_spec_kernel") <= F_REG_MAX_SPILL or mode == "1":
-            return image, w, 1, we
+            return image, w, 1, we, wg
     if w_tile:
         w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
         image, _ = build(False, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-        return image, w, 2, we
+        return image, w, 2, we, wg
     return None
