@@ -162,7 +162,7 @@ class DeviceTopology:
                  tper=np.ascontiguousarray(mm_system.torsion_per, dtype=np.int32).reshape(-1))
         try:
             return specialize.image_for(n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], pairs[:n.value])
-        except RuntimeError as exc:
+        except (RuntimeError, OSError) as exc:   # no compiler, compile error, cache directory not writable
             import logging
             logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
             return None

@@ -780,6 +780,10 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     grad = GradKernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=FENCE_EVERY) \
         if os.environ.get("PM_SPEC_GRAD", "1") != "0" else None
     wg = choose_warps_grad(n_atoms, grad.n_gout) if grad is not None else 0
+    if wg and os.environ.get("PM_SPEC_GRAD_WARPS"):
+        wg = min(wg, int(os.environ["PM_SPEC_GRAD_WARPS"]))
+    if grad is not None and os.environ.get("PM_SPEC_GRAD_FENCE"):
+        grad.fence_every = int(os.environ["PM_SPEC_GRAD_FENCE"])
 
     def build(f_reg, w, fence):
         src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
