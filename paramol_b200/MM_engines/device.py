@@ -135,8 +135,11 @@ class DeviceTopology:
         if built is not None and self.conf_per_tile == 32:
             image, warps, tiles, warps_energy, warps_grad = built
             buf = ctypes.create_string_buffer(image, len(image))
-            _lib.check(self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy, warps_grad), "pm_set_specialized")
-            self.specialized = True
+            if self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy, warps_grad) == 0:
+                self.specialized = True
+            else:   # the generic kernel of the same handle keeps working
+                import logging
+                logging.warning("paramol_b200: specialised kernel not installed (%s)", self._L.pm_last_error().decode())
 
     @staticmethod
     def _build_specialized(mm_system, topo):
