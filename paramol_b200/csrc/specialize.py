@@ -735,7 +735,7 @@ def choose_warps_energy(n_atoms):
 
 F_REG_WARPS = 8       # forces in registers: 255 registers per thread
 F_REG_MIN_WARPS = 6
-F_REG_MAX_ATOMS = 20   # measured on B200 vs the team-mode interpreter: 18 atoms 1.28x, 20 atoms 1.24x, 24 atoms 0.89x (fits only
+F_REG_MAX_ATOMS = 20   # measured on B200 vs the team-mode interpreter: 18 atoms 1.28x, 20 atoms 1.24x, 22 atoms 0.84x, 24 atoms 0.89x (fits only
                        # with a fence after every block); 28 atoms spill 1 KB at best
 F_REG_MAX_SPILL = 512  # bytes of spill stores tolerated (aniline at fence 6: 204 bytes, still the fastest)
 
