@@ -133,7 +133,8 @@ class CpuOracleWorkload:
         from paramol_b200.Utils.synthetic import perturbed_conformations
         self.O = O
         self.mm = mm_system
-        self.threads = threads or O.max_threads()
+        # every host core this process may run on (torchrun exports OMP_NUM_THREADS=1; the C port takes the count explicitly)
+        self.threads = threads or max(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), 1)
         probe = perturbed_conformations(x_base, 4096, seed=99)
         O.energies_forces(mm_system, probe[:64], n_threads=self.threads)  # spin up the OpenMP team
         t0 = time.perf_counter()
