@@ -158,12 +158,12 @@ int pm_esp_potential(int n_atoms, const double *coords_dev, const double *grid_d
  * exactly this topology by paramol_b200/csrc/specialize.py (the topology as straight-line code); pm_eval / pm_eval_ex then use
  * it for full evaluations (mode 0; `pm_e_spec_kernel` with warps_energy warps per CTA for with_forces = 0 when the image has it)
  * and the generic kernel for everything else.  Same inputs, same
- * outputs, same reference code replaced as pm_eval.  tiles_per_warp: 2 (coordinate + force tile in shared memory) or 1 (forces
- * kept in registers).  warps_grad > 0: the image also holds `pm_grad_spec_kernel` / `pm_grad_spec_reduce`, which pm_grad then
+ * outputs, same reference code replaced as pm_eval.  n_force_tile_atoms: how many atoms keep their force
+ * accumulators in a (packed) shared-memory tile; the others are accumulated in registers (0 = all in registers).  warps_grad > 0: the image also holds `pm_grad_spec_kernel` / `pm_grad_spec_reduce`, which pm_grad then
  * uses.  image = NULL removes it.  Needs pm_conf_per_tile(h) == 32.
  * pm_topology_pairs (host only, no CUDA call): the pair list in derived-table order for a given conformations-per-tile value,
  * so that the source can be generated and compiled before a GPU is present. */
-int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int tiles_per_warp, int warps_energy,
+int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int n_force_tile_atoms, int warps_energy,
                        int warps_grad);
 int pm_has_specialized(pm_handle h);
 int pm_topology_pairs(const pm_topology *topo, int cpw, int *n_pairs, int *out_pairs);

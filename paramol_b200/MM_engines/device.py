@@ -144,7 +144,7 @@ class DeviceTopology:
     @staticmethod
     def _build_specialized(mm_system, topo):
         """
-        (image, warps, tiles per warp, energy warps, gradient warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
+        (image, warps, atoms in the force tile, energy warps, gradient warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
         ``PARAMOL_B200_SPECIALIZE`` ("0" off, anything else / unset: automatic).  If the compiler is not available the generic
         kernel stays in place -- both are the CUDA path; nothing falls back to the CPU.
         """
@@ -152,7 +152,7 @@ class DeviceTopology:
             return None
         from ..csrc import specialize
         n_atoms = int(mm_system.n_atoms)
-        if not specialize.eligible(n_atoms):
+        if not specialize.eligible(n_atoms) and not os.environ.get("PM_SPEC_FREG", "").startswith("top"):
             return None
         L = _lib.lib()
         n = ctypes.c_int()

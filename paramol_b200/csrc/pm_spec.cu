@@ -41,7 +41,7 @@ static void pm_spec_free(void *p) {
 
 extern "C" int pm_has_specialized(pm_handle h) { return h && h->spec_state ? 1 : 0; }
 
-extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int tiles_per_warp, int warps_energy,
+extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, int warps, int n_force_tile_atoms, int warps_energy,
                                   int warps_grad) {
     if (!h) return pm_fail_msg("pm_set_specialized: null handle");
     PMS_CUDA(cudaSetDevice(h->device));
@@ -51,7 +51,8 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     }
     if (!image || n_bytes <= 0) return 0;  // NULL image: back to the generic kernel
     if (h->rf || h->prog.cpw != 32) return pm_fail_msg("pm_set_specialized: needs a NoCutoff topology with 32 conformations per tile");
-    if (warps < 1 || warps > 32 || tiles_per_warp < 1 || tiles_per_warp > 2) return pm_fail_msg("pm_set_specialized: bad warp / tile count");
+    if (warps < 1 || warps > 32 || n_force_tile_atoms < 0 || n_force_tile_atoms > h->prog.n_atoms)
+        return pm_fail_msg("pm_set_specialized: bad warp count or force-tile size");
     PmSpecState *st = new PmSpecState();
     if (cudaLibraryLoadData(&st->lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
         delete st;
@@ -69,7 +70,7 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     st->tab_dev = (double *)tab;
     st->warps = warps;
     const size_t tile = (size_t)3 * h->prog.n_atoms * 32 * sizeof(double);
-    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps * (128 + (size_t)tiles_per_warp * tile);
+    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps * (128 + tile + (size_t)3 * n_force_tile_atoms * 32 * sizeof(double));
     if (st->smem > (size_t)h->max_smem ||
         cudaFuncSetAttribute((const void *)st->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess) {
         cudaGetLastError();

@@ -32,6 +32,9 @@ class KernelSource:
         # forces in registers: True (all atoms), False (none: shared force tile) or an iterable of atom indices (the rest go to the tile)
         self.f_reg_atoms = set(range(int(n_atoms))) if f_in_registers is True else set(int(a) for a in (f_in_registers or ()))
         self.f_reg = len(self.f_reg_atoms) == int(n_atoms)
+        # atoms whose forces live in the shared force tile, packed: tile row of atom a = 3 * f_tile_index[a]
+        self.f_tile_atoms = [a for a in range(int(n_atoms)) if a not in self.f_reg_atoms]
+        self.f_tile_index = {a: i for i, a in enumerate(self.f_tile_atoms)}
         self.x_reg = bool(x_in_registers)
         self.fence_every = int(fence_every)
         self.sync_every = int(sync_every)
@@ -75,7 +78,7 @@ class KernelSource:
         if atom in self.f_reg_atoms:
             self.emit("F%d.x %s= %s.x; F%d.y %s= %s.y; F%d.z %s= %s.z;" % (atom, sign, expr_vec, atom, sign, expr_vec, atom, sign, expr_vec))
         else:
-            self.emit("PMF_%s(%d, %s);" % ("ADD" if sign == "+" else "SUB", atom, expr_vec))
+            self.emit("PMF_%s(%d, %s);" % ("ADD" if sign == "+" else "SUB", self.f_tile_index[atom], expr_vec))
 
     # ---- stars: bonds + angles around a centre ---------------------------------------------------
     def gen_stars(self):
@@ -226,7 +229,7 @@ class KernelSource:
         body = "\n            ".join(self.lines)
         f_decl = "\n            ".join("pm_d3 F%d = pm_d3{0.0, 0.0, 0.0};" % a for a in sorted(self.f_reg_atoms))
         if not self.f_reg:
-            f_decl += "\n            for (int k = lane; k < TILE_D; k += 32) fs[k] = 0.0; __syncwarp();"
+            f_decl += "\n            for (int k = lane; k < %d; k += 32) fs[k] = 0.0; __syncwarp();" % (3 * len(self.f_tile_atoms) * 32)
         if not self.wf:
             f_decl = ""
         res_lines = []
@@ -234,7 +237,8 @@ class KernelSource:
             if a in self.f_reg_atoms:
                 fx, fy, fz = "F%d.x" % a, "F%d.y" % a, "F%d.z" % a
             else:
-                fx, fy, fz = "fs[%d * 32 + lane]" % (3 * a), "fs[%d * 32 + lane]" % (3 * a + 1), "fs[%d * 32 + lane]" % (3 * a + 2)
+                ti = self.f_tile_index[a]
+                fx, fy, fz = "fs[%d * 32 + lane]" % (3 * ti), "fs[%d * 32 + lane]" % (3 * ti + 1), "fs[%d * 32 + lane]" % (3 * ti + 2)
             res_lines.append("{ const double dx = %s - fr[%d * 32], dy = %s - fr[%d * 32], dz = %s - fr[%d * 32];" % (fx, 3 * a, fy, 3 * a + 1, fz, 3 * a + 2))
             m = ["spec_tab[SPEC_ND + %d]" % (9 * a + q) for q in range(9)]
             res_lines.append("  const double t0 = fma(dz, %s, fma(dy, %s, dx * %s)), t1 = fma(dz, %s, fma(dy, %s, dx * %s)), t2 = fma(dz, %s, fma(dy, %s, dx * %s));"
@@ -247,14 +251,15 @@ class KernelSource:
             fout = "\n                ".join(
                 ("fo[%d * 32] = F%d.x; fo[%d * 32] = F%d.y; fo[%d * 32] = F%d.z;" % (3 * a, a, 3 * a + 1, a, 3 * a + 2, a)) if a in self.f_reg_atoms else
                 ("fo[%d * 32] = fs[%d * 32 + lane]; fo[%d * 32] = fs[%d * 32 + lane]; fo[%d * 32] = fs[%d * 32 + lane];"
-                 % (3 * a, 3 * a, 3 * a + 1, 3 * a + 1, 3 * a + 2, 3 * a + 2)) for a in range(N))
+                 % (3 * a, 3 * self.f_tile_index[a], 3 * a + 1, 3 * self.f_tile_index[a] + 1, 3 * a + 2, 3 * self.f_tile_index[a] + 2))
+                for a in range(N))
         if self.x_reg:
             x_load = "const double *xg = xt + (size_t)tile * TILE_D + lane;\n        " + "\n        ".join(
                 "const pm_d3 X%d = pm_d3{xg[%d * 32], xg[%d * 32], xg[%d * 32]};" % (a, 3 * a, 3 * a + 1, 3 * a + 2) for a in range(N))
         else:
             x_load = ""
         kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
-                                f_tile=0 if (self.f_reg or not self.wf) else 1, x_tile=0 if self.x_reg else 1, x_load=x_load)
+                                f_doubles=0 if (self.f_reg or not self.wf) else 3 * len(self.f_tile_atoms) * 32, x_tile=0 if self.x_reg else 1, x_load=x_load)
         return kernel if not with_header else _HEADER.format(N=N, ND=self.n_derived) + kernel
 
 
@@ -284,7 +289,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
     size_t off = ((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127;
-    const size_t per_warp = 128 + (size_t)TILE_D * sizeof(double) * ({f_tile} + {x_tile});
+    const size_t per_warp = 128 + ((size_t)TILE_D * {x_tile} + (size_t){f_doubles}) * sizeof(double);
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
     double *xs = reinterpret_cast<double *>(wbase + 128);
@@ -724,6 +729,15 @@ def choose_warps_grad(n_atoms, n_gout):
     return warps if warps >= 6 else 0
 
 
+def choose_warps_hybrid(n_atoms, n_tile_atoms):
+    """Warps per CTA when n_tile_atoms keep their forces in a packed shared tile and the rest in registers (255 registers: 8)."""
+    import math
+    table = ((257 * 16 + 127) // 128) * 128
+    per_warp = 128 + 3 * (n_atoms + n_tile_atoms) * 32 * 8
+    warps = min(F_REG_WARPS, int(math.floor((MAX_SMEM - table) / per_warp)))
+    return warps if warps >= F_REG_MIN_WARPS else None
+
+
 def choose_warps_energy(n_atoms):
     """Warps per CTA of the energy-only specialised kernel (coordinate tile only)."""
     import math
@@ -765,7 +779,7 @@ def eligible(n_atoms):
 def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     """
     One cubin with ``pm_ef_spec_kernel`` (energies, forces, residual) and, when enough warps fit, ``pm_e_spec_kernel``
-    (energies only) and the gradient kernels sharing ``spec_tab``.  Returns (image, warps, tiles_per_warp, warps_energy,
+    (energies only) and the gradient kernels sharing ``spec_tab``.  Returns (image, warps, atoms in the force tile, warps_energy,
     warps_grad) or None when neither shape of
     the E+F kernel suits the molecule.
 
@@ -797,24 +811,29 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
 
     mode = os.environ.get("PM_SPEC_FREG", "auto")
     w_tile = choose_warps(n_atoms)
-    if mode.startswith("top") and w_tile:   # experiment: only the k busiest atoms in registers, the others in the force tile
-        k = int(mode[3:])
+
+    def busiest(k):
         count = np.zeros(n_atoms)
         for arr in (bonds, angles, torsions):
             for a in np.asarray(arr).ravel():
                 count[int(a)] += 1
-        keep = [int(a) for a in np.argsort(-count, kind="stable")[:k]]
-        w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
+        return [int(a) for a in np.argsort(-count, kind="stable")[:k]]
+
+    if mode.startswith("top"):   # experiment: only the k busiest atoms in registers, the others in a packed force tile
+        keep = busiest(int(mode[3:]))
+        w = int(os.environ.get("PM_SPEC_WARPS", choose_warps_hybrid(n_atoms, n_atoms - len(keep)) or 0))
+        if w < 1:
+            return None
         image, _ = build(keep, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-        return image, w, 2, we, wg
+        return image, w, n_atoms - len(keep), we, wg
     w_reg = choose_warps_f_reg(n_atoms)
     if mode != "0" and w_reg:
         w = int(os.environ.get("PM_SPEC_WARPS", w_reg))
         image, report = build(True, w, int(os.environ.get("PM_SPEC_FENCE", f_reg_fence(n_atoms))))
         if 0 <= _spills(report, "pm_ef_spec_kernel") <= F_REG_MAX_SPILL or mode == "1":
-            return image, w, 1, we, wg
+            return image, w, 0, we, wg
     if w_tile:
         w = int(os.environ.get("PM_SPEC_WARPS", w_tile))
         image, _ = build(False, w, int(os.environ.get("PM_SPEC_FENCE", FENCE_EVERY)))
-        return image, w, 2, we, wg
+        return image, w, n_atoms, we, wg
     return None
