@@ -374,7 +374,8 @@ def run_ours(args):
     achieved_gbs = bytes_conf * S / t_kernel / 1e9
     info = topo.launch_info(True)
 
-    cpu = cpu_oracle_rate(mm, xb, args.term_type, args.cpu_seconds)
+    # the CPU port is timed beside the single-GPU run only (at N > 1 the driver's reference arm provides it)
+    cpu = cpu_oracle_rate(mm, xb, args.term_type, args.cpu_seconds) if world == 1 else None
 
     value = world * S * args.steps / t_dev
     line = {
