@@ -164,8 +164,9 @@ def test_fma_peak_probe():
     assert fl.value > 1e12  # a B200 sustains tens of TFLOP/s of DFMA
 
 
-@pytest.mark.parametrize("n_atoms", [5, 12, 15, 16])
-def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
+@pytest.mark.parametrize("n_atoms,shape", [(5, "auto"), (12, "auto"), (12, "0"), (12, "top6"), (15, "auto"), (16, "auto"), (16, "0"),
+                                           (20, "auto")])
+def test_specialized_kernel_equals_generic(n_atoms, shape, monkeypatch):
     """The topology-specialised kernel (csrc/specialize.py, installed automatically for small molecules) against the generic
     program-interpreting kernel on the same tiles: energies, residuals and forces to 1e-11 of the largest entry (a few of the 32805 random conformations are near-singular), several parameter vectors per
     call, a partial last tile, non-trivial metric; energy-only calls keep using the generic kernel."""
@@ -178,6 +179,9 @@ def test_specialized_kernel_equals_generic(n_atoms, monkeypatch):
     monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "0")
     generic = DeviceTopology(mm)
     monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "auto")
+    # shapes of the generated E+F kernel: forces in registers ("auto" picks it when it fits), in the shared force tile ("0"),
+    # or the busiest atoms in registers and the rest in a packed tile ("top6")
+    monkeypatch.setenv("PM_SPEC_FREG", shape)
     spec = DeviceTopology(mm)
     assert not generic.specialized and spec.specialized
     rng = np.random.default_rng(n_atoms)
