@@ -641,7 +641,8 @@ def generate(n_atoms, bonds, angles, torsions, tors_per, pairs, warps, f_in_regi
 # ---------------------------------------------------------------------------------------------------------------------
 MAX_SMEM = 227 * 1024
 FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fences -> 168 registers, no spills, fastest
-SYNC_EVERY = 0
+SYNC_EVERY = 18      # a CTA barrier every 18 blocks keeps the warps loosely in step, so that fetched instruction lines serve
+                     # several of them (measured on B200: aniline 0.630 -> 0.608 ms, 12 and 18 atoms -0.5 ... -2 %; 9 or 14: no gain)
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
 MAX_WARPS_ENERGY = 16   # 128 registers, no spills
