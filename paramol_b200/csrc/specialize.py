@@ -369,8 +369,9 @@ class GradKernelSource(KernelSource):
     of ``pm_grad`` through ``grad_perm``.  Deterministic, no atomics.
     """
 
-    def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=2):
-        KernelSource.__init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_grad_spec_kernel", False, fence_every, 0, True)
+    def __init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=2, sync_every=0):
+        KernelSource.__init__(self, n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_grad_spec_kernel", False, fence_every,
+                              sync_every, True)
         self.go_bond = 0
         self.go_angle = 2 * len(self.bonds)
         self.go_tors = self.go_angle + 2 * len(self.angles)
@@ -586,14 +587,21 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     __syncthreads();
     uint32_t parity = 0;
     const long warp_stride = (long)gridDim.x * n_warps;
-    for (long tile = (long)blockIdx.x * n_warps + warp; tile < n_tiles; tile += warp_stride) {{
+    // uniform trip count per CTA (the body may contain CTA barriers): a warp without a tile of its own repeats the last tile with
+    // zero coefficients, i.e. adds nothing
+    const long first_cta = (long)blockIdx.x * n_warps;
+    const long n_iter = first_cta < n_tiles ? (n_tiles - first_cta + warp_stride - 1) / warp_stride : 0;
+    for (long it = 0; it < n_iter; ++it) {{
+        long tile = first_cta + warp + it * warp_stride;
+        const bool live = tile < n_tiles;
+        if (!live) tile = n_tiles - 1;
         if (lane == 0) {{
             pm_fence_proxy_async();
             pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
             pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
         }}
         const long sconf = tile * 32 + lane;
-        const bool valid = sconf < n_conf;
+        const bool valid = live && sconf < n_conf;
         const double ae = (valid && coef_e != nullptr) ? coef_e[sconf] : 0.0;
         const double bf = (valid && coef_f != nullptr) ? coef_f[sconf] : 0.0;
         double *lc_base = ls + lane;
@@ -643,6 +651,7 @@ MAX_SMEM = 227 * 1024
 FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fences -> 168 registers, no spills, fastest
 SYNC_EVERY = 18      # a CTA barrier every 18 blocks keeps the warps loosely in step, so that fetched instruction lines serve
                      # several of them (measured on B200: aniline 0.630 -> 0.608 ms, 12 and 18 atoms -0.5 ... -2 %; 9 or 14: no gain)
+GRAD_SYNC_EVERY = 6   # measured on B200 (aniline gradient): 0 -> 1.04 ms, 4 -> 0.98, 6 -> 0.977, 12 -> 0.995, 18 -> 1.01
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
 MAX_WARPS_ENERGY = 16   # 128 registers, no spills
@@ -792,7 +801,8 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
     sync = int(os.environ.get("PM_SPEC_SYNC", SYNC_EVERY))
     we = choose_warps_energy(n_atoms) or 0
 
-    grad = GradKernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=FENCE_EVERY) \
+    grad = GradKernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, fence_every=FENCE_EVERY,
+                            sync_every=int(os.environ.get("PM_SPEC_GRAD_SYNC", GRAD_SYNC_EVERY))) \
         if os.environ.get("PM_SPEC_GRAD", "1") != "0" else None
     wg = choose_warps_grad(n_atoms, grad.n_gout) if grad is not None else 0
     if wg and os.environ.get("PM_SPEC_GRAD_WARPS"):
