@@ -651,6 +651,7 @@ MAX_SMEM = 227 * 1024
 FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fences -> 168 registers, no spills, fastest
 SYNC_EVERY = 18      # a CTA barrier every 18 blocks keeps the warps loosely in step, so that fetched instruction lines serve
                      # several of them (measured on B200: aniline 0.630 -> 0.608 ms, 12 and 18 atoms -0.5 ... -2 %; 9 or 14: no gain)
+ENERGY_SYNC_EVERY = 18   # aniline energy-only: 0 -> 0.293 ms, 12 -> 0.277, 18 -> 0.273
 GRAD_SYNC_EVERY = 6   # measured on B200 (aniline gradient): 0 -> 1.04 ms, 4 -> 0.98, 6 -> 0.977, 12 -> 0.995, 18 -> 1.01
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
@@ -814,8 +815,8 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
         src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
                        fence_every=fence, sync_every=sync)
         if we:
-            src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY, 0,
-                                with_forces=False).source(we, with_header=False)
+            src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY,
+                                int(os.environ.get("PM_SPEC_E_SYNC", ENERGY_SYNC_EVERY)), with_forces=False).source(we, with_header=False)
         if wg:
             src += grad.source(wg)
         return compile_image(src, want_report=True)
