@@ -38,6 +38,8 @@ class KernelSource:
         self.x_reg = bool(x_in_registers)
         self.fence_every = int(fence_every)
         self.sync_every = int(sync_every)
+        import os as _os
+        self.pair_sync_every = int(_os.environ.get("PM_SPEC_PSYNC", PAIR_SYNC_EVERY))
         self.wf = bool(with_forces)
         self._blocks = 0
         self.name = name
@@ -63,6 +65,11 @@ class KernelSource:
         loads of all later blocks to the top (which costs more registers than the interleaving gains)."""
         self.emit("}")
         self._blocks += 1
+        psync = self.pair_sync_every
+        if psync and self._blocks % psync == 0 and not (self.sync_every and self._blocks % self.sync_every == 0):
+            # the warps that share a scheduler (and its instruction buffer: warp, warp + 4, ...) wait for each other only
+            self.emit('asm volatile("bar.sync %0, %1;" :: "r"(1 + (warp & 3)), "r"(32 * ((n_warps + 3 - (warp & 3)) / 4)) : "memory");')
+            return
         if self.sync_every and self._blocks % self.sync_every == 0:
             # keeps the warps of the CTA within the same stretch of this (instruction-cache sized) straight-line code, so that a
             # fetched line serves all of them; the trip count of the tile loop is uniform per CTA for that reason
@@ -651,6 +658,7 @@ MAX_SMEM = 227 * 1024
 FENCE_EVERY = 2      # measured on B200 (aniline): 2 blocks between compiler fences -> 168 registers, no spills, fastest
 SYNC_EVERY = 18      # a CTA barrier every 18 blocks keeps the warps loosely in step, so that fetched instruction lines serve
                      # several of them (measured on B200: aniline 0.630 -> 0.608 ms, 12 and 18 atoms -0.5 ... -2 %; 9 or 14: no gain)
+PAIR_SYNC_EVERY = 0      # barriers between the warps of one scheduler only: measured slower (aniline 0.70 ms at 2-3, 0.64 at 6)
 ENERGY_SYNC_EVERY = 18   # aniline energy-only: 0 -> 0.293 ms, 12 -> 0.277, 18 -> 0.273
 GRAD_SYNC_EVERY = 6   # measured on B200 (aniline gradient): 0 -> 1.04 ms, 4 -> 0.98, 6 -> 0.977, 12 -> 0.995, 18 -> 1.01
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
