@@ -213,3 +213,26 @@ def test_specialized_kernel_equals_generic(n_atoms, shape, monkeypatch):
     ens = DeviceEnsemble(spec, X, F, np.zeros(n_conf))
     fres2 = ens.evaluate(spec.prepare(torch.from_numpy(rows).cuda()), with_forces=True, want_fres=True)[1]
     assert (fres2 - 2.0 * out[1][1]).abs().max().item() <= 1e-12 * out[1][1].abs().max().item()
+
+
+def test_empty_batches_are_refused_with_a_message(golden_dir):
+    """The reference never evaluates an empty ensemble (``system.py:324-354`` loops over ``ref_coordinates``); the C
+    ABI refuses zero-sized batches instead of launching an empty grid, and says why through ``pm_last_error``."""
+    import torch
+    from paramol_b200 import _lib
+    from paramol_b200.MM_engines.device import DeviceTopology
+    s, x0 = _system(golden_dir, "aniline")
+    topo = DeviceTopology(s)
+    L = _lib.lib()
+    slots = torch.from_numpy(topo.slots_from_system(s)[None, :]).cuda()
+    derived = topo.prepare(slots)
+    buf = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    h, p = topo._h, buf.data_ptr()
+    for what, rc in (("pm_eval", L.pm_eval(h, derived.data_ptr(), 1, p, p, 0, 1, p, p, None, None)),
+                     ("pm_eval", L.pm_eval(h, derived.data_ptr(), 0, p, p, 8, 1, p, p, None, None)),
+                     ("pm_pack_tiles", L.pm_pack_tiles(h, p, 0, p, None)),
+                     ("pm_reduce_objective", L.pm_reduce_objective(p, p, p, None, 0.0, 1, 0, p, p, None))):
+        assert rc != 0, what
+        with pytest.raises(_lib.B200Error, match="empty|no conformations"):
+            _lib.check(rc, what)
+    torch.cuda.synchronize()
