@@ -126,10 +126,27 @@ def config4(S=200_000):
     t0 = time.perf_counter()
     lls.fit_parameters_lls([system])
     torch.cuda.synchronize()
+    t_fit_first = time.perf_counter() - t0          # includes the one-time cuSOLVER / cuBLAS handle and workspace set-up
+    t0 = time.perf_counter()
+    lls.fit_parameters_lls([system])
+    torch.cuda.synchronize()
+    fit_reduction = lls.reduction
     t_fit = time.perf_counter() - t0
-    return dict(config=4, workload="LLS lig60: S=%d conformations x M=%d columns" % (S, M), design_matrix_s=t_design,
+    # the tall reduction alone, both ways, on the matrix the fit just used
+    red = {}
+    B = torch.randn(S, dtype=torch.float64, device="cuda")
+    for name, defect in (("cholesky_qr2", lls.CHOLESKY_QR_MAX_DEFECT), ("householder", 0.0)):
+        lls.CHOLESKY_QR_MAX_DEFECT = defect
+        lls._reduce_tall(A, B)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lls._reduce_tall(A, B)
+        torch.cuda.synchronize()
+        red[name + "_s"] = time.perf_counter() - t0
+        red[name + "_ran"] = lls.reduction
+    return dict(config=4, reduction_in_fit=fit_reduction, full_fit_first_call_s=t_fit_first, **red, workload="LLS lig60: S=%d conformations x M=%d columns" % (S, M), design_matrix_s=t_design,
                 design_GB_s=(S * 60 * 24 + S * M * 8) / t_design / 1e9, full_fit_s=t_fit,
-                note="full fit = design matrix + zero-parameter energy pass + weighting + device QR (library) + host lstsq on the "
+                note="full fit = design matrix + zero-parameter energy pass + weighting + device reduction to (R, Q^T b) (CholeskyQR2 or Householder, library calls) + host lstsq on the "
                      "stacked (M + reg) x M system")
 
 

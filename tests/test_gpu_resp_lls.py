@@ -154,7 +154,9 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
     from paramol_b200.Utils.synthetic import perturbed_conformations
     from paramol_b200.Utils.netcdf_lite import read_paramol_data
     X10 = read_paramol_data(os.path.join(golden_dir, "aniline_10_struct.nc"))[0]
-    for eq_opt in (False, True):
+    # the tall problem is reduced by CholeskyQR2 when the design matrix allows it and by Householder QR otherwise (forced
+    # in the third case): the fit must not depend on which one ran
+    for eq_opt, force_householder in ((False, False), (True, False), (True, True)):
         engine = B200Engine(True, **kwargs_dict)
         system = ParaMolSystem("aniline", engine, 14)
         system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
@@ -196,10 +198,36 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
         Bfull = np.concatenate([Bw, alpha * init])
         want = np.linalg.lstsq(Afull, Bfull, rcond=None)[0] / sc
         assert np.allclose(np.asarray(ps.optimizable_parameters_values), x_before)
+        if force_householder:
+            lls.CHOLESKY_QR_MAX_DEFECT = 0.0
         fitted = lls.fit_parameters_lls([system])
         got = lls._parameters
-        assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max(), np.abs(got - want).max()
+        assert lls.reduction in ("cholesky_qr2", "householder") and (lls.reduction == "householder" or not force_householder)
+        assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max(), (lls.reduction, np.abs(got - want).max())
         assert len(fitted) == len(x_before)
+
+
+def test_lls_reduction_cholesky_qr2_and_householder_fallback():
+    """``LinearLeastSquare._reduce_tall``: (R, Q^T b) must reproduce the least-squares problem, || A x - b ||^2 =
+    || R x - Q^T b ||^2 + const, i.e. R^T R = A^T A and R^T (Q^T b) = A^T b; a rank-deficient matrix (duplicated
+    column) must fall back to the Householder factorisation."""
+    import torch
+    from paramol_b200.MM_engines.least_square import LinearLeastSquare
+    lls = LinearLeastSquare.__new__(LinearLeastSquare)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn((5000, 40), dtype=torch.float64, device="cuda", generator=g)
+    A[:, 7] = A[:, 6] * (1.0 + 1e-4) + 1e-4 * A[:, 7]          # a nearly collinear pair, as the eq-bracketing columns are
+    b = torch.randn(5000, dtype=torch.float64, device="cuda", generator=g)
+    for case in ("well", "deficient"):
+        if case == "deficient":
+            A = torch.cat([A, A[:, 3:4]], dim=1)
+        R, qtb = lls._reduce_tall(A, b)
+        assert lls.reduction == ("cholesky_qr2" if case == "well" else "householder"), (case, lls.reduction)
+        G, rhs = (A.T @ A).cpu().numpy(), (A.T @ b).cpu().numpy()
+        R, qtb = R.cpu().numpy(), qtb.cpu().numpy()
+        assert np.abs(R.T @ R - G).max() <= 1e-11 * np.abs(G).max()
+        assert np.abs(R.T @ qtb - rhs).max() <= 1e-10 * np.abs(rhs).max()
+        assert np.abs(np.tril(R, -1)).max() <= 1e-12 * np.abs(R).max()
 
 
 @pytest.mark.parametrize("n_atoms,n_grid,n_conf", [(1, 5, 3), (3, 33, 4), (14, 600, 3), (31, 64, 5), (59, 77, 4), (60, 513, 3),
