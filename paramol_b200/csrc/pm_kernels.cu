@@ -644,6 +644,8 @@ __global__ void pm_reduce_stage1(const double *__restrict__ emm, const double *_
     const long lo = (long)blockIdx.x * chunk;
     long hi = lo + chunk;
     if (hi > n_conf) hi = n_conf;
+    // unrolled so that the loads of four iterations are in flight together (the sums keep their order)
+#pragma unroll 4
     for (long s = lo + threadIdx.x; s < hi; s += blockDim.x) {
         const double d = (eref ? eref[s] : 0.0) - e[s] - d_shift;
         const double ws = w ? w[s] : 1.0;
