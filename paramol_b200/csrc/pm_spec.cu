@@ -70,7 +70,18 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     st->tab_dev = (double *)tab;
     st->warps = warps;
     const size_t tile = (size_t)3 * h->prog.n_atoms * 32 * sizeof(double);
-    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps * (128 + tile + (size_t)3 * n_force_tile_atoms * 32 * sizeof(double));
+    // optional: extra tiles per warp of the E+F kernel (the reference-force buffer of the prefetching variant)
+    int ef_info[2] = {0, 0};
+    {
+        void *info = nullptr;
+        size_t info_bytes = 0;
+        if (cudaLibraryGetGlobal(&info, &info_bytes, st->lib, "spec_ef_info") != cudaSuccess || info_bytes != sizeof(ef_info) ||
+            cudaMemcpy(ef_info, info, sizeof(ef_info), cudaMemcpyDeviceToHost) != cudaSuccess || ef_info[0] < 0 || ef_info[0] > 1)
+            ef_info[0] = 0;
+        cudaGetLastError();
+    }
+    st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) +
+               (size_t)warps * (128 + tile * (size_t)(1 + ef_info[0]) + (size_t)3 * n_force_tile_atoms * 32 * sizeof(double));
     if (st->smem > (size_t)h->max_smem ||
         cudaFuncSetAttribute((const void *)st->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess) {
         cudaGetLastError();

@@ -41,6 +41,9 @@ class KernelSource:
         import os as _os
         self.pair_sync_every = int(_os.environ.get("PM_SPEC_PSYNC", PAIR_SYNC_EVERY))
         self.wf = bool(with_forces)
+        # second shared tile per warp: the reference forces of the tile arrive by bulk copy while the body runs, and the next
+        # tile's coordinates are requested as soon as the body has read the current ones (set by image_for when it fits)
+        self.prefetch = 0
         self._blocks = 0
         self.name = name
         self.off_bond = 0
@@ -265,8 +268,13 @@ class KernelSource:
                 "const pm_d3 X%d = pm_d3{xg[%d * 32], xg[%d * 32], xg[%d * 32]};" % (a, 3 * a, 3 * a + 1, 3 * a + 2) for a in range(N))
         else:
             x_load = ""
-        kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout,
+        pf = 1 if (self.prefetch and self.wf and not self.x_reg) else 0
+        pfr = 1 if (pf and self.prefetch == 2) else 0
+        kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout, PF=pf, PFR=pfr,
                                 f_doubles=0 if (self.f_reg or not self.wf) else 3 * len(self.f_tile_atoms) * 32, x_tile=0 if self.x_reg else 1, x_load=x_load)
+        if self.name == "pm_ef_spec_kernel":
+            # extra TILE_D buffers per warp of the E+F kernel, read by pm_set_specialized to size the shared memory
+            kernel = "__constant__ int spec_ef_info[2] = {%d, 0};\n" % pfr + kernel
         return kernel if not with_header else _HEADER.format(N=N, ND=self.n_derived) + kernel
 
 
@@ -296,36 +304,63 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
     size_t off = ((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127;
-    const size_t per_warp = 128 + ((size_t)TILE_D * {x_tile} + (size_t){f_doubles}) * sizeof(double);
+    const size_t per_warp = 128 + ((size_t)TILE_D * ({x_tile} + {PFR}) + (size_t){f_doubles}) * sizeof(double);
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
+    uint64_t *bar_r = bar + 1;
     double *xs = reinterpret_cast<double *>(wbase + 128);
     double *fs = xs + ({x_tile} ? TILE_D : 0);
+    double *rs = fs + {f_doubles};
     (void)fs;
+    (void)rs;
     for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = acos_tab[i];
     if (lane == 0) {{
         pm_mbar_init(bar, 1);
+        pm_mbar_init(bar_r, 1);
         pm_fence_mbar_init();
     }}
     __syncthreads();
-    uint32_t parity = 0;
+    uint32_t parity = 0, parity_r = 0;
     const long warp_stride = (long)gridDim.x * n_warps;
     // uniform trip count per CTA (the body may contain CTA barriers): a warp without a tile of its own repeats the last tile
     // of the problem and stores nothing
     const long first_cta = (long)blockIdx.x * n_warps;
     const long n_iter = first_cta < n_tiles ? (n_tiles - first_cta + warp_stride - 1) / warp_stride : 0;
+    if ({PF} && n_iter > 0 && lane == 0) {{   // coordinates of the first tile
+        long tile0 = first_cta + warp;
+        if (tile0 >= n_tiles) tile0 = n_tiles - 1;
+        pm_fence_proxy_async();
+        pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
+        pm_bulk_g2s(xs, xt + (size_t)tile0 * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+    }}
     for (long it = 0; it < n_iter; ++it) {{
         long tile = first_cta + warp + it * warp_stride;
         const bool live = tile < n_tiles;
         if (!live) tile = n_tiles - 1;
         if (lane == 0) {{
-            if ({x_tile}) {{
-                pm_fence_proxy_async();
-                pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
-                pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+            if ({PF}) {{
+                // reference forces of this tile into the second buffer while the body runs (the buffer was last read in the
+                // previous iteration's epilogue, before its closing __syncwarp)
+                if ({PFR} && fres != nullptr) {{
+                    pm_fence_proxy_async();
+                    pm_mbar_expect_tx(bar_r, (uint32_t)(TILE_D * sizeof(double)));
+                    pm_bulk_g2s(rs, fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar_r);
+                }} else if (fres != nullptr) {{
+                    pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                }}
+                if (tile + warp_stride < n_tiles) {{
+                    pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                    if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                }}
+            }} else {{
+                if ({x_tile}) {{
+                    pm_fence_proxy_async();
+                    pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
+                    pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+                }}
+                if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                if (tile + warp_stride < n_tiles) pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
             }}
-            if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
-            if (tile + warp_stride < n_tiles) pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
         }}
         {x_load}
         {f_decl}
@@ -341,11 +376,25 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
         {{
             {body}
         }}
+        if ({PF}) {{
+            __syncwarp();   // every lane has read its coordinates: the next tile's may overwrite them during the epilogue
+            if (lane == 0 && it + 1 < n_iter) {{
+                long next = first_cta + warp + (it + 1) * warp_stride;
+                if (next >= n_tiles) next = n_tiles - 1;
+                pm_fence_proxy_async();
+                pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
+                pm_bulk_g2s(xs, xt + (size_t)next * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
+            }}
+        }}
         const long sconf = tile * 32 + lane;
         const double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
         double res = 0.0;
         if (fres != nullptr) {{
-            const double *fr = fref_t + (size_t)tile * TILE_D + lane;
+            if ({PFR}) {{
+                pm_mbar_wait(bar_r, parity_r);
+                parity_r ^= 1;
+            }}
+            const double *fr = {PFR} ? rs + lane : fref_t + (size_t)tile * TILE_D + lane;
             {{
                 {res}
             }}
@@ -664,6 +713,10 @@ GRAD_SYNC_EVERY = 6   # measured on B200 (aniline gradient): 0 -> 1.04 ms, 4 -> 
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
 MAX_WARPS_ENERGY = 16   # 128 registers, no spills
+PREFETCH = 0   # 0: coordinates requested at the top of the tile loop (L2-prefetched one tile ahead); 1: next tile's coordinates
+               # requested right after the body; 2: also the reference forces by bulk copy into a second tile per warp.
+               # Measured on B200 (aniline, 2^20): 0 -> 0.619 ms, 1 -> 0.649 ms, 2 -> 0.636 ms: the waits they remove are
+               # already covered by the other warp of the scheduler, the extra warp barrier and 86 KB of shared memory are not
 
 
 def choose_warps(n_atoms):
@@ -820,8 +873,13 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
         grad.fence_every = int(os.environ["PM_SPEC_GRAD_FENCE"])
 
     def build(f_reg, w, fence):
-        src = generate(n_atoms, bonds, angles, torsions, tors_per, pairs, w, f_in_registers=f_reg, x_in_registers=False,
-                       fence_every=fence, sync_every=sync)
+        ks = KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, f_reg, "pm_ef_spec_kernel", False, fence, sync)
+        tile = 3 * n_atoms * 32 * 8
+        table = ((257 * 16 + 127) // 128) * 128
+        ks.prefetch = int(os.environ.get("PM_SPEC_PREFETCH", PREFETCH))
+        if ks.prefetch == 2 and table + w * (128 + 2 * tile + 3 * len(ks.f_tile_atoms) * 32 * 8) > MAX_SMEM:
+            ks.prefetch = 1
+        src = ks.source(w)
         if we:
             src += KernelSource(n_atoms, bonds, angles, torsions, tors_per, pairs, False, "pm_e_spec_kernel", False, FENCE_EVERY,
                                 int(os.environ.get("PM_SPEC_E_SYNC", ENERGY_SYNC_EVERY)), with_forces=False).source(we, with_header=False)
