@@ -270,7 +270,9 @@ class KernelSource:
             x_load = ""
         pf = 1 if (self.prefetch and self.wf and not self.x_reg) else 0
         pfr = 1 if (pf and self.prefetch == 2) else 0
-        kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout, PF=pf, PFR=pfr,
+        import os as _os
+        topsync = 1 if (self.sync_every and int(_os.environ.get("PM_SPEC_TOPSYNC", TOP_SYNC))) else 0
+        kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout, PF=pf, PFR=pfr, TOPSYNC=topsync,
                                 f_doubles=0 if (self.f_reg or not self.wf) else 3 * len(self.f_tile_atoms) * 32, x_tile=0 if self.x_reg else 1, x_load=x_load)
         if self.name == "pm_ef_spec_kernel":
             # extra TILE_D buffers per warp of the E+F kernel, read by pm_set_specialized to size the shared memory
@@ -369,6 +371,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
             parity ^= 1;
         }}
         __syncwarp();
+        if ({TOPSYNC}) __syncthreads();   // all warps enter the body together (uniform trip count)
         const double *xc_base = xs + lane;
         double *fc_base = fs + lane;
         (void)fc_base;
@@ -713,6 +716,8 @@ GRAD_SYNC_EVERY = 6   # measured on B200 (aniline gradient): 0 -> 1.04 ms, 4 -> 
 MIN_WARPS = 9        # below that the team-mode generic kernel wins (24 atoms: 6 warps -> 0.95x)
 MAX_WARPS = 10
 MAX_WARPS_ENERGY = 16   # 128 registers, no spills
+TOP_SYNC = 0   # CTA barrier at the top of every tile iteration: measured slower (aniline 0.617 -> 0.652 ms: all warps then wait for
+               # their coordinate tiles at the same time)
 PREFETCH = 0   # 0: coordinates requested at the top of the tile loop (L2-prefetched one tile ahead); 1: next tile's coordinates
                # requested right after the body; 2: also the reference forces by bulk copy into a second tile per warp.
                # Measured on B200 (aniline, 2^20): 0 -> 0.619 ms, 1 -> 0.649 ms, 2 -> 0.636 ms: the waits they remove are
