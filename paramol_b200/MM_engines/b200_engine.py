@@ -246,10 +246,9 @@ class B200Engine:
     @staticmethod
     def wrap_phase(phase):
         """phase % (sign(phase) * 2 pi), with 2 pi for phase == 0 (reference :576-584); works on arrays."""
-        phase = np.asarray(phase, dtype=np.float64)
-        div = np.sign(phase) * 2.0 * np.pi
-        div = np.where(div == 0.0, 2.0 * np.pi, div)
-        return np.mod(phase, div)
+        # a modulus that carries the sign of the dividend is the C fmod: bit-identical to np.mod(phase, sign(phase) * 2 pi)
+        # (np.mod is fmod plus a correction that only fires when the signs of divisor and remainder differ), in one pass
+        return np.fmod(np.asarray(phase, dtype=np.float64), 2.0 * np.pi)
 
     def set_periodic_torsion_force_parameters(self, ff_torsion_terms):
         self._slots_cache = None
