@@ -441,6 +441,15 @@ class B200Engine:
         store_rows = np.atleast_2d(np.asarray(store_rows, dtype=np.float64))
         n_vec = store_rows.shape[0]
         base = self.current_slots() if base_slots is None else np.asarray(base_slots, dtype=np.float64)
+        if n_vec == 1 and plan["branch"] not in ("A", "B"):
+            # the optimiser's f(x): one row and no nonbonded rebuild -- 1-D scatters (same values, half the indexing cost)
+            row = store_rows[0]
+            slots = np.array(base, dtype=np.float64).reshape(-1)
+            if len(plan["dst"]):
+                slots[plan["dst"]] = row[plan["src"]]
+            if len(plan["ph_dst"]):
+                slots[plan["ph_dst"]] = self.wrap_phase(row[plan["ph_src"]])
+            return slots[None, :]
         slots = np.repeat(base[None, :], n_vec, axis=0)
         if len(plan["dst"]):
             slots[:, plan["dst"]] = store_rows[:, plan["src"]]
@@ -516,11 +525,13 @@ class B200Engine:
     def load_slots(self, slots_row):
         """Writes one slots row back into the MM system arrays (keeps ``self.system`` in step with the fast path)."""
         s = self.system
+        row = np.array(slots_row, dtype=np.float64).reshape(-1)   # one private copy: source of the writes and the new cache
         o = 0
         for arr in (s.bond_par, s.angle_par, s.torsion_par, s.particle_par, s.exception_par):
-            arr[...] = np.asarray(slots_row[o:o + arr.size]).reshape(arr.shape)
-            o += arr.size
-        self._slots_cache = np.array(slots_row, dtype=np.float64).reshape(-1)
+            n = arr.size
+            arr[...] = row[o:o + n].reshape(arr.shape)
+            o += n
+        self._slots_cache = row
 
     # ------------------------------------------------------------------------------------------
     #                                       PRIVATE METHODS
