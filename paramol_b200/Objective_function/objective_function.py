@@ -325,6 +325,28 @@ class ObjectiveFunction:
         for hp, scale in zip(per_system, w_scales):
             if hp is not None and scale != 1.0:
                 hp[:, 1:5] *= scale
+        if n_vec == 1:
+            # the optimiser's f(x): the same expressions on Python floats (identical IEEE operations in the same order,
+            # without a dozen one-element numpy calls)
+            rows = [None if hp is None else hp[0].tolist() for hp in per_system]
+            value = 0.0
+            if e_prop is not None:
+                val = 0.0
+                for k, system in enumerate(e_prop.systems):
+                    r = rows[self.systems.index(system)]
+                    m = r[0] / r[5]
+                    val += (r[2] - 2.0 * m * r[1] + m * m * r[3]) / float(e_prop.variance[k])
+                if set_values:
+                    e_prop.value = val
+                value += e_prop.weight * val
+            if f_prop is not None:
+                val = 0.0
+                for system in f_prop.systems:
+                    val += rows[self.systems.index(system)][4] / (3 * system.n_atoms)
+                if set_values:
+                    f_prop.value = val
+                value += f_prop.weight * val
+            return np.array([value])
         if e_prop is not None:
             vals = np.zeros(n_vec)
             for system in e_prop.systems:
