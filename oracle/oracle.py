@@ -379,3 +379,82 @@ def resp_sums(x, grid, v):
     dp = ctypes.POINTER(ctypes.c_double)
     lib().pmo_resp_sums(N, xp, G, gp, vp, inv_r.ctypes.data_as(dp), A.ctypes.data_as(dp), B.ctypes.data_as(dp))
     return inv_r, A, B
+
+
+# --------------------------------------------------------------------------------------------------
+# LLS (MM_engines/least_square.py) -- numpy restatement, PINNED by tests/golden/lls_reference_fixtures.npz, which
+# tests/golden/make_lls_fixtures.py produced by running the reference's own least_square.py (tests/test_lls_reference_fixtures.py)
+# --------------------------------------------------------------------------------------------------
+def lls_design_matrix(coords, parameter_space, alpha_bond=0.05):
+    """LinearLeastSquare._calculate_a, least_square.py:469-649 (vectorised over conformations).
+    Returns (A centred [S, M], p0 [M], keys, init [M], symmetry tags)."""
+    X = np.asarray(coords, dtype=np.float64)
+    cols, p0, keys, init, symm = [], [], [], [], []
+    spec = {"bond_k": ("bond_eq", 0), "angle_k": ("angle_eq", 1), "torsion_k": ("torsion_phase", 2)}
+    for parameter in parameter_space.optimizable_parameters:
+        t = parameter.ff_term
+        if parameter.param_key in spec:
+            partner_key, kind = spec[parameter.param_key]
+            atoms = (list(t.atoms) + [0, 0, 0])[:4]
+            q = internal_coordinates(X, [kind], [atoms])[:, 0]
+            partner = t.parameters[partner_key]
+            if partner.optimize:
+                if kind == 0:      # :517-518
+                    centres = [partner.value * (1 - alpha_bond), partner.value * (1 + alpha_bond)]
+                elif kind == 1:    # :566-567
+                    centres = [q.min(), q.max()]
+                else:              # :612-613
+                    centres = [-np.pi / 4, np.pi / 4]
+                tags = ["_x", "_y"]
+            else:
+                centres, tags = [partner.value], [""]
+            for c, tag in zip(centres, tags):
+                if kind == 2:
+                    cols.append(1 + np.cos(t.parameters["torsion_periodicity"].value * q - c))
+                else:
+                    cols.append(0.5 * (q - c) * (q - c))
+                p0.append(c)
+                keys.append(parameter.param_key)
+                init.append(parameter.value)
+                symm.append(parameter.symmetry_group + tag)
+        elif parameter.param_key not in ("torsion_phase", "bond_eq", "angle_eq"):
+            raise NotImplementedError(parameter.param_key)
+    A = np.stack(cols, axis=1)
+    A = A - A.mean(axis=0)   # :640-642
+    return A, np.asarray(p0), keys, np.asarray(init), symm
+
+
+def lls_symmetry_rows(symm, n_parameters):
+    """LinearLeastSquare._add_symmetries, least_square.py:293-337."""
+    rows, covered = [], []
+    for i, si in enumerate(symm):
+        if si in covered or si in ("X_x", "X_y", "X"):
+            continue
+        for j in range(i + 1, len(symm)):
+            if symm[j] == si:
+                r = np.zeros(n_parameters)
+                r[i], r[j] = 1.0, -1.0
+                rows.append(r)
+        covered.append(si)
+    return np.asarray(rows).reshape(-1, n_parameters)
+
+
+def lls_fit(A, B, weights, ref_energies, scaling_constants, prior_widths, init, symm, include_regularization=True,
+            scaling_factor=1.0):
+    """fit_parameters_lls, least_square.py:99-140: row weighting, preconditioning, regularisation rows (:253-291), symmetry rows,
+    np.linalg.lstsq on the stacked system, scaling reverted.  Returns the parameter vector (``_parameters``)."""
+    sc = np.asarray(scaling_constants, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64) * np.ones(A.shape[0])
+    var = np.var(ref_energies)
+    Aw = A * np.sqrt(w)[:, None] / np.sqrt(var) / sc[None, :]
+    Bw = B * np.sqrt(w) / np.sqrt(var)
+    rows, rhs = [Aw], [Bw]
+    if include_regularization:
+        alpha = scaling_factor / sc
+        rows.append(np.identity(len(sc)) / np.asarray(prior_widths)[None, :] * alpha)
+        rhs.append(alpha * np.asarray(init))
+    srows = lls_symmetry_rows(symm, len(sc))
+    if len(srows):
+        rows.append(srows)
+        rhs.append(np.zeros(len(srows)))
+    return np.linalg.lstsq(np.vstack(rows), np.concatenate(rhs), rcond=None)[0] / sc

@@ -1,12 +1,12 @@
 """
 Full-size checks (``-m gpu``): BASELINE.json config 2 (aniline, 2^20 perturbed conformations) through size-independent
-properties, plus an oracle spot check on a slice:
+properties, plus the oracle on every conformation:
   * Newton's third law: the MM forces of every conformation sum to zero;
   * rigid-body invariance: rotating + translating every conformation leaves the energies unchanged and rotates the forces;
   * shard additivity: the partial rows of three uneven shards add up to the row of the whole set, and the assembled
     objective is the same (what the multi-GPU allreduce relies on);
   * determinism: two evaluations are bitwise identical;
-  * the first 2048 conformations against the CPU oracle (1e-9).
+  * ALL 2^20 conformations against the CPU oracle (energies and forces 1e-9, residual sums 1e-8).
 """
 import os
 
@@ -46,11 +46,18 @@ def test_config2_full_size_properties(golden_dir):
     # determinism
     emm2, fres2, _ = ens.evaluate(derived)
     assert torch.equal(emm, emm2) and torch.equal(fres, fres2)
-    # oracle on a slice
-    n_chk = 2048
-    E_o, F_o = O.energies_forces(mm, X[:n_chk].cpu().numpy(), n_threads=4)
-    assert np.abs(emm[0, :n_chk].cpu().numpy() - E_o).max() < 1e-9 * np.abs(E_o).max()
-    assert np.abs(F[:n_chk].cpu().numpy() - F_o).max() < 1e-9 * np.abs(F_o).max()
+    # EVERY conformation against the CPU oracle (the C port does millions of aniline conformations per second), in slabs so
+    # that the host copies stay small; the residual sums against the oracle's forces as well
+    slab = 1 << 17
+    n_thr = max(1, min(O.max_threads(), 32))
+    Fref_h_metric = np.tile(np.eye(3).ravel(), (14, 1))
+    for lo in range(0, S_FULL, slab):
+        hi = min(S_FULL, lo + slab)
+        E_o, F_o = O.energies_forces(mm, X[lo:hi].cpu().numpy(), n_threads=n_thr)
+        assert np.abs(emm[0, lo:hi].cpu().numpy() - E_o).max() < 1e-9 * np.abs(E_o).max(), lo
+        assert np.abs(F[lo:hi].cpu().numpy() - F_o).max() < 1e-9 * np.abs(F_o).max(), lo
+        res_o = O.force_residuals(F_o, Fref[lo:hi].cpu().numpy(), Fref_h_metric.reshape(14, 3, 3), n_threads=n_thr)
+        assert np.abs(fres[0, lo:hi].cpu().numpy() - res_o).max() <= 1e-8 * np.abs(res_o).max(), lo
     # shard additivity of the partial rows
     d_shift = float(Eref.mean())
     whole = ens.reduce(emm, fres, d_shift=d_shift).cpu().numpy()[0]

@@ -24,6 +24,9 @@ def _close_ef(a, b):
 
 def _system(golden_dir, name):
     from paramol_b200.Utils.amber import system_from_prmtop, read_inpcrd
+    if name.startswith("lig"):   # synthetic drug-like ligands of BASELINE.json configs 3-5 (8 lanes per conformation at 50-60 atoms)
+        from paramol_b200.Utils.synthetic import make_ligand
+        return make_ligand(int(name[3:]))
     return (system_from_prmtop(os.path.join(golden_dir, name + ".prmtop")),
             read_inpcrd(os.path.join(golden_dir, name + ".inpcrd")))
 
@@ -76,7 +79,8 @@ def test_aniline_goldens_through_cuda(aniline_system, aniline_data, goldens):
     assert np.abs(r["emm_energy_only_kernel"][0] - gold_e).max() < 1e-7
 
 
-@pytest.mark.parametrize("name,n_conf", [("aniline", 1000), ("caffeine", 257), ("norfloxacin", 96), ("ethane", 33)])
+@pytest.mark.parametrize("name,n_conf", [("aniline", 1000), ("caffeine", 257), ("norfloxacin", 96), ("ethane", 33),
+                                         ("lig50", 203), ("lig60", 131), ("lig33", 77), ("lig45", 64)])
 def test_ef_parity_vs_oracle(golden_dir, name, n_conf):
     from oracle import oracle as O
     s, x0 = _system(golden_dir, name)
@@ -95,6 +99,57 @@ def test_ef_parity_vs_oracle(golden_dir, name, n_conf):
     d = F - Fref
     res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
     assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
+
+
+def _system_with_slots(s, row):
+    sp = s.copy()
+    o = 0
+    for arr in (sp.bond_par, sp.angle_par, sp.torsion_par, sp.particle_par, sp.exception_par):
+        arr[...] = row[o:o + arr.size].reshape(arr.shape)
+        o += arr.size
+    return sp
+
+
+def test_config3_shape_batched_vectors_vs_oracle():
+    """BASELINE.json config 3 in shape (60-atom ligand, a batch of perturbed parameter vectors per launch; here 9 vectors x 4100
+    conformations, a ragged last tile): per-vector energies, forces and residual sums against the oracle evaluated with that
+    vector's parameters.  This is the 8-lanes-per-conformation path with the parameter-vector loop inside the launch."""
+    import torch
+    from oracle import oracle as O
+    from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
+    from paramol_b200.Utils.synthetic import make_ligand
+    s, x0 = make_ligand(60)
+    rng = np.random.default_rng(60)
+    n_conf, n_vec = 4100, 9
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    E0, F0 = O.energies_forces(s, X, n_threads=4)
+    Eref = E0 + rng.normal(0, 5, n_conf)
+    Fref = F0 + rng.normal(0, 50, F0.shape)
+    metric = np.tile(np.eye(3).ravel(), (s.n_atoms, 1)) * rng.uniform(0.5, 2.0, (s.n_atoms, 1))
+    topo = DeviceTopology(s)
+    topo.set_force_metric(metric)
+    base = topo.slots_from_system(s)
+    slots = base[None] * (1.0 + 0.02 * rng.uniform(-1, 1, (n_vec, len(base))))
+    slots[0] = base
+    ens = DeviceEnsemble(topo, X, Fref, Eref)
+    derived = topo.prepare(torch.from_numpy(slots).cuda())
+    emm, fres, fmm = ens.evaluate(derived, want_fmm=True)
+    emm_h, fres_h = emm.cpu().numpy(), fres.cpu().numpy()
+    Fmm = ens.forces_from_tiles(fmm).cpu().numpy()
+    d_shift = float(np.mean(Eref))
+    partials = ens.reduce(emm, fres, d_shift=d_shift).cpu().numpy()
+    e_only = ens.evaluate(derived, with_forces=False)[0].cpu().numpy()
+    for p in range(n_vec):
+        E, F = O.energies_forces(_system_with_slots(s, slots[p]), X, n_threads=4)
+        assert np.abs(emm_h[p] - E).max() < 1e-9 * max(1.0, np.abs(E).max()), p
+        assert np.abs(e_only[p] - E).max() < 1e-9 * max(1.0, np.abs(E).max()), p
+        assert np.abs(Fmm[p] - F).max() < 1e-9 * np.abs(F).max(), p
+        d = F - Fref
+        res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
+        assert np.abs(fres_h[p] - res).max() <= OBJ_RTOL * np.abs(res).max(), p
+        dd = (Eref - E) - d_shift
+        want = np.array([dd.sum(), dd.sum(), (dd * dd).sum(), n_conf, res.sum(), n_conf, 0, 0])
+        assert np.all(np.abs(partials[p] - want) <= 1e-9 * np.maximum(1.0, np.abs(want))), (p, partials[p], want)
 
 
 def test_batched_parameter_vectors_and_reduction(golden_dir):

@@ -4,8 +4,9 @@ GPU parity of the two linear fitting paths (run with ``-m gpu``).
 RESP: the reference's own test body (ParaMol/Tests/Tasks/test_resp.py:78-151) -- explicit solver without restraint,
 with L2 (a = 0.5) and with hyperbolic (a = 0.001, b = 0.1) restraints -- against the three golden charge vectors
 (tolerance 1e-4 as in the reference), plus the assembled sums against the CPU oracle on seeded multi-conformation input.
-LLS: the reference has no test for this path ("parity unpinned" at the reference level); the device design matrix and the
-fitted parameters are compared with a numpy restatement of ParaMol/MM_engines/least_square.py.
+LLS: the reference has no test for this path, so the device path is compared (a) with fixtures produced by running the reference's
+own ParaMol/MM_engines/least_square.py in the build container (tests/golden/make_lls_fixtures.py) and (b) at larger sizes with the
+oracle's numpy restatement of that file, which the same fixtures pin (tests/test_lls_reference_fixtures.py).
 """
 import os
 
@@ -115,37 +116,10 @@ def test_resp_sums_potential_and_objective_vs_oracle(golden_dir):
 
 
 def _numpy_lls(system, parameter_space, weights, include_reg, a_reg, alpha_bond=0.05):
-    """numpy restatement of LinearLeastSquare.fit_parameters_lls (least_square.py:68-146) with the oracle's geometry."""
+    """The oracle's restatement of LinearLeastSquare._calculate_a (least_square.py:469-649), which tests/test_lls_reference_fixtures.py
+    pins to fixtures produced by the reference's own code."""
     from oracle import oracle as O
-    X = np.asarray(system.ref_coordinates)
-    cols, p0, keys, init, symm = [], [], [], [], []
-    for parameter in parameter_space.optimizable_parameters:
-        t = parameter.ff_term
-        if parameter.param_key == "bond_k":
-            q = O.internal_coordinates(X, [0], [t.atoms + [0, 0]])[:, 0]
-            eq = t.parameters["bond_eq"]
-            centres = [eq.value * (1 - alpha_bond), eq.value * (1 + alpha_bond)] if eq.optimize else [eq.value]
-            for tag, c in zip(("_x", "_y"), centres):
-                cols.append(0.5 * (q - c) ** 2); p0.append(c); keys.append("bond_k"); init.append(parameter.value)
-                symm.append(parameter.symmetry_group + (tag if eq.optimize else ""))
-        elif parameter.param_key == "angle_k":
-            q = O.internal_coordinates(X, [1], [t.atoms + [0]])[:, 0]
-            eq = t.parameters["angle_eq"]
-            centres = [q.min(), q.max()] if eq.optimize else [eq.value]
-            for tag, c in zip(("_x", "_y"), centres):
-                cols.append(0.5 * (q - c) ** 2); p0.append(c); keys.append("angle_k"); init.append(parameter.value)
-                symm.append(parameter.symmetry_group + (tag if eq.optimize else ""))
-        elif parameter.param_key == "torsion_k":
-            q = O.internal_coordinates(X, [2], [t.atoms])[:, 0]
-            ph = t.parameters["torsion_phase"]
-            n = t.parameters["torsion_periodicity"].value
-            centres = [-np.pi / 4, np.pi / 4] if ph.optimize else [ph.value]
-            for tag, c in zip(("_x", "_y"), centres):
-                cols.append(1 + np.cos(n * q - c)); p0.append(c); keys.append("torsion_k"); init.append(parameter.value)
-                symm.append(parameter.symmetry_group + (tag if ph.optimize else ""))
-    A = np.stack(cols, axis=1)
-    A = A - A.mean(axis=0)
-    return A, np.asarray(p0), keys, np.asarray(init), symm
+    return O.lls_design_matrix(system.ref_coordinates, parameter_space, alpha_bond)
 
 
 def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
@@ -207,6 +181,103 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
         assert len(fitted) == len(x_before)
 
 
+@pytest.mark.parametrize("name", ["a10_eq_uniform", "a600_keq_uniform", "a600_eq_uniform", "a600_eq_boltzmann"])
+def test_lls_matches_reference_fixtures(golden_dir, name):
+    """The device LLS against fixtures produced by RUNNING the reference's own ``ParaMol/MM_engines/least_square.py``
+    (``tests/golden/make_lls_fixtures.py``): design matrix, right-hand side, column bookkeeping, fitted parameter vector and
+    the reconstructed optimizable values.  This pins SURVEY row a19 to the reference itself."""
+    from lls_fixture_util import build_system, check_design, load_case
+    from paramol_b200.MM_engines.least_square import LinearLeastSquare
+    fx = load_case(golden_dir, name)
+    system, ps = build_system(golden_dir, fx)
+    lls = LinearLeastSquare(ps, True, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01, weighting_method=str(fx["weighting"]),
+                            weighting_temperature=300.0)
+    A = lls._calculate_a(system, 0.05, 0.05)
+    B = lls._calculate_b(system)
+    assert np.array_equal(np.array(lls._param_keys_list), fx["keys"]) and np.array_equal(np.array(lls._param_symmetries_list), fx["symm"])
+    assert np.abs(np.asarray(lls._p0) - fx["p0"]).max() <= 1e-12
+    assert np.abs(lls.mm_energies_zero - fx["mm_energies_zero"]).max() <= 1e-9 * max(1.0, np.abs(fx["mm_energies_zero"]).max())
+    check_design(fx, A, B, rtol_a=1e-10)
+    fitted = np.asarray(lls.fit_parameters_lls([system]), dtype=np.float64)
+    want = fx["parameters"]
+    assert np.abs(lls._parameters - want).max() <= 1e-6 * np.abs(want).max(), (lls.reduction, np.abs(lls._parameters - want).max())
+    assert np.abs(fitted - fx["fitted_values"]).max() <= 1e-6 * np.abs(fx["fitted_values"]).max()
+    assert np.abs(np.asarray(system.weights) * np.ones(len(B)) - fx["weights"]).max() <= 1e-14
+
+
+def test_lls_config4_shape_lig60_vs_numpy():
+    """BASELINE.json config 4 in shape: the 60-atom ligand with every bonded force constant, equilibrium value and phase
+    optimizable (742 design-matrix columns), 20 000 conformations: device design matrix and fitted parameters against the
+    reference-structured numpy pipeline (lstsq on the full stacked matrix).  This is where the conditioning of the reduction
+    (nearly collinear bracketing columns) matters."""
+    from oracle import oracle as O
+    from paramol_b200.MM_engines.least_square import LinearLeastSquare
+    from paramol_b200.Utils.synthetic import make_ligand, perturbed_conformations
+    mm, x0 = make_ligand(60)
+    engine = B200Engine(system=mm)
+    system = ParaMolSystem("lig60", engine, 60)
+    system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
+    n_conf = 20000
+    X = perturbed_conformations(x0, n_conf, sigma=0.004, seed=17)
+    E, _ = O.energies_forces(engine.system, X, n_threads=4)
+    rng = np.random.default_rng(2)
+    system.ref_coordinates, system.ref_energies = X, E + rng.normal(0, 2.0, len(E))
+    system.n_structures = n_conf
+    ps = ParameterSpace()
+    ps.get_optimizable_parameters([system], symmetry_constrained=False)
+    lls = LinearLeastSquare(ps, True, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01, weighting_method="uniform",
+                            weighting_temperature=300.0)
+    A_want, p0, keys, init, symm = _numpy_lls(system, ps, None, True, 1.0)
+    assert A_want.shape == (n_conf, 742)
+    A_dev = lls._calculate_a(system, 0.05, 0.05)
+    assert A_dev.shape == A_want.shape
+    assert np.abs(A_dev - A_want).max() <= 1e-10 * max(1.0, np.abs(A_want).max())
+    assert np.allclose(lls._p0, p0, rtol=0, atol=1e-12) and lls._param_keys_list == keys and lls._param_symmetries_list == symm
+    B = np.asarray(system.ref_energies) - lls._energies_with_zeroed_parameters(system)
+    B = B - B.mean()
+    E_zero = O.energies_forces(_zeroed(engine.system), X, want_forces=False, n_threads=4)[0]
+    assert np.abs(lls.mm_energies_zero - E_zero).max() <= 1e-9 * max(1.0, np.abs(E_zero).max())
+    w = np.ones(n_conf) / n_conf
+    var = np.var(system.ref_energies)
+    sc_dict, _ = ps.calculate_scaling_constants("default")
+    sc = np.asarray([sc_dict[k] for k in keys])
+    pw_dict, _ = ps.calculate_prior_widths("default")
+    pw = np.asarray([pw_dict[k] for k in keys])
+    Aw = A_want * np.sqrt(w)[:, None] / np.sqrt(var) / sc[None, :]
+    Bw = B * np.sqrt(w) / np.sqrt(var)
+    alpha = 1.0 / sc
+    rows = [Aw, np.identity(len(sc)) / pw[None, :] * alpha[None, :]]
+    rhs = [Bw, alpha * init]
+    sym_rows = []
+    covered = []
+    for i, si in enumerate(symm):
+        if si in covered or si in ("X_x", "X_y", "X"):
+            continue
+        for j in range(i + 1, len(symm)):
+            if symm[j] == si:
+                r = np.zeros(len(sc))
+                r[i], r[j] = 1.0, -1.0
+                sym_rows.append(r)
+        covered.append(si)
+    if sym_rows:
+        rows.append(np.asarray(sym_rows))
+        rhs.append(np.zeros(len(sym_rows)))
+    want = np.linalg.lstsq(np.vstack(rows), np.concatenate(rhs), rcond=None)[0] / sc
+    lls.fit_parameters_lls([system])
+    got = lls._parameters
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), (lls.reduction, np.abs(got - want).max(), np.abs(want).max())
+
+
+def _zeroed(mm):
+    """Copy of an MMSystem with the bonded force constants, equilibrium values and phases zeroed (what update_systems(zeros) does
+    for a bonded-only parameter space; abs() and the phase wrap leave zeros alone)."""
+    z = mm.copy()
+    z.bond_par[...] = 0.0
+    z.angle_par[...] = 0.0
+    z.torsion_par[...] = 0.0
+    return z
+
+
 def test_lls_reduction_cholesky_qr2_and_householder_fallback():
     """``LinearLeastSquare._reduce_tall``: (R, Q^T b) must reproduce the least-squares problem, || A x - b ||^2 =
     || R x - Q^T b ||^2 + const, i.e. R^T R = A^T A and R^T (Q^T b) = A^T b; a rank-deficient matrix (duplicated
@@ -231,7 +302,7 @@ def test_lls_reduction_cholesky_qr2_and_householder_fallback():
 
 
 @pytest.mark.parametrize("n_atoms,n_grid,n_conf", [(1, 5, 3), (3, 33, 4), (14, 600, 3), (31, 64, 5), (59, 77, 4), (60, 513, 3),
-                                                   (63, 40, 3), (64, 100, 2), (97, 130, 3), (131, 70, 2), (160, 45, 2)])
+                                                   (60, 500, 256), (63, 40, 3), (64, 100, 2), (97, 130, 3), (131, 70, 2), (160, 45, 2)])
 def test_resp_assemble_sizes_vs_numpy(n_atoms, n_grid, n_conf):
     """pm_resp_assemble through the C ABI for atom counts on both sides of every tiling boundary (micro-tile padding, number of
     warps, micro-tiles per thread) and grid sizes that leave partial tiles and partial chunks, against numpy."""
