@@ -29,7 +29,7 @@
  * Conformation "tiles": conformations are kept resident in HBM as tiles of CPW = pm_conf_per_tile(h) conformations,
  * tile t = doubles [3*n_atoms][CPW] with the conformation index fastest; a whole tile is one contiguous TMA bulk
  * copy into the shared memory of the warp that evaluates it.  CPW = 32 / (lanes per conformation) is chosen per
- * topology so that enough warps fit in shared memory (env PM_CPW overrides).  pm_pack_tiles converts
+ * topology so that enough warps fit in shared memory (or fixed by the caller: pm_create's conf_per_tile).  pm_pack_tiles converts
  * from the reference's [S][N][3] C-order arrays (ParaMolSystem.ref_coordinates / ref_forces,
  * ParaMol/System/system.py:85-123).
  */
@@ -67,8 +67,10 @@ int pm_version(void);
 int pm_device_count(void);
 
 /* ---- handle ------------------------------------------------------------------------------------ */
-/* Replaces OpenMMEngine.init_openmm / Context creation (ParaMol/MM_engines/openmm.py:161-254). */
-int pm_create(const pm_topology *topo, int device, pm_handle *out);
+/* Replaces OpenMMEngine.init_openmm / Context creation (ParaMol/MM_engines/openmm.py:161-254).
+ * conf_per_tile: conformations per tile (32, 16, 8 or 4), or 0 to let the library choose per topology.  The
+ * topology-specialised kernels (pm_set_specialized) need 32. */
+int pm_create(const pm_topology *topo, int device, int conf_per_tile, pm_handle *out);
 int pm_destroy(pm_handle h);
 int pm_n_slots(pm_handle h);          /* doubles per parameter vector (layout above)           */
 int pm_n_derived(pm_handle h);        /* doubles per parameter vector of the derived table      */

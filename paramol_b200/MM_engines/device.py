@@ -86,9 +86,15 @@ class DeviceTopology:
         ``ParaMol/MM_engines/openmm.py:622-626``); every other exception is a scaled 1-4 interaction.
     device : int or None
         CUDA device index (default: current device).
+    conf_per_tile : int or None
+        Conformations per tile (32, 16, 8, 4); None lets the library choose (``pm_create(..., conf_per_tile=0, ...)``).
+
+    ``specialize_status`` says which E+F kernel serves full evaluations: "installed" (generated for this topology), "not eligible"
+    (molecule too large / reaction field / switched off) or the reason the generated kernel could not be built or installed.
+    ``PARAMOL_B200_SPECIALIZE=require`` turns the last case into a :obj:`B200Error` (``bench.py`` sets it).
     """
 
-    def __init__(self, mm_system, device=None):
+    def __init__(self, mm_system, device=None, conf_per_tile=None):
         torch = _torch()
         L = _lib.lib()
         if not torch.cuda.is_available() or L.pm_device_count() < 1:
@@ -97,24 +103,21 @@ class DeviceTopology:
         s = mm_system
         self.n_atoms = int(s.n_atoms)
         self.k_coul = float(s.one_4pi_eps0)
+        #: CutoffNonPeriodic + reaction field (the system of the reference's Tests/aniline.xml): served by the generic kernel
+        #: only; pm_delta_eval and pm_grad do not implement it
+        self.rf = s.nonbonded_method != "NoCutoff"
         topo, self._keep = _pm_topology(s)
         self.exception_active = self._keep["act"]
         k = self._keep
         # Small molecules: a kernel generated for this topology (csrc/specialize.py).  It works on tiles of 32 conformations, so
         # the image is built first (host-only pair list) and, if there is one, the handle is created with that tile shape.
-        built = self._build_specialized(s, topo)
+        self.specialize_status = "not eligible"
+        built = self._build_specialized(s, topo, status=self)
         h = ctypes.c_void_p()
-        saved_cpw = os.environ.get("PM_CPW")
-        if built is not None:
-            os.environ["PM_CPW"] = "32"
-        try:
-            _lib.check(L.pm_create(ctypes.byref(topo), self.device, ctypes.byref(h)), "pm_create")
-        finally:
-            if built is not None:
-                if saved_cpw is None:
-                    os.environ.pop("PM_CPW", None)
-                else:
-                    os.environ["PM_CPW"] = saved_cpw
+        # conformations per tile: 32 for the generated kernels, else the caller's choice (``conf_per_tile`` argument or, for
+        # sweeps only, the PM_CPW environment variable), else 0 = chosen by the library per topology
+        cpw = 32 if built is not None else int(conf_per_tile if conf_per_tile is not None else (os.environ.get("PM_CPW") or 0))
+        _lib.check(L.pm_create(ctypes.byref(topo), self.device, cpw, ctypes.byref(h)), "pm_create")
         self._h = h
         self._L = L
         self.n_bonds, self.n_angles, self.n_torsions, self.n_exceptions = (len(k["bond"]), len(k["angle"]),
@@ -137,12 +140,24 @@ class DeviceTopology:
             buf = ctypes.create_string_buffer(image, len(image))
             if self._L.pm_set_specialized(self._h, buf, len(image), warps, tiles, warps_energy, warps_grad) == 0:
                 self.specialized = True
+                self.specialize_status = "installed"
             else:   # the generic kernel of the same handle keeps working
+                self.specialize_status = "not installed: " + self._L.pm_last_error().decode()
+                if os.environ.get("PARAMOL_B200_SPECIALIZE", "auto") == "require":
+                    raise B200Error("topology-specialised kernel " + self.specialize_status)
                 import logging
-                logging.warning("paramol_b200: specialised kernel not installed (%s)", self._L.pm_last_error().decode())
+                logging.warning("paramol_b200: specialised kernel %s", self.specialize_status)
+        # every rank must run the same kernel (same tile shape, bitwise reproducible partial sums): a rank whose compile failed
+        # while the others succeeded is an error, not a silent per-rank difference
+        from ..Utils import dist as _dist
+        if _dist.world_size() > 1:
+            flags = _dist.allreduce_sum_numpy(np.array([1.0 if self.specialized else 0.0, float(self.conf_per_tile)]))
+            if flags[0] not in (0.0, float(_dist.world_size())) or flags[1] != self.conf_per_tile * _dist.world_size():
+                raise B200Error("ranks disagree on the E+F kernel of this topology (specialised on %d of %d ranks; this rank: %s)"
+                                % (int(flags[0]), _dist.world_size(), self.specialize_status))
 
     @staticmethod
-    def _build_specialized(mm_system, topo):
+    def _build_specialized(mm_system, topo, status=None):
         """
         (image, warps, atoms in the force tile, energy warps, gradient warps) of the topology-specialised kernels of ``mm_system`` or None.  Controlled by
         ``PARAMOL_B200_SPECIALIZE`` ("0" off, anything else / unset: automatic).  If the compiler is not available the generic
@@ -166,6 +181,10 @@ class DeviceTopology:
         try:
             return specialize.image_for(n_atoms, k["bond"], k["angle"], k["tors"], k["tper"], pairs[:n.value])
         except (RuntimeError, OSError) as exc:   # no compiler, compile error, cache directory not writable
+            if status is not None:
+                status.specialize_status = "not built: %s" % (str(exc).splitlines()[0] if str(exc) else type(exc).__name__)
+            if os.environ.get("PARAMOL_B200_SPECIALIZE", "auto") == "require":
+                raise B200Error("topology-specialised kernel could not be built: %s" % exc)
             import logging
             logging.warning("paramol_b200: topology-specialised kernel not built (%s); using the generic kernel", exc)
             return None
@@ -308,6 +327,8 @@ class DeviceTopology:
         pair).  Returns None when a row touches more than ``max_fraction`` of the terms or more atoms than the kernel's
         per-proposal limit -- the caller then evaluates the batch in full.
         """
+        if self.rf:      # pm_delta_eval has no reaction-field variant: the caller evaluates in full
+            return None
         m = self._delta_maps()
         k = self._keep
         rows = np.atleast_2d(np.asarray(slots_rows, dtype=np.float64))

@@ -88,6 +88,7 @@ class ObjectiveFunction:
         self._batch_lims = None
         self._parallel_function = None
         self._state = {}
+        self._state_version = 0
         self.last_timings = {}
         if self._parallel:
             self.init_parallel()
@@ -101,6 +102,13 @@ class ObjectiveFunction:
 
     def get_f_count(self):
         return self._f_count
+
+    def invalidate(self):
+        """Drop every cached per-system device state (force metric, energy shift, static weights, captured graphs).  Needed only
+        after IN-PLACE edits of property variances or manual weights (replacing the arrays is detected by itself); see
+        :meth:`paramol_b200.System.system.ParaMolSystem.invalidate_device_data` for in-place edits of the reference data."""
+        self._state_version += 1
+        self._state = {}
 
     def init_parallel(self):
         """
@@ -178,6 +186,10 @@ class ObjectiveFunction:
             raise NotImplementedError("the analytic gradient needs the fused device path")
         if self._weighting_method.upper() == "NON_BOLTZMANN":
             raise NotImplementedError("analytic gradient: NON_BOLTZMANN weights depend on the parameters")
+        for system in self.systems:
+            if getattr(system.engine.system, "nonbonded_method", "NoCutoff") != "NoCutoff":
+                raise NotImplementedError("analytic gradient: the cutoff / reaction-field variant ({}) is not implemented; "
+                                          "use finite differences through f_batch".format(system.name))
         start_time = time.time()
         x = np.asarray(parameters_values, dtype=np.float64)
         self.parameter_space.update_systems(self.systems, parameters_values)
@@ -254,7 +266,8 @@ class ObjectiveFunction:
         need_f = f_prop is not None and system in f_prop.systems
         ens = system.device_ensemble()
         key = (id(ens), need_e, need_f, None if f_prop is None else f_prop.term_type,
-               None if f_prop is None else id(f_prop.variance), self._weighting_method.upper(), id(system.wham_weights))
+               None if f_prop is None else id(f_prop.variance), self._weighting_method.upper(), id(system.wham_weights),
+               getattr(system, "_data_version", 0), self._state_version)
         st = self._state.get(s_idx)
         if st is not None and st["key"] == key:
             return st
@@ -301,7 +314,14 @@ class ObjectiveFunction:
         w = torch.exp(-st["beta"] * (d - mean[:, None]))
         z = w.sum(dim=1, keepdim=True)
         _dist.allreduce_sum_tensor_(z)
-        bad = ~torch.isfinite(z) | (z <= 0)
+        # The reference (and ParaMolSystem.compute_conformations_weights) evaluates this under np.seterr(all='raise') and falls
+        # back to uniform weights on ANY floating-point error (system.py:193, 215-221): overflow of the exponentials or of their
+        # sum, but also UNDERFLOW of an exponential or of w / z (a result below the smallest normal double).  Same conditions
+        # here, decided globally over ranks.
+        tiny = torch.finfo(torch.float64).tiny
+        w_min = w.min(dim=1, keepdim=True).values
+        _dist.allreduce_min_tensor_(w_min)
+        bad = ~torch.isfinite(z) | (z <= 0) | (w_min < tiny) | (w_min / z < tiny)
         w = torch.where(bad, torch.full_like(w, 1.0 / st["n_global"]), w / z)
         if emm.shape[0] == 1:
             system.weights = w[0].cpu().numpy()

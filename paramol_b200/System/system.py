@@ -85,7 +85,20 @@ class ParaMolSystem:
     def _data_key(self):
         def k(a):
             return None if a is None else (id(a), len(a))
-        return (k(self.ref_coordinates), k(self.ref_forces), k(self.ref_energies), id(self.engine._topo))
+        return (k(self.ref_coordinates), k(self.ref_forces), k(self.ref_energies), id(self.engine._topo),
+                getattr(self, "_data_version", 0))
+
+    def invalidate_device_data(self):
+        """
+        Call after editing ``ref_coordinates`` / ``ref_energies`` / ``ref_forces`` / ``weights`` / ``wham_weights`` IN PLACE
+        (``ref_energies -= ref_energies.min()``, ``ref_forces[:] = ...``).  The device-resident copies (and everything
+        :obj:`ObjectiveFunction` derives from them: energy shift, static weights, captured CUDA graphs) are keyed on the identity
+        of the host arrays, so REPLACING an array is detected, mutating it is not -- the reference re-reads the host arrays on
+        every call and has no such rule.  Every method of this class that mutates reference data calls this itself.
+        """
+        self._data_version = getattr(self, "_data_version", 0) + 1
+        self._ensemble = None
+        self._ensemble_key = None
 
     def device_ensemble(self, pinned=False):
         """The device-resident copy of this system's conformations (rebuilt when the reference arrays are replaced)."""

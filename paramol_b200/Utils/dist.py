@@ -64,6 +64,20 @@ def allreduce_sum_tensor_(tensor):
     return tensor
 
 
+def allreduce_min_tensor_(tensor):
+    """In-place min-allreduce of a torch tensor; identity on one rank."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return tensor
+    if d.get_backend() == "gloo" and tensor.is_cuda:
+        t = tensor.cpu()
+        d.all_reduce(t, op=d.ReduceOp.MIN)
+        tensor.copy_(t)
+        return tensor
+    d.all_reduce(tensor, op=d.ReduceOp.MIN)
+    return tensor
+
+
 def shard_bounds(n_items, n_ranks=None, r=None):
     """Contiguous shard [lo, hi) of rank ``r``: the first ``n_items % n_ranks`` ranks get one extra item."""
     n_ranks = world_size() if n_ranks is None else n_ranks

@@ -38,7 +38,7 @@ SIGNATURES = {
     "pm_last_error": (ctypes.c_char_p, []),
     "pm_version": (ctypes.c_int, []),
     "pm_device_count": (ctypes.c_int, []),
-    "pm_create": (ctypes.c_int, [ctypes.POINTER(PmTopology), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "pm_create": (ctypes.c_int, [ctypes.POINTER(PmTopology), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "pm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_n_slots": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_n_derived": (ctypes.c_int, [ctypes.c_void_p]),

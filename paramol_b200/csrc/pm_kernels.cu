@@ -841,7 +841,7 @@ extern "C" int pm_topology_pairs(const pm_topology *t, int cpw, int *n_pairs, in
     return 0;
 }
 
-extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
+extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm_handle *out) {
     if (!t || !out) return pm_fail("pm_create: null argument");
     if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_create: n_atoms out of range");
     if (t->nonbonded_method != 0 && t->nonbonded_method != 1) return pm_fail("pm_create: unknown nonbonded method");
@@ -863,12 +863,8 @@ extern "C" int pm_create(const pm_topology *t, int device, pm_handle *out) {
     // ---- choose CPW (conformations per warp; L = 32 / CPW lanes per conformation) ---------------------------
     // The derived-table size does not depend on L, the program size only weakly: plan with the L = 1 program.
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    int cpw = 0;
-    const char *env = getenv("PM_CPW");
-    if (env && *env) {
-        cpw = atoi(env);
-        if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: PM_CPW must be 32, 16, 8 or 4");
-    }
+    int cpw = conf_per_tile;
+    if (cpw != 0 && cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: conf_per_tile must be 0 (auto), 32, 16, 8 or 4");
     if (rf) cpw = 32;  // the reaction-field variant is instantiated for one lane per conformation only
     PmHostProgram host;
     const int n_derived_est = 2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * (N * (N - 1) / 2) + 2;

@@ -750,33 +750,59 @@ def cache_dir():
     return d
 
 
+NVCC_FLAGS = ["-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v"]
+_NVCC_ID = {}
+
+
+def _nvcc_identity(nvcc):
+    """Release string of the compiler (part of the cache key: another nvcc may generate another image)."""
+    import subprocess
+    if nvcc not in _NVCC_ID:
+        try:
+            out = subprocess.run([nvcc, "--version"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True).stdout
+            _NVCC_ID[nvcc] = out.strip().splitlines()[-1] if out.strip() else "unknown"
+        except OSError:
+            _NVCC_ID[nvcc] = "unknown"
+    return _NVCC_ID[nvcc]
+
+
 def compile_image(source, want_report=False):
-    """nvcc -cubin for sm_100a, cached in-tree by the hash of the source (the cache travels with the repository snapshot, so
-    a molecule compiled once -- e.g. by ``__graft_entry__.build()`` -- is not compiled again on the GPU box).  With
-    ``want_report`` also returns the ptxas resource report (kept next to the image)."""
+    """nvcc -cubin for sm_100a, cached by the hash of (source, pm_device.cuh, compiler flags).  The cache directory
+    ``paramol_b200/_spec_cache/`` is git-ignored but NOT gpurun-ignored: an image compiled here (e.g. by
+    ``__graft_entry__.build()``) travels to the GPU box with the working-tree snapshot and is only loaded there; a molecule first
+    seen on a box with nvcc is compiled once on that box.  Safe when several ranks start at once: source, report and image are
+    written under per-process names and moved into place with ``os.replace``, so a reader never sees a partial file and
+    concurrent writers produce identical bytes.  With ``want_report`` also returns the ptxas resource report."""
     import hashlib
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "pm_device.cuh"), "rb") as fh:
-        key = hashlib.sha256(source.encode() + fh.read()).hexdigest()[:24]
+        key = hashlib.sha256(source.encode() + fh.read() + " ".join(NVCC_FLAGS).encode()).hexdigest()[:24]
     path = os.path.join(cache_dir(), key + ".cubin")
     if not os.path.exists(path) or not os.path.exists(path + ".txt"):
         nvcc = _nvcc()
         if nvcc is None:
             raise RuntimeError("nvcc not found: cannot compile the topology-specialised kernel")
-        src = os.path.join(cache_dir(), key + ".cu")
+        tag = ".tmp%d" % os.getpid()
+        src = os.path.join(cache_dir(), key + tag + ".cu")
         with open(src, "w") as fh:
             fh.write(source)
-        tmp = path + ".tmp%d" % os.getpid()
-        res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v",
-                              "-I", here, src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed on the specialised kernel:\n" + res.stdout[-2000:])
-        with open(tmp + ".txt", "w") as fh:
-            fh.write(res.stdout)
-        os.replace(tmp + ".txt", path + ".txt")
-        os.replace(tmp, path)
+        tmp = path + tag
+        try:
+            res = subprocess.run([nvcc] + NVCC_FLAGS + ["-I", here, src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                 universal_newlines=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on the specialised kernel:\n" + res.stdout[-2000:])
+            with open(tmp + ".txt", "w") as fh:
+                fh.write("# %s\n# %s\n" % (_nvcc_identity(nvcc), " ".join(NVCC_FLAGS)) + res.stdout.replace(key + tag, key))
+            os.replace(src, os.path.join(cache_dir(), key + ".cu"))
+            os.replace(tmp + ".txt", path + ".txt")
+            os.replace(tmp, path)
+        finally:
+            for leftover in (src, tmp, tmp + ".txt"):
+                if os.path.exists(leftover):
+                    os.remove(leftover)
     with open(path, "rb") as fh:
         image = fh.read()
     if want_report:

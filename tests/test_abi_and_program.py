@@ -100,7 +100,7 @@ def test_compute_calls_fail_loudly_without_gpu():
     L = _lib.lib()
     topo, keep = _topology(s)
     h = ctypes.c_void_p()
-    assert L.pm_create(ctypes.byref(topo), 0, ctypes.byref(h)) != 0
+    assert L.pm_create(ctypes.byref(topo), 0, 0, ctypes.byref(h)) != 0
     assert b"no CUDA device" in L.pm_last_error()
 
 

@@ -160,6 +160,34 @@ def test_fused_objective_vs_oracle_with_perturbed_parameters(kwargs_dict, golden
         assert abs(got_serial - w) <= 1e-8 * abs(w)
 
 
+@pytest.mark.parametrize("spread", [30.0, 400.0, 2500.0, -1850.0])
+def test_non_boltzmann_fused_equals_seam_for_wide_energy_spreads(kwargs_dict, golden_dir, spread):
+    """NON_BOLTZMANN weights fall back to uniform on ANY floating-point error of the reference's np.seterr(all='raise') block
+    (system.py:193, 215-221) -- including UNDERFLOW of exp(-beta d), which sets in at a spread of ~1.7e3 kJ/mol at 300 K.  The
+    fused device weights must take the same branch as the host path (``fused=False``), whatever the spread."""
+    system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False)
+    if spread > 0:
+        system.ref_energies = np.asarray(system.ref_energies) + spread * np.arange(10)
+    else:   # one outlier: nothing overflows, ONE exponential underflows
+        system.ref_energies = np.asarray(system.ref_energies) + spread * (np.arange(10) == 7)
+    ps = ParameterSpace()
+    _, x0 = ps.get_optimizable_parameters([system])
+    e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type="norm")
+    e_prop.calculate_variance()
+    f_prop.calculate_variance()
+    settings = dict(objective_function_settings, weighting_method="non_boltzmann", checkpoint_freq=10 ** 9)
+    fused = ObjectiveFunction(None, ps, [e_prop, f_prop], [system], **settings)
+    seam = ObjectiveFunction(None, ps, [e_prop, f_prop], [system], fused=False, **settings)
+    a = fused.f(np.asarray(x0).copy())
+    w_fused = np.array(system.weights, copy=True)
+    b = seam.f(np.asarray(x0).copy())
+    w_seam = np.array(system.weights, copy=True)
+    assert np.abs(w_fused - w_seam).max() <= 1e-12 * np.abs(w_seam).max(), (w_fused, w_seam)
+    assert abs(a - b) <= 1e-10 * abs(b)
+    if spread >= 2500.0 or spread < 0:
+        assert np.allclose(w_seam, 0.1)    # the underflow branch was taken
+
+
 def test_nan_objective_becomes_1e16(kwargs_dict, golden_dir):
     system = _aniline(kwargs_dict, golden_dir, opt_charges=False, opt_lj=False, opt_sc=False)
     ps = ParameterSpace()

@@ -71,6 +71,53 @@ def test_xml_roundtrip(golden_dir, tmp_path):
     ET.parse(p)
 
 
+def test_checkpoint_xml_has_the_vocabulary_openmm_deserializes(golden_dir, tmp_path, aniline_system):
+    """The checkpoint written by ObjectiveFunction.f must be loadable by XmlSerializer.deserialize like the reference's own
+    (ParaMol/MM_engines/openmm.py:341-364).  OpenMM is not installed here, so the check is structural against the reference
+    fixture Tests/aniline.xml, which IS XmlSerializer output: same force list in the same order with the same forceGroups, every
+    attribute and child node of every <Force> present (the NonbondedForce proxy reads alpha, ewaldTolerance, dispersionCorrection,
+    the offsets nodes ... without defaults), identical term data."""
+    ref_path = os.path.join(golden_dir, "aniline.xml")
+    s = system_from_xml(ref_path)
+    p = str(tmp_path / "ck.xml")
+    write_system_xml(s, p)
+    ref_forces = list(ET.parse(ref_path).getroot().find("Forces"))
+    got_forces = list(ET.parse(p).getroot().find("Forces"))
+    assert [f.get("type") for f in got_forces] == [f.get("type") for f in ref_forces]      # CMMotionRemover kept, none invented
+    for fr, fg in zip(ref_forces, got_forces):
+        assert set(fr.attrib) <= set(fg.attrib), (fr.get("type"), set(fr.attrib) - set(fg.attrib))
+        assert fr.get("forceGroup") == fg.get("forceGroup") and fr.get("version") == fg.get("version")
+        assert [c.tag for c in fr] == [c.tag for c in fg], fr.get("type")
+        for cr, cg in zip(fr, fg):
+            assert len(cr) == len(cg)
+            for er, eg in zip(cr, cg):
+                assert er.tag == eg.tag and set(er.attrib) == set(eg.attrib)
+                for key in er.attrib:
+                    assert float(er.get(key)) == float(eg.get(key)), (fr.get("type"), key)
+        if fr.get("type") == "NonbondedForce":
+            for key in fr.attrib:
+                if key != "type":
+                    assert float(fr.get(key)) == float(fg.get(key)), key
+    # a System that was not read from XML (AMBER topology): complete vocabulary with OpenMM's defaults, one force per name
+    p2 = str(tmp_path / "ck2.xml")
+    write_system_xml(aniline_system, p2)
+    nb = [f for f in ET.parse(p2).getroot().find("Forces") if f.get("type") == "NonbondedForce"][0]
+    nb_ref = [f for f in ref_forces if f.get("type") == "NonbondedForce"][0]
+    assert set(nb_ref.attrib) <= set(nb.attrib) and nb.get("method") == "0"
+    assert [c.tag for c in nb] == [c.tag for c in nb_ref]
+    # a second PeriodicTorsionForce survives the round trip with its own torsions
+    s3 = system_from_xml(ref_path)
+    s3.force_names.insert(3, "PeriodicTorsionForce")
+    s3.force_attrs.insert(3, {"forceGroup": "7", "type": "PeriodicTorsionForce", "usesPeriodic": "0", "version": "2"})
+    s3.torsion_force_sizes.append(2)
+    s3.add_torsions([[0, 1, 2, 3], [3, 2, 1, 0]], [2, 3], [[0.0, 1.5], [3.0, 0.5]])
+    p3 = str(tmp_path / "ck3.xml")
+    write_system_xml(s3, p3)
+    s4 = system_from_xml(p3)
+    assert s4.torsion_force_sizes == [len(s.torsion_idx), 2] and s4.force_names == s3.force_names
+    assert np.array_equal(s4.torsion_idx, s3.torsion_idx) and np.array_equal(s4.torsion_par, s3.torsion_par)
+
+
 def test_gaussian_reader_excerpt(golden_dir):
     conf, grid, esp, energy = GaussianESP().read_log_files(os.path.join(golden_dir, "aniline_opt_excerpt.log"))
     full = np.load(os.path.join(golden_dir, "aniline_esp.npz"))
