@@ -43,6 +43,7 @@ extern "C" {
 #define PM_NPARTIAL 8 /* doubles per (parameter vector) row written by pm_reduce_objective */
 
 typedef struct pm_handle_s *pm_handle;
+typedef struct pm_comm_s *pm_comm; /* intra-node communicator of the conformation-sharded objective (see pm_comm_create) */
 
 /* Topology: what app.AmberPrmtopFile(...).createSystem(...) hands to ParaMol
  * (ParaMol/MM_engines/openmm.py:161-254) minus the parameter values.  All arrays are host int32. */
@@ -138,6 +139,35 @@ long pm_reduce_scratch_doubles(int n_vec);
 int pm_reduce_objective(const double *emm_dev, const double *fres_dev, const double *eref_dev,
                         const double *weights_dev, double d_shift, int n_vec, long n_conf,
                         double *partials_dev, double *scratch_dev, void *stream);
+
+/* ---- fused evaluation + reduction (+ cross-GPU sum): the objective call as ONE pass ----------------------------- */
+/* pm_eval followed by pm_reduce_objective without the [P][S] round trip: the E(+F) kernel adds the five weighted sums per warp
+ * while it evaluates, a second small kernel adds the warps' rows in a fixed order (deterministic) and writes
+ * partials_dev [P][PM_NPARTIAL] exactly as pm_reduce_objective does.  fref_tiles_dev != NULL (with_forces = 1): the force
+ * residual enters column [4].  emm_dev / fres_dev [P][S]: optional per-conformation outputs (NULL = not written).
+ * comm != NULL: the rows of ALL ranks of the communicator are summed inside that second kernel -- every rank pushes its 8
+ * doubles per vector into its peers' inboxes over NVLink (peer-to-peer stores), waits for theirs and adds them in rank order, so
+ * every rank holds the same global sums bit for bit and [5] is the global conformation count.  This is the single collective
+ * of the conformation-sharded objective (the reference's counterpart: the fork pool's gather + np.sum of
+ * ParaMol/Objective_function/objective_function.py:268-311).  scratch_dev: pm_eval_reduce_scratch_doubles(h, P, S) doubles. */
+long pm_eval_reduce_scratch_doubles(pm_handle h, int n_vec, long n_conf);
+int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                   const double *fref_tiles_dev, long n_conf, int with_forces, const double *eref_dev,
+                   const double *weights_dev, double d_shift, double *partials_dev, double *scratch_dev, pm_comm comm,
+                   double *emm_dev, double *fres_dev, void *stream);
+
+/* ---- intra-node communicator (one process per GPU, NVLink / NVSwitch peer memory) -------------------------------- */
+/* pm_comm_create allocates this rank's inbox on `device` and returns its 64-byte CUDA IPC handle in handle_out; the host
+ * layer exchanges the handles (torch.distributed all_gather) and passes all of them, in rank order, to pm_comm_connect, which
+ * maps the peers' inboxes.  max_vec bounds n_vec of the calls that use the communicator.  All ranks must issue the same
+ * sequence of communicating calls (SPMD); a peer that never arrives makes the kernel give up after ~2 s, poison the result with
+ * NaN and count a timeout (pm_comm_timeouts) instead of hanging the GPU.
+ * pm_comm_allreduce: the same one-shot sum for an arbitrary small buffer (n <= 8 * max_vec doubles), in place. */
+int pm_comm_create(int device, int rank, int world, int max_vec, void *handle_out, pm_comm *out);
+int pm_comm_connect(pm_comm c, const void *all_handles);
+int pm_comm_allreduce(pm_comm c, double *buf_dev, int n, void *stream);
+long pm_comm_timeouts(pm_comm c);
+int pm_comm_destroy(pm_comm c);
 
 /* ---- RESP (K5) ------------------------------------------------------------------------------------ */
 /* Normal-equation sums over conformations, the inverse distances R_m[j][i] = 1/|x_mj - g_mi| being generated on the fly:

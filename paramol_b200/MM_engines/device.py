@@ -528,6 +528,34 @@ class DeviceEnsemble:
                    "pm_reduce_objective")
         return partials
 
+    def evaluate_reduce(self, derived, with_forces=True, d_shift=0.0, weights="own", comm=None, want_emm=False, want_fres=False):
+        """
+        ``pm_eval_reduce``: evaluation, residual reduction and -- with ``comm`` (:obj:`paramol_b200.Utils.dist.DeviceComm`) --
+        the sum over ranks as one pass; no [P, S] arrays are written unless asked for.  Returns (partials [P, 8] CUDA: global
+        sums when ``comm`` is given, emm or None, fres or None).  The force residual is included when ``with_forces`` and the
+        ensemble holds reference forces.
+        """
+        torch = _torch()
+        topo = self.topology
+        n_vec = int(derived.shape[0])
+        need = int(topo._L.pm_eval_reduce_scratch_doubles(topo._h, n_vec, self.n_conf))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float64, device=self.device)
+        partials = self._buf("partials", (n_vec, NPARTIAL))
+        w = self.weights if isinstance(weights, str) else weights
+        use_f = bool(with_forces) and self.fref_tiles is not None
+        emm = self._buf("emm", (n_vec, self.n_conf)) if want_emm else None
+        fres = self._buf("fres", (n_vec, self.n_conf)) if (want_fres and use_f) else None
+        _lib.check(topo._L.pm_eval_reduce(topo._h, derived.data_ptr(), n_vec, self.coord_tiles.data_ptr(),
+                                          self.fref_tiles.data_ptr() if use_f else None, self.n_conf, int(bool(with_forces)),
+                                          self.eref.data_ptr() if self.eref is not None else None,
+                                          w.data_ptr() if w is not None else None, float(d_shift), partials.data_ptr(),
+                                          self._scratch.data_ptr(), comm.handle if comm is not None else None,
+                                          emm.data_ptr() if emm is not None else None,
+                                          fres.data_ptr() if fres is not None else None, _stream_ptr(self.device)),
+                   "pm_eval_reduce")
+        return partials, emm, fres
+
     # ---- delta evaluation ---------------------------------------------------------------------------------
     def set_delta_base(self, slots_row, derived_row, emm_row, fres_row, fmm_tiles_row):
         """Keep copies of the per-conformation results of ONE fully evaluated vector as the base of later delta evaluations."""

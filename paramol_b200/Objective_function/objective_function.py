@@ -276,6 +276,9 @@ class ObjectiveFunction:
             assert f_prop.variance is not None, "ForceProperty.calculate_variance() was not called."
             ens.topology.set_force_metric(f_prop.metric(f_prop.systems.index(system)))
         st["n_global"] = system.n_structures_global()
+        # multi-GPU: the peer-memory communicator whose all-reduce runs inside the reduction kernel (None: single rank, gloo, or
+        # IPC unavailable -> NCCL all-reduce of the partial sums); creating it is a collective, done here on every rank
+        st["comm"] = _dist.device_comm(ens.device.index)
         st["d_shift"] = 0.0
         if need_e:
             assert e_prop.variance is not None, "EnergyProperty.calculate_variance() was not called."
@@ -531,8 +534,9 @@ class ObjectiveFunction:
         return ens.delta_evaluate(plan, derived)
 
     def _capture_graph(self, st, ens):
-        """CUDA graph of one single-vector evaluation of ``ens``: pinned slots -> device, ``pm_prepare_params``, the E(+F)
-        kernel, ``pm_reduce_objective``, partial sums -> pinned host.  The graph owns its buffers."""
+        """CUDA graph of one single-vector evaluation of ``ens``: pinned slots -> device, ``pm_prepare_params``,
+        ``pm_eval_reduce`` (the E(+F) kernel with the fused residual reduction, then the row sum that is also the all-reduce over
+        NVLink peer memory in multi-GPU runs), global sums -> pinned host.  The graph owns its buffers."""
         import torch
         topo = ens.topology
         g = dict(pin_in=torch.empty((1, topo.n_slots), dtype=torch.float64).pin_memory(),
@@ -542,22 +546,23 @@ class ObjectiveFunction:
         saved_bufs, saved_scratch = ens._buffers, ens._scratch
         ens._buffers, ens._scratch = g["bufs"], None
         try:
-            # allocate the graph's private buffers eagerly (same shapes as the capture will ask for), then capture
+            # allocate the graph's private buffers eagerly (same shapes as the capture will ask for), then capture.  The eager
+            # call communicates too (every rank runs it: the sequence numbers of the communicator stay in step).
+            comm = st.get("comm")
             g["slots_dev"].copy_(g["pin_in"])
             topo.prepare(g["slots_dev"], g["derived"])
-            emm, fres, _ = ens.evaluate(g["derived"], with_forces=st["need_f"], want_fres=st["need_f"])
-            ens.reduce(emm, fres, d_shift=st["d_shift"])
+            ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
             g["scratch"] = ens._scratch
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 g["slots_dev"].copy_(g["pin_in"], non_blocking=True)
                 topo.prepare(g["slots_dev"], g["derived"])
-                emm, fres, _ = ens.evaluate(g["derived"], with_forces=st["need_f"], want_fres=st["need_f"])
-                part = ens.reduce(emm, fres, d_shift=st["d_shift"])
+                part, _, _ = ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
                 g["pin_out"].copy_(part, non_blocking=True)
             g["graph"] = graph
             g["part_dev"] = part
+            g["global"] = comm is not None or _dist.world_size() == 1    # the sums in pin_out are already global
         finally:
             ens._buffers, ens._scratch = saved_bufs, saved_scratch
         return g
@@ -576,6 +581,7 @@ class ObjectiveFunction:
                      and self._weighting_method.upper() != "NON_BOLTZMANN")
         multi_rank = _dist.world_size() > 1
         graph_rows = {}
+        global_parts = {}
         for s_idx, (system, slots) in enumerate(zip(self.systems, slots_per_system)):
             st = self._system_state(s_idx, system)
             states.append(st)
@@ -593,9 +599,9 @@ class ObjectiveFunction:
                     g = st["graph"]
                     g["pin_in"].copy_(torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64)))
                     g["graph"].replay()
-                    if multi_rank:   # the partial sums stay on the device for the allreduce
+                    if not g["global"]:   # NCCL fallback: the partial sums stay on the device for the allreduce
                         partial_list.append(g["part_dev"])
-                    else:
+                    else:                 # one replay + one stream synchronisation, on one GPU as on eight
                         graph_rows[s_idx] = g["pin_out"]
                         partial_list.append("graph")
                     continue
@@ -616,6 +622,18 @@ class ObjectiveFunction:
                         st["nb_cache"] = ens.build_nonbonded_cache(derived[0:1])
                         st["nb_key"] = key
                     nb_cache = st["nb_cache"]
+            if not self._delta and nb_cache is None and self._weighting_method.upper() != "NON_BOLTZMANN":
+                # the common case: evaluation, residual reduction and (multi-GPU) the sum over ranks in one pass
+                comm = st.get("comm")
+                if comm is not None and n_vec > comm.max_vec:
+                    comm = None
+                part, _, _ = ens.evaluate_reduce(derived, with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
+                if comm is not None or not multi_rank:
+                    global_parts[s_idx] = part
+                    partial_list.append("global")
+                else:
+                    partial_list.append(part)
+                continue
             if self._delta and nb_cache is None:
                 emm, fres = self._forward_delta(st, ens, np.asarray(slots, dtype=np.float64), derived)
             else:
@@ -640,12 +658,13 @@ class ObjectiveFunction:
                 keep = r_prop.value
                 reg = np.atleast_1d(r_prop.calculate_property(X))
                 r_prop.value = keep
-        if live or graph_rows:
+        if live or graph_rows or global_parts:
             host_partials = None
             if live:
                 stacked = live[0].unsqueeze(0) if len(live) == 1 else torch.stack(live, dim=0)  # [n_live, P, 8]
-                _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective
+                _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective (NCCL / gloo fallback)
                 host_partials = stacked.cpu().numpy()
+            global_host = {i: t.cpu().numpy() for i, t in global_parts.items()}
             if graph_rows:
                 # the replays were issued on the current stream; the raw-handle comparison keeps a cached Stream object
                 # valid without paying torch.cuda.current_stream() (~15 us) on every call
@@ -659,6 +678,8 @@ class ObjectiveFunction:
             for i, p in enumerate(partial_list):
                 if p is None:
                     per_system.append(None)
+                elif isinstance(p, str) and p == "global":
+                    per_system.append(global_host[i] * 1.0)
                 elif isinstance(p, str):
                     per_system.append(graph_rows[i].numpy().copy())
                 else:

@@ -64,6 +64,16 @@ SIGNATURES = {
     "pm_reduce_objective": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_double, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_eval_reduce_scratch_doubles": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long]),
+    "pm_eval_reduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.POINTER(ctypes.c_void_p)]),
+    "pm_comm_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_comm_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "pm_comm_timeouts": (ctypes.c_long, [ctypes.c_void_p]),
+    "pm_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_resp_scratch_doubles": (ctypes.c_long, [ctypes.c_int, ctypes.c_long, ctypes.c_int]),
     "pm_resp_assemble": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -34,6 +34,15 @@ struct PmProg {
     const double *nb_e;
 };
 
+// Fused residual reduction (pm_eval_reduce): when rows != nullptr the E(+F) kernels add, per warp, the five weighted sums of
+// pm_reduce_objective over the conformations they evaluate and write one row of 5 doubles per (vector, warp of the grid).
+struct PmRed {
+    const double *eref;  // [S] reference energies or null (= 0)
+    const double *w;     // [S] weights or null (= 1)
+    double d_shift;
+    double *rows;        // [P][grid * warps][5] or null: no fused reduction
+};
+
 // =============================================================================================
 // The object behind pm_handle
 // =============================================================================================
@@ -66,7 +75,13 @@ int pm_spec_metric_changed(pm_handle h);
 int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel serves that mode
 int pm_spec_can_eval(pm_handle h, int with_forces);
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
-                 double *fres, double *fmm_t, int with_forces, cudaStream_t stream);
+                 double *fres, double *fmm_t, int with_forces, PmRed red, cudaStream_t stream);
+
+// pm_comm.cu
+int pm_comm_max_vec(pm_comm c);
+// rows [P][n_rows][5] -> partials [P][PM_NPARTIAL]; with a communicator the rows of all ranks are summed (one-shot all-reduce
+// over NVLink peer memory inside the same kernel) and every rank gets the global sums
+int pm_reduce_rows(const double *rows_dev, long n_rows, int n_vec, long n_conf, double *partials_dev, pm_comm comm, cudaStream_t stream);
 int pm_spec_can_grad(pm_handle h);
 long pm_spec_grad_scratch(pm_handle h);  // doubles
 int pm_spec_grad(pm_handle h, const double *derived_dev, const double *xt, const double *fmm_t, const double *fref_t, long n_conf,

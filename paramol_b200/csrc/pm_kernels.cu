@@ -122,6 +122,12 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     }
 }
 
+__device__ __forceinline__ double pm_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // All NL cells of one i-substituent of a "simple" axis (one torsion of periodicity 1..4 per cell) as ONE branch-free block:
 // NL independent dependency chains.  Returns A = sum_l a_il; B[q] and e_tors are accumulated in place.
 template <int NL, bool WITH_F>
@@ -175,7 +181,7 @@ template <int CPW, bool WITH_F, int MAXW, bool RF = false>
 __global__ void __launch_bounds__(MAXW * 32, 1)
     pm_ef_kernel(PmProg g, const double *__restrict__ derived, int n_vec, const double *__restrict__ xt,
                  const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm,
-                 double *__restrict__ fres, double *__restrict__ fmm_t) {
+                 double *__restrict__ fres, double *__restrict__ fmm_t, PmRed red) {
     constexpr int L = 32 / CPW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -197,8 +203,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const size_t per_warp = 128 + (size_t)tile_d * sizeof(double) * (WITH_F ? 2 : 1);
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
+    double *racc = reinterpret_cast<double *>(wbase + 64);  // fused residual reduction: this warp's 5 running sums
     double *xs = reinterpret_cast<double *>(wbase + 128);
     double *fs = xs + tile_d;  // only touched when WITH_F
+    const bool want_res = WITH_F && fref_t != nullptr;
 
     for (int i = threadIdx.x; i < g.n_int; i += blockDim.x) s_int[i] = g.ints[i];
     for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = g.acos_tab[i];
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
         const double2 *s_pangle = reinterpret_cast<const double2 *>(s_der + g.doff_angle);
         const double2 *s_ptors = reinterpret_cast<const double2 *>(s_der + g.doff_tors);
         const double *s_ppair = s_der + g.doff_pair;
+        if (red.rows != nullptr && lane < 5) racc[lane] = 0.0;
 
         for (long tile = first_tile; tile < n_tiles; tile += warp_stride) {
             // ---- coordinates of CPW conformations: one TMA bulk copy into this warp's tile ---------
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (WITH_F && nb_cached) pm_bulk_g2s(fs, g.nb_f_tiles + (size_t)tile * tile_d, tile_bytes, bar);
                 // hide HBM latency of what comes next: this tile's reference forces (read in the epilogue) and the
                 // coordinates of the next tile of this warp
-                if (WITH_F && fres != nullptr)
+                if (want_res)
                     pm_bulk_prefetch_l2(fref_t + (size_t)tile * tile_d, (uint32_t)(tile_d * sizeof(double)));
                 if (tile + warp_stride < n_tiles)
                     pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * tile_d, (uint32_t)(tile_d * sizeof(double)));
@@ -547,7 +556,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             const long sconf = tile * CPW + col;
             double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
             double res = 0.0;
-            if (WITH_F && fres != nullptr) {
+            if (want_res) {
                 const double *fr = fref_t + (size_t)tile * tile_d + col;
                 for (int a = tl; a < N; a += L) {
                     const double dx = fs[(3 * a) * CPW + col] - fr[(3 * a) * CPW];
@@ -569,14 +578,44 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 }
             }
             if (tl == 0 && sconf < n_conf) {
-                emm[(size_t)p * n_conf + sconf] = e_total;
+                if (emm != nullptr) emm[(size_t)p * n_conf + sconf] = e_total;
                 if (WITH_F && fres != nullptr) fres[(size_t)p * n_conf + sconf] = res;
+            }
+            if (red.rows != nullptr) {
+                // fused pm_reduce_objective: the five weighted sums of this tile join the warp's running sums (fixed order:
+                // deterministic for a given launch geometry); no [P][S] arrays are written or re-read
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
+                if (tl == 0 && sconf < n_conf) {
+                    const double d = (red.eref != nullptr ? red.eref[sconf] : 0.0) - e_total - red.d_shift;
+                    const double ws = red.w != nullptr ? red.w[sconf] : 1.0;
+                    q0 = d;
+                    q1 = ws * d;
+                    q2 = q1 * d;
+                    q3 = ws;
+                    q4 = ws * res;
+                }
+                q0 = pm_warp_sum(q0);
+                q1 = pm_warp_sum(q1);
+                q2 = pm_warp_sum(q2);
+                q3 = pm_warp_sum(q3);
+                q4 = pm_warp_sum(q4);
+                if (lane == 0) {
+                    racc[0] += q0;
+                    racc[1] += q1;
+                    racc[2] += q2;
+                    racc[3] += q3;
+                    racc[4] += q4;
+                }
             }
             if (WITH_F && fmm_t != nullptr) {
                 double *fo = fmm_t + ((size_t)p * n_tiles + tile) * tile_d;
                 for (int k = lane; k < tile_d; k += 32) fo[k] = fs[k];
             }
             __syncwarp();
+        }
+        if (red.rows != nullptr) {
+            __syncwarp();
+            if (lane < 5) red.rows[(((size_t)p * gridDim.x + blockIdx.x) * n_warps + warp) * 5 + lane] = racc[lane];
         }
     }
 }
@@ -626,12 +665,6 @@ __global__ void pm_unpack_kernel(const double *__restrict__ tiles, long n_conf, 
 // =============================================================================================
 #define PM_RED_BLOCKS 256
 #define PM_RED_THREADS 256
-
-__device__ __forceinline__ double pm_warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 __global__ void pm_reduce_stage1(const double *__restrict__ emm, const double *__restrict__ fres, const double *__restrict__ eref,
                                  const double *__restrict__ w, double d_shift, long n_conf, double *__restrict__ scratch) {
@@ -732,7 +765,7 @@ int pm_fail_msg(const std::string &msg) { return pm_fail(msg); }  // for the oth
         if (_e != cudaSuccess) return pm_fail(std::string(#call) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
-typedef void (*pm_ef_fn)(PmProg, const double *, int, const double *, const double *, long, long, double *, double *, double *);
+typedef void (*pm_ef_fn)(PmProg, const double *, int, const double *, const double *, long, long, double *, double *, double *, PmRed);
 
 template <int MAXW>
 static pm_ef_fn pm_pick_kernel_w(int cpw, int wf) {
@@ -1097,10 +1130,23 @@ extern "C" int pm_prepare_params(pm_handle h, const double *slots_dev, int n_vec
     return 0;
 }
 
-extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
-                          const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
-                          double *fmm_tiles_dev, int mode, const double *nb_e_dev, const double *nb_f_tiles_dev, void *stream) {
-    if (!h || !derived_dev || !coord_tiles_dev || !emm_dev) return pm_fail("pm_eval: null argument");
+// rows of the fused reduction one launch of the E(+F) kernels writes per parameter vector (one per warp of the grid)
+static long pm_red_rows(pm_handle h, int with_forces, long n_conf) {
+    const int wf = with_forces ? 1 : 0;
+    int warps = h->warps[wf];
+    pm_spec_launch_info(h, wf, nullptr, nullptr, &warps);
+    const long n_tiles = pm_n_tiles(h, n_conf);
+    long grid = h->n_sm;
+    if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
+    if (grid < 1) grid = 1;
+    return grid * warps;
+}
+
+static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                        const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
+                        double *fmm_tiles_dev, int mode, const double *nb_e_dev, const double *nb_f_tiles_dev, PmRed red,
+                        void *stream) {
+    if (!h || !derived_dev || !coord_tiles_dev || (!emm_dev && !red.rows)) return pm_fail("pm_eval: null argument");
     if (n_vec < 1 || n_conf < 1) return pm_fail("pm_eval: empty batch");
     if (fres_dev && !fref_tiles_dev) return pm_fail("pm_eval: fres requested without reference forces");
     if (!with_forces && (fres_dev || fmm_tiles_dev)) return pm_fail("pm_eval: force outputs requested with with_forces=0");
@@ -1110,9 +1156,9 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
     // Full evaluation of a small molecule: the topology-specialised kernels -- one launch (plus a constant-table copy) per
     // parameter vector, so batches over small ensembles (launch-bound: < 32768 conformations) stay on the generic kernel, which
     // loops over the vectors inside one launch.
-    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0) && (n_vec == 1 || n_conf >= 32768))
+    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0) && (n_vec == 1 || n_conf >= 32768 || red.rows))
         return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
-                            with_forces ? 1 : 0, (cudaStream_t)stream);
+                            with_forces ? 1 : 0, red, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
     const int warps = h->warps[wf];
@@ -1132,10 +1178,40 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
     }
     pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf], h->rf);
     fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(prog, derived_dev, n_vec, coord_tiles_dev,
-                                                                                fref_tiles_dev, n_conf, n_tiles, emm_dev,
-                                                                                wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr);
+                                                                                wf ? fref_tiles_dev : nullptr, n_conf, n_tiles, emm_dev,
+                                                                                wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr, red);
     PM_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                          const double *fref_tiles_dev, long n_conf, int with_forces, double *emm_dev, double *fres_dev,
+                          double *fmm_tiles_dev, int mode, const double *nb_e_dev, const double *nb_f_tiles_dev, void *stream) {
+    if (!emm_dev) return pm_fail("pm_eval: null argument");
+    // the kernels compute the force residual whenever they are given reference forces: only hand them over when it is wanted
+    return pm_eval_core(h, derived_dev, n_vec, coord_tiles_dev, fres_dev ? fref_tiles_dev : nullptr, n_conf, with_forces, emm_dev,
+                        fres_dev, fmm_tiles_dev, mode, nb_e_dev, nb_f_tiles_dev, PmRed{nullptr, nullptr, 0.0, nullptr}, stream);
+}
+
+// ---- fused evaluation + residual reduction (+ cross-GPU sum) ------------------------------------------------------
+extern "C" long pm_eval_reduce_scratch_doubles(pm_handle h, int n_vec, long n_conf) {
+    if (!h || n_vec < 1 || n_conf < 1) return -1;
+    const long r0 = pm_red_rows(h, 0, n_conf), r1 = pm_red_rows(h, 1, n_conf);
+    return (long)n_vec * (r0 > r1 ? r0 : r1) * 5;
+}
+
+extern "C" int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
+                              const double *fref_tiles_dev, long n_conf, int with_forces, const double *eref_dev,
+                              const double *weights_dev, double d_shift, double *partials_dev, double *scratch_dev, pm_comm comm,
+                              double *emm_dev, double *fres_dev, void *stream) {
+    if (!h || !partials_dev || !scratch_dev) return pm_fail("pm_eval_reduce: null argument");
+    if (!with_forces && (fref_tiles_dev || fres_dev)) return pm_fail("pm_eval_reduce: force inputs/outputs given with with_forces=0");
+    if (comm && n_vec > pm_comm_max_vec(comm)) return pm_fail("pm_eval_reduce: more parameter vectors than the communicator was created for");
+    PmRed red{eref_dev, weights_dev, d_shift, scratch_dev};
+    const int rc = pm_eval_core(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, with_forces, emm_dev, fres_dev, nullptr,
+                                0, nullptr, nullptr, red, stream);
+    if (rc) return rc;
+    return pm_reduce_rows(scratch_dev, pm_red_rows(h, with_forces, n_conf), n_vec, n_conf, partials_dev, comm, (cudaStream_t)stream);
 }
 
 extern "C" int pm_eval(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,

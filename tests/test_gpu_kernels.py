@@ -291,3 +291,46 @@ def test_empty_batches_are_refused_with_a_message(golden_dir):
         with pytest.raises(_lib.B200Error, match="empty|no conformations"):
             _lib.check(rc, what)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("name,n_conf,n_vec,weighted", [("aniline", 40000, 1, True), ("aniline", 1003, 3, False), ("aniline", 10, 1, True),
+                                                        ("lig50", 5000, 2, True), ("caffeine", 777, 1, False)])
+def test_fused_eval_reduce_equals_eval_then_reduce(golden_dir, name, n_conf, n_vec, weighted):
+    """``pm_eval_reduce`` (the E(+F) kernel with the residual reduction in its epilogue + the row-sum kernel) against
+    ``pm_eval`` followed by ``pm_reduce_objective`` on the same inputs: the eight sums per vector to 1e-12 relative (the two paths
+    add the same terms in a different order), with and without weights, generated and interpreting kernels, E+F and energy-only;
+    the optional per-conformation outputs of the fused call equal those of ``pm_eval``."""
+    import torch
+    from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(99)
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    Fref = rng.normal(0, 80.0, X.shape)
+    Eref = rng.normal(-100.0, 5.0, n_conf)
+    topo = DeviceTopology(s)
+    base = topo.slots_from_system(s)
+    slots = base[None] * (1.0 + 0.02 * rng.uniform(-1, 1, (n_vec, len(base))))
+    ens = DeviceEnsemble(topo, X, Fref, Eref)
+    if weighted:
+        w = rng.uniform(0.1, 1.0, n_conf)
+        ens.set_weights(w / w.sum())
+    derived = topo.prepare(torch.from_numpy(slots).cuda())
+    for with_forces in (True, False):
+        emm, fres, _ = ens.evaluate(derived, with_forces=with_forces, want_fres=with_forces)
+        want = ens.reduce(emm, fres if with_forces else None, d_shift=-100.0).cpu().numpy().copy()
+        emm_h = emm.cpu().numpy().copy()
+        fres_h = fres.cpu().numpy().copy() if with_forces else None
+        got, emm2, fres2 = ens.evaluate_reduce(derived, with_forces=with_forces, d_shift=-100.0, want_emm=True, want_fres=with_forces)
+        got = got.cpu().numpy()
+        scale = np.maximum(np.abs(want), 1e-300)
+        if not with_forces:
+            want[:, 4] = got[:, 4] = 0.0
+        assert np.all(np.abs(got - want) <= 1e-12 * np.maximum(scale, np.abs(want).max(axis=1, keepdims=True) * 1e-4)), (got, want)
+        # (batches over small ensembles: pm_eval interprets the topology, the fused call runs the generated kernel -> 1e-13, not bits)
+        assert np.abs(emm2.cpu().numpy() - emm_h).max() <= 1e-13 * np.abs(emm_h).max()
+        if with_forces:
+            assert np.abs(fres2.cpu().numpy() - fres_h).max() <= 1e-13 * np.abs(fres_h).max()
+        bare = ens.evaluate_reduce(derived, with_forces=with_forces, d_shift=-100.0)[0].cpu().numpy()
+        if not with_forces:
+            bare[:, 4] = 0.0
+        assert np.array_equal(bare, got)   # deterministic: same launch geometry, same order
