@@ -246,6 +246,37 @@ int pm_lls_internal(int n_atoms, const double *coords_dev, long n_conf, int n_te
 int pm_lls_columns(const double *q_dev, long n_conf, int n_terms, int n_cols, const int *col_term_dev,
                    const int *col_kind_dev, const double *col_p0_dev, const int *col_per_dev, double *a_dev, void *stream);
 
+/* ---- LLS (K3 + K4 fused): normal equations straight from the resident conformation tiles ---------------------------- */
+/* A plan holds the columns of LinearLeastSquare._calculate_a (ParaMol/MM_engines/least_square.py:469-649) as a term table: term t
+ * is the internal coordinate of one optimizable force constant (kind 0 bond a0-a1, 1 angle at a1, 2 dihedral a0-a1-a2-a3 of
+ * periodicity term_per[t], conventions of ParaMol/Utils/geometry.py) and owns term_ncol[t] = 1 or 2 consecutive columns (2: the
+ * "_x"/"_y" expansion used when the equilibrium value / phase is optimizable too).  All arrays here are HOST int32; term_atoms is
+ * [n_terms][4].  conf_per_tile: layout of the coordinates handed to the calls below -- the pm_pack_tiles layout of a pm_handle
+ * (4, 8, 16, 32) or 1 = plain [S][N][3].  The columns are generated inside the kernels; the [S][M] matrix never exists. */
+typedef struct pm_lls_s *pm_lls;
+int pm_lls_create(int device, int n_atoms, int conf_per_tile, int n_terms, const int *term_kind, const int *term_atoms,
+                  const int *term_per, const int *term_ncol, pm_lls *out);
+int pm_lls_n_cols(pm_lls p);
+/* Per column (HOST arrays [M]): p0 = r0 / theta0 / phase delta; mean (NULL = 0) is subtracted from the raw column
+ * 1/2 (q - p0)^2 or 1 + cos(n phi - delta) (the centring of least_square.py:641-645); scale (NULL = 1) multiplies the centred
+ * column (1 / scaling constant, :112-117). */
+int pm_lls_set_columns(pm_lls p, const double *p0, const double *mean, const double *scale);
+long pm_lls_scratch_doubles(pm_lls p, long n_conf);
+/* y[j] = sum_s w_s e_s (a_sj - mean_j)  (e_dev, w_dev NULL = 1: with mean = 0 these are the column sums) and, when minmax_dev
+ * != NULL, [n_terms][2] = min and max of the internal coordinate over the conformations (bonds and angles; the reference centres
+ * the angle expansion at the observed extrema, :583-586). */
+int pm_lls_colstats(pm_lls p, const double *coords_dev, long n_conf, const double *e_dev, const double *w_dev, double *y_dev,
+                    double *minmax_dev, double *scratch_dev, void *stream);
+/* e[s] = b[s] - sum_j (a_sj - mean_j) z[j]   (b_dev NULL = 0): the residual of a trial solution z in parameter units. */
+int pm_lls_residual(pm_lls p, const double *coords_dev, long n_conf, const double *z_dev, const double *b_dev, double *e_dev,
+                    void *stream);
+/* g[(M+1)][(M+1)] = [A b]^T [A b] with A_sj = rowscale_s * scale_j * (a_sj - mean_j) and b_s = rowscale_s * b_dev[s] as column M
+ * (rowscale_dev NULL = 1; b_dev NULL = 0): the weighted normal equations A^T W A, A^T W b and b^T W b of
+ * least_square.py:104-135 in one pass on the FP64 tensor-core instruction.  Multi-GPU: add the g of the ranks (one all-reduce). */
+int pm_lls_normal(pm_lls p, const double *coords_dev, long n_conf, const double *rowscale_dev, const double *b_dev, double *g_dev,
+                  double *scratch_dev, void *stream);
+int pm_lls_destroy(pm_lls p);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Measured FMA-pipe peak of the current device: runs a register-only FMA kernel and returns FLOP/s
  * (2 flop per FMA) in *flops and the kernel time in *ms.  fp64 = 1: DFMA, 0: FFMA. */

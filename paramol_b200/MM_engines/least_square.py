@@ -9,18 +9,21 @@ expansions, of equilibrium values and torsion phases), with the public surface o
 
 What changes underneath:
 
-* the design matrix (reference ``:469-649``: a Python loop over every conformation for every column) is two kernels --
-  ``pm_lls_internal`` (bond lengths / angles / dihedrals with the conventions of ``ParaMol/Utils/geometry.py``) and
-  ``pm_lls_columns`` (1/2 (q - q0)^2 and 1 + cos(n phi - delta)) -- on device-resident coordinates;
-* the right-hand side (reference ``:651-692``) is one energy-only launch of the E+F kernel with the optimizable
-  parameters zeroed;
-* the tall least-squares problem is reduced ON THE DEVICE to the QR factors (R, Q^T b) of the weighted, centred, scaled
-  [S, M] matrix (``_reduce_tall``: CholeskyQR2, Householder ``torch.linalg.qr`` when that breaks down; FP64 library
-  calls); the regularisation and symmetry rows are appended to
-  the M x M triangular factor and the small stacked system goes through ``np.linalg.lstsq`` exactly as the reference's
-  full system does.  Since ||A x - b||^2 = ||R x - Q^T b||^2 + const for every x, both systems have the same
-  (minimum-norm) minimiser; the solve itself never uses the normal equations, which would square the condition number.
-* multi-GPU: every rank factorises its shard, the R factors are gathered (TSQR).
+* the design matrix (reference ``:469-649``: a Python loop over every conformation for every column) is never stored: the
+  fused kernels of ``csrc/pm_lls_kernels.cu`` generate its columns -- internal coordinates with the conventions of
+  ``ParaMol/Utils/geometry.py``, then 1/2 (q - q0)^2 and 1 + cos(n phi - delta), centred, weighted and scaled -- from the
+  conformation tiles that are already resident on the device (the same tiles the E+F kernels read) and contract them on the spot:
+  ``pm_lls_colstats`` (column means, observed extrema of the angles), ``pm_lls_normal`` (G = [A b]^T W [A b] on the FP64
+  tensor-core instruction) and ``pm_lls_residual`` (b - A x);
+* the right-hand side (reference ``:651-692``) is one energy-only launch of the E+F kernel with the optimizable parameters zeroed;
+* the (M x M) normal equations -- plus the regularisation and symmetry rows of the reference (``:253-337``) as E^T E -- are solved
+  by Cholesky factorisation and polished by iterative refinement against the TRUE residual b - A x (two more passes over the
+  tiles per step), which removes the squared condition number from the error of the solution as long as the factorisation is
+  usable as a preconditioner (kappa(A) <~ 1e7); when Cholesky breaks down or the refinement does not contract, the fit falls back to
+  the orthogonal route of round 1 (``_reduce_tall``: materialised matrix, CholeskyQR2 / Householder, host ``lstsq``: the
+  minimum-norm solution of the reference for rank-deficient systems).  ``self.reduction`` records which route ran;
+* multi-GPU: every rank contracts its shard; column sums, extrema, G and the refinement gradients are summed with one all-reduce
+  each.
 """
 import copy
 import ctypes
@@ -34,6 +37,70 @@ from ..Utils import dist as _dist
 def _torch():
     import torch
     return torch
+
+
+class LlsPlan:
+    """``pm_lls`` handle bound to the resident conformation tiles of a :obj:`paramol_b200.MM_engines.device.DeviceEnsemble`."""
+
+    def __init__(self, ensemble, kinds, atoms, pers, ncols):
+        torch = _torch()
+        self._L = _lib.lib()
+        self.ens = ensemble
+        self.device = ensemble.device
+        self.n_conf = int(ensemble.n_conf)
+        self.n_terms = len(kinds)
+        arr = [np.ascontiguousarray(a, dtype=np.int32) for a in (kinds, np.asarray(atoms).reshape(-1, 4), pers, ncols)]
+        h = ctypes.c_void_p()
+        topo = ensemble.topology
+        _lib.check(self._L.pm_lls_create(self.device.index, int(topo.n_atoms), int(topo.conf_per_tile), self.n_terms,
+                                         arr[0].ctypes.data, arr[1].ctypes.data, arr[2].ctypes.data, arr[3].ctypes.data, ctypes.byref(h)),
+                   "pm_lls_create")
+        self._h = h
+        self.n_cols = int(self._L.pm_lls_n_cols(h))
+        self.means = None
+        self._scratch = torch.empty(int(self._L.pm_lls_scratch_doubles(h, self.n_conf)), dtype=torch.float64, device=self.device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.pm_lls_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def set_columns(self, p0, mean, scale):
+        a = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in (p0, mean, scale)]
+        assert all(v is None or v.shape == (self.n_cols,) for v in a)
+        _lib.check(self._L.pm_lls_set_columns(self._h, *[None if v is None else v.ctypes.data for v in a]), "pm_lls_set_columns")
+
+    def colstats(self, e, w, want_minmax=False):
+        """(y [M] = sum_s w_s e_s (a_sj - mean_j), min/max [T, 2] or None) over this rank's conformations (CUDA tensors)."""
+        torch = _torch()
+        y = torch.empty(self.n_cols, dtype=torch.float64, device=self.device)
+        mm = torch.empty((self.n_terms, 2), dtype=torch.float64, device=self.device) if want_minmax else None
+        _lib.check(self._L.pm_lls_colstats(self._h, self.ens.coord_tiles.data_ptr(), self.n_conf, None if e is None else e.data_ptr(),
+                                           None if w is None else w.data_ptr(), y.data_ptr(), None if mm is None else mm.data_ptr(),
+                                           self._scratch.data_ptr(), self._stream()), "pm_lls_colstats")
+        return y, mm
+
+    def residual(self, z, b):
+        torch = _torch()
+        e = torch.empty(self.n_conf, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.pm_lls_residual(self._h, self.ens.coord_tiles.data_ptr(), self.n_conf, z.data_ptr(),
+                                           None if b is None else b.data_ptr(), e.data_ptr(), self._stream()), "pm_lls_residual")
+        return e
+
+    def normal(self, row_scale, b):
+        torch = _torch()
+        n = self.n_cols + 1
+        g = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        _lib.check(self._L.pm_lls_normal(self._h, self.ens.coord_tiles.data_ptr(), self.n_conf,
+                                         None if row_scale is None else row_scale.data_ptr(), None if b is None else b.data_ptr(),
+                                         g.data_ptr(), self._scratch.data_ptr(), self._stream()), "pm_lls_normal")
+        return g
 
 
 class LinearLeastSquare:
@@ -73,6 +140,9 @@ class LinearLeastSquare:
         self._A_dev = None
         self.mm_energies_zero = None
         self.reduction = None
+        self.refinement_steps = 0
+        self.timings = {}
+        self._plan = None
 
     # ------------------------------------------------------------------------------------------
     #                                       PUBLIC METHODS
@@ -81,30 +151,61 @@ class LinearLeastSquare:
         """Fits the optimizable bonded parameters of ``systems[0]`` (reference ``:68-146``); returns the parameter vector."""
         assert self._weighting_method.upper() != "NON_BOLTZMANN", \
             "LLS does not support {} weighting method.".format(self._weighting_method)
+        import time
         torch = _torch()
         system = systems[0]
-        A = self._calculate_a_device(system, alpha_bond, alpha_angle)
-        self._n_parameters = A.shape[1]
-        B = torch.from_numpy(self._calculate_b(system)).to(A.device)
+        self.timings = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            self.timings[name] = self.timings.get(name, 0.0) + (t1 - t0)
+            t0 = t1
+
+        plan = self._device_plan(system, alpha_bond, alpha_angle)          # term table, centres, column means
+        lap("plan_and_means_s")
+        self._n_parameters = plan.n_cols
+        dev = plan.device
+        B = torch.from_numpy(self._calculate_b(system)).to(dev)
+        lap("rhs_s")
         system.compute_conformations_weights(temperature=self._weighting_temperature, weighting_method=self._weighting_method,
                                              emm=None)
         var = self._global_variance(np.asarray(system.ref_energies, dtype=np.float64))
         row_scale = torch.from_numpy(np.sqrt(np.asarray(system.weights, dtype=np.float64) * np.ones(system.n_structures))
-                                     / np.sqrt(var)).to(A.device)
+                                     / np.sqrt(var)).to(dev)
         self._calculate_scaling_constants()
-        col_scale = torch.from_numpy(1.0 / self._scaling_constants).to(A.device)
-        A = A * row_scale[:, None] * col_scale[None, :]
-        B = B * row_scale
-        # device-side reduction of the tall problem: A = Q R
-        R, qtb = self._reduce_tall(A, B)
-        R_all, qtb_all = self._gather_factors(R, qtb)
-        self._A = R_all
-        self._B = qtb_all
+        col_scale = 1.0 / self._scaling_constants
+        plan.set_columns(self._p0, plan.means, col_scale)
+        G = plan.normal(row_scale, B)                                        # [(M+1), (M+1)] = [A b]^T W [A b], this rank's shard
+        _dist.allreduce_sum_tensor_(G)                                       # the one data-path collective of the fit
+        G = G.cpu().numpy()
+        lap("normal_equations_s")
+        M = self._n_parameters
+        # regularisation and symmetry rows of the reference, collected as E x = f
+        self._A, self._B = np.zeros((0, M)), np.zeros(0)
         if self._include_regularization:
-            self._A, self._B = self._add_regularization()
+            self._add_regularization()
         self._add_symmetries(system)
-        self._parameters = np.linalg.lstsq(self._A, self._B, rcond=None)[0]
-        self._parameters = self._parameters / self._scaling_constants
+        E, f = self._A, self._B
+        N = G[:M, :M] + E.T @ E
+        rhs = G[:M, M] + E.T @ f
+        x = self._solve_refined(plan, N, rhs, E, f, row_scale, B, col_scale)
+        lap("solve_and_refine_s")
+        if x is None:
+            # accuracy fallback: the orthogonal reduction of the materialised matrix and the reference's own lstsq
+            A = self._calculate_a_device(system, alpha_bond, alpha_angle)
+            A = A * row_scale[:, None] * torch.from_numpy(col_scale).to(dev)[None, :]
+            R, qtb = self._reduce_tall(A, B * row_scale)
+            R_all, qtb_all = self._gather_factors(R, qtb)
+            self._A = np.vstack((R_all, E))
+            self._B = np.concatenate((qtb_all, f))
+            x = np.linalg.lstsq(self._A, self._B, rcond=None)[0]
+            lap("fallback_s")
+        else:
+            self._A, self._B = N, rhs
+        self._parameters = x / self._scaling_constants
         self._reconstruct_parameters(self._parameters)
         self._parameter_space.get_optimizable_parameters([system], symmetry_constrained=False)
         return self._parameter_space.optimizable_parameters_values
@@ -257,6 +358,129 @@ class LinearLeastSquare:
             elif parameter.param_key not in ["torsion_phase", "bond_eq", "angle_eq"]:
                 raise NotImplementedError("Fitting of {} not implemented in LLS.".format(parameter.param_key))
         return
+
+    # ---- fused path ---------------------------------------------------------------------------------------
+    #: iterative refinement: accepted when a correction is below this fraction of the solution ...
+    REFINE_TOL = 1e-13
+    #: ... within this many steps, every step contracting at least by REFINE_MIN_CONTRACTION
+    REFINE_MAX_STEPS = 4
+    REFINE_MIN_CONTRACTION = 0.1
+
+    def _solve_refined(self, plan, N, rhs, E, f, row_scale, B, col_scale):
+        """
+        Solution of min || diag(row_scale) (A x - b) ||^2 + || E x - f ||^2 from the normal matrix N = A^T W A + E^T E: Cholesky
+        solve, then iterative refinement with the residual recomputed from the tiles (``pm_lls_residual`` + ``pm_lls_colstats``), so
+        the error of the solution is governed by kappa(A), not kappa(A)^2.  Returns None when the factorisation fails or the
+        refinement does not contract (ill-conditioned or rank-deficient systems: the caller takes the orthogonal route).
+        """
+        import scipy.linalg
+        torch = _torch()
+        self.reduction = "householder"
+        self.refinement_steps = 0
+        if not np.all(np.isfinite(N)) or not np.all(np.isfinite(rhs)):
+            return None
+        try:
+            c = scipy.linalg.cho_factor(N, lower=True, check_finite=False)
+        except (np.linalg.LinAlgError, scipy.linalg.LinAlgError, ValueError):
+            return None
+        x = scipy.linalg.cho_solve(c, rhs, check_finite=False)
+        w2 = row_scale * row_scale
+        cs = torch.from_numpy(np.ascontiguousarray(col_scale)).to(row_scale.device)
+        last = None
+        for step in range(self.REFINE_MAX_STEPS):
+            z = torch.from_numpy(np.ascontiguousarray(x * col_scale)).to(row_scale.device)   # parameter units
+            e = plan.residual(z, B)
+            y = plan.colstats(e, w2)[0] * cs
+            _dist.allreduce_sum_tensor_(y)
+            grad = y.cpu().numpy() + E.T @ (f - E @ x)
+            dx = scipy.linalg.cho_solve(c, grad, check_finite=False)
+            size = float(np.abs(dx).max()) / max(float(np.abs(x).max()), 1e-300)
+            if not np.isfinite(size) or (last is not None and size > self.REFINE_MIN_CONTRACTION * last and size > self.REFINE_TOL):
+                return None
+            x = x + dx
+            self.refinement_steps = step + 1
+            if size <= self.REFINE_TOL:
+                self.reduction = "normal_equations_refined"
+                return x
+            last = size
+        return None
+
+    def _term_table(self, alpha_bond, alpha_angle):
+        """(kinds, atoms, periodicities, columns per term, owners) of the optimizable force constants, in column order."""
+        kinds, atoms, pers, ncols, owners = [], [], [], [], []
+        partner_key = {"bond_k": ("bond_eq", 0), "angle_k": ("angle_eq", 1), "torsion_k": ("torsion_phase", 2)}
+        for parameter in self._parameter_space.optimizable_parameters:
+            if parameter.param_key in partner_key:
+                key, kind = partner_key[parameter.param_key]
+                kinds.append(kind)
+                at = list(parameter.ff_term.atoms) + [0, 0, 0]
+                atoms.append(at[:4])
+                pers.append(int(parameter.ff_term.parameters["torsion_periodicity"].value) if kind == 2 else 0)
+                ncols.append(2 if parameter.ff_term.parameters[key].optimize else 1)
+                owners.append(parameter)
+            elif parameter.param_key not in ["torsion_phase", "bond_eq", "angle_eq"]:
+                raise NotImplementedError("Fitting of {} not implemented in LLS.".format(parameter.param_key))
+        assert owners, "No bonded force constant is optimizable."
+        return kinds, atoms, pers, ncols, owners
+
+    def _column_centres(self, owners, kinds, q_min, q_max, alpha_bond):
+        """Fills the per-column bookkeeping lists of the reference (``:486-640``) and returns the centres p0 [M]."""
+        self._initial_param_regularization = []
+        self._param_keys_list = []
+        self._p0 = []
+        self._param_symmetries_list = []
+        partner_key = {"bond_k": "bond_eq", "angle_k": "angle_eq", "torsion_k": "torsion_phase"}
+        for t, parameter in enumerate(owners):
+            partner = parameter.ff_term.parameters[partner_key[parameter.param_key]]
+            kind = kinds[t]
+            if partner.optimize:
+                if kind == 0:
+                    centres = [partner.value * (1 - alpha_bond), partner.value * (1 + alpha_bond)]
+                elif kind == 1:
+                    centres = [float(q_min[t]), float(q_max[t])]
+                else:
+                    centres = [-np.pi / 4, np.pi / 4]
+                tags = ["_x", "_y"]
+            else:
+                centres = [partner.value]
+                tags = [""]
+            for centre, tag in zip(centres, tags):
+                self._p0.append(centre)
+                self._param_keys_list.append(parameter.param_key)
+                self._initial_param_regularization.append(parameter.value)
+                self._param_symmetries_list.append(parameter.symmetry_group + tag)
+        self._initial_param_regularization = np.asarray(self._initial_param_regularization)
+        return np.asarray(self._p0, dtype=np.float64)
+
+    def _device_plan(self, system, alpha_bond, alpha_angle):
+        """``pm_lls`` plan of the fit on the resident tiles of ``system``: terms, centres (angles: the GLOBAL observed extrema) and
+        the global column means."""
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.B200Error("no CUDA device is visible: the B200 path has no CPU fallback")
+        kinds, atoms, pers, ncols, owners = self._term_table(alpha_bond, alpha_angle)
+        ens = system.device_ensemble()
+        plan = LlsPlan(ens, kinds, atoms, pers, ncols)
+        # pass 1: observed extrema of the internal coordinates (only the angle expansion needs them)
+        q_min = q_max = np.zeros(len(kinds))
+        if any(k == 1 and n == 2 for k, n in zip(kinds, ncols)):
+            plan.set_columns(np.zeros(plan.n_cols), None, None)
+            _, mm = plan.colstats(None, None, want_minmax=True)
+            lo, hi = mm[:, 0].contiguous(), mm[:, 1].contiguous()
+            _dist.allreduce_min_tensor_(lo)
+            hi = -_dist.allreduce_min_tensor_(-hi)
+            q_min, q_max = lo.cpu().numpy(), hi.cpu().numpy()
+        p0 = self._column_centres(owners, kinds, q_min, q_max, alpha_bond)
+        # pass 2: column sums -> global means
+        plan.set_columns(p0, None, None)
+        sums = plan.colstats(None, None)[0]
+        count = float(ens.n_conf)
+        if _dist.world_size() > 1:
+            sums = _dist.allreduce_sum_tensor_(sums)
+            count = float(_dist.allreduce_sum_numpy(np.array([count]))[0])
+        plan.means = sums.cpu().numpy() / count
+        self._plan = plan
+        return plan
 
     # ---- design matrix ----------------------------------------------------------------------------------
     def _calculate_a_device(self, system, alpha_bond=None, alpha_angle=None):

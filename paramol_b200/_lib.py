@@ -74,6 +74,18 @@ SIGNATURES = {
     "pm_comm_allreduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "pm_comm_timeouts": (ctypes.c_long, [ctypes.c_void_p]),
     "pm_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "pm_lls_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "pm_lls_n_cols": (ctypes.c_int, [ctypes.c_void_p]),
+    "pm_lls_set_columns": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_lls_scratch_doubles": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_long]),
+    "pm_lls_colstats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_lls_residual": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "pm_lls_normal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_lls_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_resp_scratch_doubles": (ctypes.c_long, [ctypes.c_int, ctypes.c_long, ctypes.c_int]),
     "pm_resp_assemble": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -34,8 +34,10 @@ struct PmProg {
     const double *nb_e;
 };
 
-// Fused residual reduction (pm_eval_reduce): when rows != nullptr the E(+F) kernels add, per warp, the five weighted sums of
-// pm_reduce_objective over the conformations they evaluate and write one row of 5 doubles per (vector, warp of the grid).
+// Fused residual reduction (pm_eval_reduce): when rows != nullptr the topology-interpreting E(+F) kernel adds, per warp, the five
+// weighted sums of pm_reduce_objective over the conformations it evaluates and writes one row of 5 doubles per (vector, warp of
+// the grid).  (The generated kernels keep their round-1 form -- per-conformation energy and residual out, summed by
+// pm_reduce_stage1: any epilogue added to their 13k-instruction straight-line body cost 5-8 % of the kernel, measured.)
 struct PmRed {
     const double *eref;  // [S] reference energies or null (= 0)
     const double *w;     // [S] weights or null (= 1)
@@ -75,7 +77,7 @@ int pm_spec_metric_changed(pm_handle h);
 int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel serves that mode
 int pm_spec_can_eval(pm_handle h, int with_forces);
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
-                 double *fres, double *fmm_t, int with_forces, PmRed red, cudaStream_t stream);
+                 double *fres, double *fmm_t, int with_forces, cudaStream_t stream);
 
 // pm_comm.cu
 int pm_comm_max_vec(pm_comm c);

@@ -1130,16 +1130,22 @@ extern "C" int pm_prepare_params(pm_handle h, const double *slots_dev, int n_vec
     return 0;
 }
 
-// rows of the fused reduction one launch of the E(+F) kernels writes per parameter vector (one per warp of the grid)
+// rows of the fused reduction one launch of the interpreting E(+F) kernel writes per parameter vector (one per warp of the grid)
 static long pm_red_rows(pm_handle h, int with_forces, long n_conf) {
     const int wf = with_forces ? 1 : 0;
-    int warps = h->warps[wf];
-    pm_spec_launch_info(h, wf, nullptr, nullptr, &warps);
+    const int warps = h->warps[wf];
     const long n_tiles = pm_n_tiles(h, n_conf);
     long grid = h->n_sm;
     if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
     if (grid < 1) grid = 1;
     return grid * warps;
+}
+
+// full evaluations of a small molecule go to the generated kernels: one launch (plus a constant-table copy) per parameter vector,
+// so batches over small ensembles (launch-bound: < 32768 conformations) stay on the interpreter, which loops over the vectors
+// inside one launch
+static bool pm_use_spec(pm_handle h, int with_forces, int n_vec, long n_conf, int mode) {
+    return mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0) && (n_vec == 1 || n_conf >= 32768);
 }
 
 static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
@@ -1150,23 +1156,18 @@ static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const
     if (n_vec < 1 || n_conf < 1) return pm_fail("pm_eval: empty batch");
     if (fres_dev && !fref_tiles_dev) return pm_fail("pm_eval: fres requested without reference forces");
     if (!with_forces && (fres_dev || fmm_tiles_dev)) return pm_fail("pm_eval: force outputs requested with with_forces=0");
-    if (mode < 0 || mode > 2) return pm_fail("pm_eval_ex: mode must be 0 (all terms), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
-    if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval_ex: mode 2 needs the cached nonbonded arrays");
+    if (mode < 0 || mode > 2) return pm_fail("pm_eval: mode must be 0 (full), 1 (nonbonded only) or 2 (bonded + cached nonbonded)");
+    if (mode == 2 && (!nb_e_dev || (with_forces && !nb_f_tiles_dev))) return pm_fail("pm_eval: mode 2 needs the nonbonded cache");
     PM_CUDA(cudaSetDevice(h->device));
-    // Full evaluation of a small molecule: the topology-specialised kernels -- one launch (plus a constant-table copy) per
-    // parameter vector, so batches over small ensembles (launch-bound: < 32768 conformations) stay on the generic kernel, which
-    // loops over the vectors inside one launch.
-    if (mode == 0 && pm_spec_can_eval(h, with_forces ? 1 : 0) && (n_vec == 1 || n_conf >= 32768 || red.rows))
+    if (!red.rows && pm_use_spec(h, with_forces, n_vec, n_conf, mode))
         return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
-                            with_forces ? 1 : 0, red, (cudaStream_t)stream);
+                            with_forces ? 1 : 0, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
     const int warps = h->warps[wf];
-    long grid = h->n_sm;  // persistent: one CTA per SM; never more warps than tiles
-    if ((long)grid * warps > n_tiles) {
-        grid = (n_tiles + warps - 1) / warps;
-        if (grid < 1) grid = 1;
-    }
+    long grid = h->n_sm;
+    if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
+    if (grid < 1) grid = 1;
     PmProg prog = h->prog;
     if (mode == 1) {
         prog.n_star_steps = 0;
@@ -1194,10 +1195,19 @@ extern "C" int pm_eval_ex(pm_handle h, const double *derived_dev, int n_vec, con
 }
 
 // ---- fused evaluation + residual reduction (+ cross-GPU sum) ------------------------------------------------------
+static int pm_stage1_blocks(long n_conf) {
+    const long need = (n_conf + PM_RED_THREADS - 1) / PM_RED_THREADS;
+    return (int)(need < PM_RED_BLOCKS ? (need < 1 ? 1 : need) : PM_RED_BLOCKS);
+}
+
 extern "C" long pm_eval_reduce_scratch_doubles(pm_handle h, int n_vec, long n_conf) {
     if (!h || n_vec < 1 || n_conf < 1) return -1;
     const long r0 = pm_red_rows(h, 0, n_conf), r1 = pm_red_rows(h, 1, n_conf);
-    return (long)n_vec * (r0 > r1 ? r0 : r1) * 5;
+    long rows = r0 > r1 ? r0 : r1;
+    if (rows < PM_RED_BLOCKS) rows = PM_RED_BLOCKS;
+    // generated kernels: per-conformation energies and residuals of the batch are staged behind the rows
+    const long stage = (pm_spec_can_eval(h, 0) || pm_spec_can_eval(h, 1)) ? 2L * n_vec * n_conf : 0L;
+    return (long)n_vec * rows * 5 + stage;
 }
 
 extern "C" int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev,
@@ -1205,8 +1215,26 @@ extern "C" int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec,
                               const double *weights_dev, double d_shift, double *partials_dev, double *scratch_dev, pm_comm comm,
                               double *emm_dev, double *fres_dev, void *stream) {
     if (!h || !partials_dev || !scratch_dev) return pm_fail("pm_eval_reduce: null argument");
+    if (n_vec < 1 || n_conf < 1) return pm_fail("pm_eval_reduce: empty batch");
     if (!with_forces && (fref_tiles_dev || fres_dev)) return pm_fail("pm_eval_reduce: force inputs/outputs given with with_forces=0");
     if (comm && n_vec > pm_comm_max_vec(comm)) return pm_fail("pm_eval_reduce: more parameter vectors than the communicator was created for");
+    if (pm_use_spec(h, with_forces, n_vec, n_conf, 0)) {
+        // generated kernel (round-1 form: energy and residual per conformation) -> stage-1 sums as rows -> row sum (+ all-reduce)
+        const long r0 = pm_red_rows(h, 0, n_conf), r1 = pm_red_rows(h, 1, n_conf);
+        long rows = r0 > r1 ? r0 : r1;
+        if (rows < PM_RED_BLOCKS) rows = PM_RED_BLOCKS;
+        double *stage = scratch_dev + (size_t)n_vec * rows * 5;
+        double *e_buf = emm_dev ? emm_dev : stage;
+        double *r_buf = fref_tiles_dev ? (fres_dev ? fres_dev : stage + (size_t)n_vec * n_conf) : nullptr;
+        int rc = pm_eval_core(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, with_forces, e_buf, r_buf, nullptr, 0, nullptr,
+                              nullptr, PmRed{nullptr, nullptr, 0.0, nullptr}, stream);
+        if (rc) return rc;
+        const int nb = pm_stage1_blocks(n_conf);
+        pm_reduce_stage1<<<dim3(nb, n_vec), PM_RED_THREADS, 0, (cudaStream_t)stream>>>(e_buf, r_buf, eref_dev, weights_dev, d_shift, n_conf,
+                                                                                     scratch_dev);
+        PM_CUDA(cudaGetLastError());
+        return pm_reduce_rows(scratch_dev, nb, n_vec, n_conf, partials_dev, comm, (cudaStream_t)stream);
+    }
     PmRed red{eref_dev, weights_dev, d_shift, scratch_dev};
     const int rc = pm_eval_core(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, with_forces, emm_dev, fres_dev, nullptr,
                                 0, nullptr, nullptr, red, stream);

@@ -155,7 +155,7 @@ int pm_spec_can_eval(pm_handle h, int with_forces) {
 }
 
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf,
-                 double *emm, double *fres, double *fmm_t, int with_forces, PmRed red, cudaStream_t stream) {
+                 double *emm, double *fres, double *fmm_t, int with_forces, cudaStream_t stream) {
     PmSpecState *st = (PmSpecState *)h->spec_state;
     const cudaKernel_t kernel = with_forces ? st->kernel : st->kernel_e;
     const int warps = with_forces ? st->warps : st->warps_e;
@@ -170,11 +170,9 @@ int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double
     for (int p = 0; p < n_vec; ++p) {
         // the parameters of this vector become constant-bank operands of the kernel
         PMS_CUDA(cudaMemcpyAsync(st->tab_dev, derived_dev + (size_t)p * h->prog.n_derived, sizeof(double) * nd, cudaMemcpyDeviceToDevice, stream));
-        double *e_p = emm ? emm + (size_t)p * n_conf : nullptr, *r_p = fres ? fres + (size_t)p * n_conf : nullptr;
+        double *e_p = emm + (size_t)p * n_conf, *r_p = fres ? fres + (size_t)p * n_conf : nullptr;
         double *f_p = fmm_t ? fmm_t + (size_t)p * n_tiles * tile_d : nullptr;
-        double *rows_p = red.rows ? red.rows + (size_t)p * grid * warps * 5 : nullptr;
-        void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p,
-                        (void *)&red.eref, (void *)&red.w, (void *)&red.d_shift, (void *)&rows_p};
+        void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p};
         PMS_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
     }
     return 0;

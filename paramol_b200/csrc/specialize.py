@@ -301,8 +301,7 @@ _KERNEL = r'''
 extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     {name}(const double2 *__restrict__ acos_tab, const double *__restrict__ xt,
            const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm, double *__restrict__ fres,
-           double *__restrict__ fmm_t, const double *__restrict__ red_eref, const double *__restrict__ red_w, double red_shift,
-           double *__restrict__ red_rows) {{
+           double *__restrict__ fmm_t) {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
@@ -311,7 +310,6 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
     uint64_t *bar_r = bar + 1;
-    double *racc = reinterpret_cast<double *>(wbase + 64);   // fused residual reduction: this warp's five running sums
     double *xs = reinterpret_cast<double *>(wbase + 128);
     double *fs = xs + ({x_tile} ? TILE_D : 0);
     double *rs = fs + {f_doubles};
@@ -323,8 +321,6 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
         pm_mbar_init(bar_r, 1);
         pm_fence_mbar_init();
     }}
-    if (lane < 5) racc[lane] = 0.0;
-    const bool want_res = fref_t != nullptr;
     __syncthreads();
     uint32_t parity = 0, parity_r = 0;
     const long warp_stride = (long)gridDim.x * n_warps;
@@ -347,16 +343,16 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
             if ({PF}) {{
                 // reference forces of this tile into the second buffer while the body runs (the buffer was last read in the
                 // previous iteration's epilogue, before its closing __syncwarp)
-                if ({PFR} && want_res) {{
+                if ({PFR} && fres != nullptr) {{
                     pm_fence_proxy_async();
                     pm_mbar_expect_tx(bar_r, (uint32_t)(TILE_D * sizeof(double)));
                     pm_bulk_g2s(rs, fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar_r);
-                }} else if (want_res) {{
+                }} else if (fres != nullptr) {{
                     pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 }}
                 if (tile + warp_stride < n_tiles) {{
                     pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
-                    if (want_res) pm_bulk_prefetch_l2(fref_t + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                    if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 }}
             }} else {{
                 if ({x_tile}) {{
@@ -364,7 +360,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
                     pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
                     pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
                 }}
-                if (want_res) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 if (tile + warp_stride < n_tiles) pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
             }}
         }}
@@ -396,7 +392,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
         const long sconf = tile * 32 + lane;
         const double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
         double res = 0.0;
-        if (want_res) {{
+        if (fres != nullptr) {{
             if ({PFR}) {{
                 pm_mbar_wait(bar_r, parity_r);
                 parity_r ^= 1;
@@ -407,36 +403,8 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
             }}
         }}
         if (live && sconf < n_conf) {{
-            if (emm != nullptr) emm[sconf] = e_total;
+            emm[sconf] = e_total;
             if (fres != nullptr) fres[sconf] = res;
-        }}
-        if (red_rows != nullptr) {{
-            // fused pm_reduce_objective (see pm_ef_kernel): the tile's five weighted sums join the warp's running sums
-            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
-            if (live && sconf < n_conf) {{
-                const double d = (red_eref != nullptr ? red_eref[sconf] : 0.0) - e_total - red_shift;
-                const double ws = red_w != nullptr ? red_w[sconf] : 1.0;
-                q0 = d;
-                q1 = ws * d;
-                q2 = q1 * d;
-                q3 = ws;
-                q4 = ws * res;
-            }}
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {{
-                q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-                q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-                q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-                q3 += __shfl_xor_sync(0xffffffffu, q3, o);
-                q4 += __shfl_xor_sync(0xffffffffu, q4, o);
-            }}
-            if (lane == 0) {{
-                racc[0] += q0;
-                racc[1] += q1;
-                racc[2] += q2;
-                racc[3] += q3;
-                racc[4] += q4;
-            }}
         }}
         if (live && fmm_t != nullptr) {{
             double *fo = fmm_t + (size_t)tile * TILE_D + lane;
@@ -445,10 +413,6 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
             }}
         }}
         __syncwarp();
-    }}
-    if (red_rows != nullptr) {{
-        __syncwarp();
-        if (lane < 5) red_rows[((size_t)blockIdx.x * n_warps + warp) * 5 + lane] = racc[lane];
     }}
 }}
 '''

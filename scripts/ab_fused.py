@@ -15,6 +15,10 @@ if name.startswith("lig"):
     s, x0 = make_ligand(int(name[3:]))
 else:
     s = system_from_prmtop(os.path.join(G, name + ".prmtop")); x0 = read_inpcrd(os.path.join(G, name + ".inpcrd"))
+if os.environ.get("AB_OLD_IMAGE"):   # A/B against an image built by an earlier generator (E+F kernel only, forces in registers, 8 warps)
+    from paramol_b200.csrc import specialize
+    blob = open(os.environ["AB_OLD_IMAGE"], "rb").read()
+    specialize.image_for = lambda *a, **k: (blob, 8, 0, 0, 0)
 topo = DeviceTopology(s)
 g = torch.Generator(device="cuda").manual_seed(1)
 x0 = np.asarray(x0, dtype=np.float64).reshape(-1, 3)

@@ -128,8 +128,8 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
     from paramol_b200.Utils.synthetic import perturbed_conformations
     from paramol_b200.Utils.netcdf_lite import read_paramol_data
     X10 = read_paramol_data(os.path.join(golden_dir, "aniline_10_struct.nc"))[0]
-    # the tall problem is reduced by CholeskyQR2 when the design matrix allows it and by Householder QR otherwise (forced
-    # in the third case): the fit must not depend on which one ran
+    # the fit runs on the fused normal-equation kernels with iterative refinement, and on the orthogonal route (materialised
+    # matrix, QR) when that is refused (forced in the third case): the result must not depend on which one ran
     for eq_opt, force_householder in ((False, False), (True, False), (True, True)):
         engine = B200Engine(True, **kwargs_dict)
         system = ParaMolSystem("aniline", engine, 14)
@@ -172,11 +172,12 @@ def test_lls_design_matrix_and_fit_vs_numpy(kwargs_dict, golden_dir):
         Bfull = np.concatenate([Bw, alpha * init])
         want = np.linalg.lstsq(Afull, Bfull, rcond=None)[0] / sc
         assert np.allclose(np.asarray(ps.optimizable_parameters_values), x_before)
-        if force_householder:
+        if force_householder:     # refuse the refined normal-equation solve AND CholeskyQR2: the orthogonal fallback must agree
+            lls.REFINE_MAX_STEPS = 0
             lls.CHOLESKY_QR_MAX_DEFECT = 0.0
         fitted = lls.fit_parameters_lls([system])
         got = lls._parameters
-        assert lls.reduction in ("cholesky_qr2", "householder") and (lls.reduction == "householder" or not force_householder)
+        assert lls.reduction == ("householder" if force_householder else "normal_equations_refined"), lls.reduction
         assert np.abs(got - want).max() <= 1e-7 * np.abs(want).max(), (lls.reduction, np.abs(got - want).max())
         assert len(fitted) == len(x_before)
 
@@ -263,8 +264,28 @@ def test_lls_config4_shape_lig60_vs_numpy():
         rows.append(np.asarray(sym_rows))
         rhs.append(np.zeros(len(sym_rows)))
     want = np.linalg.lstsq(np.vstack(rows), np.concatenate(rhs), rcond=None)[0] / sc
+    # the fused kernels against the same numpy matrices: normal equations (DMMA), residual and gradient passes
+    import torch
+    plan = lls._device_plan(system, 0.05, 0.05)
+    assert plan.n_cols == 742 and np.abs(np.asarray(lls._p0) - p0).max() <= 1e-12
+    rs = torch.from_numpy(np.sqrt(w) / np.sqrt(var) * rng.uniform(0.5, 1.5, n_conf)).cuda()
+    rs_h = rs.cpu().numpy()
+    plan.set_columns(lls._p0, plan.means, 1.0 / sc)
+    G = plan.normal(rs, torch.from_numpy(B).cuda()).cpu().numpy()
+    Ab = np.hstack([A_want / sc[None, :], B[:, None]]) * rs_h[:, None]
+    G_want = Ab.T @ Ab
+    assert np.array_equal(G, G.T)
+    assert np.abs(G - G_want).max() <= 1e-11 * np.abs(G_want).max(), np.abs(G - G_want).max() / np.abs(G_want).max()
+    z = rng.normal(0, 1.0, 742) * sc
+    e = plan.residual(torch.from_numpy(z).cuda(), torch.from_numpy(B).cuda())
+    e_want = B - A_want @ z
+    assert np.abs(e.cpu().numpy() - e_want).max() <= 1e-11 * np.abs(e_want).max()
+    y = plan.colstats(e, rs * rs)[0].cpu().numpy()
+    y_want = A_want.T @ (rs_h * rs_h * e_want)
+    assert np.abs(y - y_want).max() <= 1e-10 * np.abs(y_want).max()
     lls.fit_parameters_lls([system])
     got = lls._parameters
+    assert lls.reduction == "normal_equations_refined", lls.reduction
     assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), (lls.reduction, np.abs(got - want).max(), np.abs(want).max())
 
 
