@@ -468,8 +468,10 @@ def run_ours(args):
                 "objective_evals_per_s": args.steps / t_e2e, "api": "ObjectiveFunction.f(x) with host x (one CUDA-graph replay per call)",
                 "cold_upload": {"seconds": arm.t_upload, "bytes": arm.upload_bytes,
                                 "note": "one-time pinned-host -> HBM staging of the conformation tiles, outside the step"}},
-        "gpu_launches": 3 * args.steps,
-        "gpu_launches_note": "per step: pm_prepare_kernel, the E+F kernel (fused residual reduction), pm_reduce_rows_kernel (row sum + all-reduce)",
+        "gpu_launches": (4 if getattr(topo, "specialized", False) else 3) * args.steps,
+        "gpu_launches_note": ("per step: pm_prepare_kernel, pm_ef_spec_kernel, pm_reduce_stage1, pm_reduce_rows_kernel (row sum + all-reduce over NVLink peer memory)"
+                              if getattr(topo, "specialized", False) else
+                              "per step: pm_prepare_kernel, pm_ef_kernel (residual reduction in its epilogue), pm_reduce_rows_kernel (row sum + all-reduce)"),
         "objective_evals_per_s": args.steps / t_dev,
         "roofline": {"bound": "fp64", "kernel": ("pm_ef_spec_kernel (topology-specialised code generated for this molecule, csrc/specialize.py)"
                                                  if getattr(topo, "specialized", False) else "pm_ef_kernel<true> (topology interpreter)"),
@@ -481,7 +483,7 @@ def run_ours(args):
                      "frac_of_nominal": achieved_tf / fp64_nominal,
                      "precision_note": "FP64 storage and arithmetic (objective tolerance 1e-8, DESIGN.md section 3): against the FP32 CUDA-core peak SURVEY 8(d) named the same kernel is half this fraction",
                      "flops_per_conformation": flops_conf, "kernel_ms": 1e3 * t_kernel,
-                     "kernel_ms_note": "pm_eval_reduce: constant-table copy + E+F kernel + row-sum kernel, CUDA events on the launch stream",
+                     "kernel_ms_note": "pm_eval_reduce: constant-table copy + E+F kernel + residual sums + row-sum kernel (with the all-reduce at N > 1), CUDA events on the launch stream",
                      "kernel_share_of_step": t_kernel * args.steps / t_dev, "launch": info,
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "bytes_per_conformation": bytes_conf, "peak_source": hbm_src}},

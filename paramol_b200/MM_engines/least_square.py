@@ -183,13 +183,10 @@ class LinearLeastSquare:
         G = G.cpu().numpy()
         lap("normal_equations_s")
         M = self._n_parameters
-        # regularisation and symmetry rows of the reference, collected as E x = f
-        self._A, self._B = np.zeros((0, M)), np.zeros(0)
-        if self._include_regularization:
-            self._add_regularization()
-        self._add_symmetries(system)
-        E, f = self._A, self._B
-        N = G[:M, :M] + E.T @ E
+        # regularisation and symmetry rows of the reference (E x = f) enter the normal equations as E^T E and E^T f; E is a diagonal
+        # block plus rows e_i - e_j, so it is kept sparse (the dense rows are only built for the orthogonal fallback)
+        E, f = self._extra_rows_sparse(system)
+        N = G[:M, :M] + (E.T @ E).toarray()
         rhs = G[:M, M] + E.T @ f
         x = self._solve_refined(plan, N, rhs, E, f, row_scale, B, col_scale)
         lap("solve_and_refine_s")
@@ -199,7 +196,7 @@ class LinearLeastSquare:
             A = A * row_scale[:, None] * torch.from_numpy(col_scale).to(dev)[None, :]
             R, qtb = self._reduce_tall(A, B * row_scale)
             R_all, qtb_all = self._gather_factors(R, qtb)
-            self._A = np.vstack((R_all, E))
+            self._A = np.vstack((R_all, E.toarray()))
             self._B = np.concatenate((qtb_all, f))
             x = np.linalg.lstsq(self._A, self._B, rcond=None)[0]
             lap("fallback_s")
@@ -404,6 +401,38 @@ class LinearLeastSquare:
                 return x
             last = size
         return None
+
+    def _extra_rows_sparse(self, system):
+        """The rows ``_add_regularization`` (diag(alpha / prior width), rhs alpha * p_init; reference ``:253-291``) and
+        ``_add_symmetries`` (e_i - e_j, rhs 0; ``:293-337``) append to the system, as (scipy.sparse CSR [K, M], f [K])."""
+        import scipy.sparse
+        M = self._n_parameters
+        rows, cols, vals, f = [], [], [], []
+        k = 0
+        if self._include_regularization:
+            alpha = self._scaling_factor / self._scaling_constants
+            self._calculate_prior_widths()
+            rows += list(range(M))
+            cols += list(range(M))
+            vals += list(alpha / self._prior_widths)
+            f += list(alpha * self._initial_param_regularization)
+            k = M
+        # one row per (first column of a symmetry group, later column of the same group), in the reference's order
+        groups = {}
+        for j, tag in enumerate(self._param_symmetries_list):
+            groups.setdefault(tag, []).append(j)
+        for tag, members in groups.items():          # dicts keep first-occurrence order
+            if tag in ("X_x", "X_y", "X"):
+                continue
+            for j in members[1:]:
+                rows += [k, k]
+                cols += [members[0], j]
+                vals += [1.0, -1.0]
+                f.append(0.0)
+                k += 1
+        E = scipy.sparse.csr_matrix((np.asarray(vals, dtype=np.float64), (np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64))),
+                                    shape=(k, M))
+        return E, np.asarray(f, dtype=np.float64)
 
     def _term_table(self, alpha_bond, alpha_angle):
         """(kinds, atoms, periodicities, columns per term, owners) of the optimizable force constants, in column order."""
