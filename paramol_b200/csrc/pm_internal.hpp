@@ -15,6 +15,7 @@ struct PmProg {
     int n_atoms, n_bonds, n_angles, n_torsions, n_pairs;
     int cpw, L;
     int n_star_steps, n_axis_steps, n_segs;
+    int n_pair_pos, off_blocks;  // team mode: 4 x 4 pair blocks (pm_program.hpp)
     int n_int;      // ints in the blob
     int n_derived;  // doubles per parameter vector in the derived table
     int off_star_tab, off_star_hdr, off_star_rec, off_axis_tab, off_axis_hdr, off_axis_rec, off_axis_terms, off_seg_hdr, off_seg_tile,

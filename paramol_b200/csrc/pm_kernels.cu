@@ -122,6 +122,31 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     }
 }
 
+// The pair of a 4 x 4 block: identical to pm_pair except that |d|^2 is kept above 2^-100 by an integer max on its high word (one
+// ALU instruction, not an FP64 one).  Block slots that do not interact carry zero parameters and may pair an atom with itself
+// (diagonal blocks, padding atoms): with the guard such a slot evaluates to exactly zero energy and force instead of 0 * inf.
+template <bool WITH_F>
+__device__ __forceinline__ void pm_pair_blk(const pm_d3 xi, const pm_d3 xj, const double *__restrict__ pp, double &e_nb, pm_d3 &fi,
+                                            pm_d3 &fj) {
+    const pm_d3 d = pm_sub(xi, xj);
+    double r2 = pm_dot(d, d);
+    r2 = __hiloint2double(max(__double2hiint(r2), 0x39B00000), __double2loint(r2));
+    const double rinv = pm_rsqrt(r2);
+    const double u = rinv * rinv;
+    const double u3 = u * u * u;
+    const double c12 = pp[0], c6 = pp[1], cq = pp[2];
+    const double a = c12 * u3;
+    const double b = a - c6;
+    const double ec = cq * rinv;
+    e_nb = fma(b, u3, e_nb);
+    e_nb += ec;
+    if (WITH_F) {
+        const double g = fma(6.0 * u3, a + b, ec) * u;
+        pm_axpy(fi, g, d);
+        pm_axpy(fj, g, d);
+    }
+}
+
 __device__ __forceinline__ double pm_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -198,14 +223,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     double *s_metric = reinterpret_cast<double *>(smem_raw + off);
     off += ((size_t)9 * N * sizeof(double) + 15) & ~(size_t)15;  // keep the derived table 16-byte aligned (double2 reads)
     double *s_der = reinterpret_cast<double *>(smem_raw + off);
-    off += (size_t)g.n_derived * sizeof(double);
+    off += (size_t)(g.n_derived + 4) * sizeof(double);  // + the zero pair slot of the 4 x 4 blocks
     off = (off + 127) & ~(size_t)127;
-    const size_t per_warp = 128 + (size_t)tile_d * sizeof(double) * (WITH_F ? 2 : 1);
+    // a tile is followed by the three rows of the padding atom (pair blocks of teams; zero coordinates, forces never read)
+    const int tile_p = tile_d + 3 * CPW;
+    const size_t per_warp = 128 + (size_t)tile_p * sizeof(double) * (WITH_F ? 2 : 1);
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
     double *racc = reinterpret_cast<double *>(wbase + 64);  // fused residual reduction: this warp's 5 running sums
     double *xs = reinterpret_cast<double *>(wbase + 128);
-    double *fs = xs + tile_d;  // only touched when WITH_F
+    double *fs = xs + tile_p;  // only touched when WITH_F
     const bool want_res = WITH_F && fref_t != nullptr;
 
     for (int i = threadIdx.x; i < g.n_int; i += blockDim.x) s_int[i] = g.ints[i];
@@ -214,6 +241,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     if (lane == 0) {
         pm_mbar_init(bar, 1);
         pm_fence_mbar_init();
+    }
+    if (lane < 3 * CPW) {
+        xs[tile_d + lane] = 0.0;
+        if (WITH_F) fs[tile_d + lane] = 0.0;
     }
     uint32_t parity = 0;
 
@@ -236,6 +267,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
         {
             const double *dsrc = derived + (size_t)p * g.n_derived;
             for (int i = threadIdx.x; i < g.n_derived; i += blockDim.x) s_der[i] = dsrc[i];
+            // zero pair slot (index n_pairs; may overlap the alignment pad of the table, hence written after the copy by the
+            // thread that copied that entry or by nobody else)
+            __syncthreads();
+            if (threadIdx.x < 4) s_der[g.doff_pair + g.pair_stride * g.n_pairs + threadIdx.x] = 0.0;
         }
         __syncthreads();
         const double2 *s_pbond = reinterpret_cast<const double2 *>(s_der + g.doff_bond);
@@ -498,6 +533,42 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 }
             }
 
+            // ================= nonbonded, teams: 4 x 4 register blocks on disjoint tile pairs ====================
+            if (L > 1 && !RF) {
+                const int4 *s_blk = reinterpret_cast<const int4 *>(s_int + g.off_blocks);
+                for (int pos = 0; pos < g.n_pair_pos; ++pos) {
+                    const int4 *rec = s_blk + (pos * L + tl) * 4;
+                    const int4 ia = rec[0], ja = rec[1], q0 = rec[2], q1 = rec[3];
+                    const int io[4] = {ia.x, ia.y, ia.z, ia.w}, jo[4] = {ja.x, ja.y, ja.z, ja.w};
+                    const unsigned qi[8] = {(unsigned)q0.x, (unsigned)q0.y, (unsigned)q0.z, (unsigned)q0.w,
+                                            (unsigned)q1.x, (unsigned)q1.y, (unsigned)q1.z, (unsigned)q1.w};
+                    pm_d3 xi[4], xj[4], ai[4], aj[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        xi[k] = pm_ldo<CPW>(xc_base, io[k]);
+                        xj[k] = pm_ldo<CPW>(xc_base, jo[k]);
+                        ai[k] = pm_d3{0.0, 0.0, 0.0};
+                        aj[k] = pm_d3{0.0, 0.0, 0.0};
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int s16 = 4 * k + m;
+                            const unsigned q = (s16 & 1) ? (qi[s16 >> 1] >> 16) : (qi[s16 >> 1] & 0xffffu);
+                            pm_pair_blk<WITH_F>(xi[k], xj[m], s_ppair + 3 * q, e_nb, ai[k], aj[m]);
+                        }
+                    }
+                    if (WITH_F) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            pm_addo<CPW>(fc_base, io[k], ai[k]);
+                            pm_subo<CPW>(fc_base, jo[k], aj[k]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
             // ================= nonbonded: plain pairs and scaled 1-4 exceptions, register-tiled over i ========
             for (int seg = 0; seg < g.n_segs; ++seg) {
                 const int2 hdr = s_seg_hdr[seg];
@@ -798,9 +869,9 @@ static void pm_plan(int n_int, int n_derived, int N, int cpw, int max_smem, int 
     size_t off = ((size_t)n_int * sizeof(int) + 15) & ~(size_t)15;
     off += (size_t)(PM_ACOS_N + 1) * sizeof(double2);
     off += ((size_t)9 * N * sizeof(double) + 15) & ~(size_t)15;
-    off += (size_t)n_derived * sizeof(double);
+    off += (size_t)(n_derived + 4) * sizeof(double);
     off = (off + 127) & ~(size_t)127;
-    const size_t pw = 128 + (size_t)3 * N * cpw * sizeof(double) * (wf ? 2 : 1);
+    const size_t pw = 128 + (size_t)3 * (N + 1) * cpw * sizeof(double) * (wf ? 2 : 1);  // tile + the rows of the padding atom
     long w = ((long)max_smem - (long)off) / (long)pw;
     if (w > PM_MAX_WARPS) w = PM_MAX_WARPS;
     if (w < 0) w = 0;
@@ -953,6 +1024,8 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     g.n_star_steps = host.n_star_steps;
     g.n_axis_steps = host.n_axis_steps;
     g.n_segs = host.n_segs;
+    g.n_pair_pos = host.n_pair_pos;
+    g.off_blocks = host.off_blocks;
     g.n_int = (int)host.blob.size();
     g.off_star_tab = host.off_star_tab;
     g.off_star_hdr = host.off_star_hdr;
@@ -1174,6 +1247,7 @@ static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const
         prog.n_axis_steps = 0;
     } else if (mode == 2) {
         prog.n_segs = 0;
+        prog.n_pair_pos = 0;
         prog.nb_e = nb_e_dev;
         prog.nb_f_tiles = nb_f_tiles_dev;
     }

@@ -17,11 +17,19 @@
 //            of c1_i and c2_l.  Impropers are axes with one cell.
 //   pair segment : an i-tile of up to 4 atoms held in registers by one lane plus a list of (j, mask, pair-base) entries.
 //            Tiles are cut into chunks so that the L lanes of a team get equal work; inside a segment the entries are
-//            ordered so that no two lanes of a team update the same j in the same step.
+//            ordered so that no two lanes of a team update the same j in the same step.  (One lane per conformation only.)
+//   pair block   : teams (L > 1) run the pair phase as 4 x 4 register blocks instead: atoms are dealt into tiles of 4
+//            (tile t = atoms t, t + T, t + 2T, t + 3T, so that the rows the lanes of a team touch spread over the shared-memory
+//            banks), a block is a pair of tiles (ti <= tj) with its 16 pair-parameter indices; pairs that do not interact
+//            (excluded, padding atoms, the lower triangle of a diagonal block) point at a zero parameter slot, so every lane runs
+//            the SAME branch-free 16-pair code on its own block -- no masks, no divergence between the lanes of a team.  A
+//            position holds up to L blocks on pairwise disjoint tiles (both tiles' forces are flushed after the block, so no
+//            two lanes of a team ever touch the same atom in one position).
 #pragma once
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <set>
 #include <vector>
@@ -34,6 +42,7 @@ struct PmHostProgram {
     std::vector<int> pair_map;  // (i, j, exception or -1) per interacting pair, kernel order
     int n_pairs = 0;
     int n_star_steps = 0, n_axis_steps = 0, n_segs = 0;
+    int n_pair_pos = 0, off_blocks = 0;  // team mode: 4 x 4 pair blocks (see below); then n_segs == 0
     int off_star_tab = 0, off_star_hdr = 0, off_star_rec = 0, off_axis_tab = 0, off_axis_hdr = 0, off_axis_rec = 0, off_axis_terms = 0;
     int off_seg_hdr = 0, off_seg_tile = 0, off_entries = 0, off_tper = 0;
     // statistics for DESIGN.md / pm_launch_info
@@ -384,6 +393,107 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
     out.n_pairs = (int)(out.pair_map.size() / 3);
     out.n_entries = total_entries;
 
+    // ---- team mode: 4 x 4 blocks on disjoint tile pairs ---------------------------------------------------------------
+    std::vector<int> block_tab;
+    const char *pb_env = getenv("PM_PAIR_BLOCKS");
+    const bool use_blocks = L > 1 && out.n_pairs > 0 && out.n_pairs < 65535 && !(pb_env && pb_env[0] == '0');
+    if (use_blocks) {
+        const int T = (N + PMH_IT - 1) / PMH_IT;
+        auto tile_atom = [&](int t, int k) {
+            const int a = t + k * T;
+            return a < N ? a : -1;
+        };
+        std::map<std::pair<int, int>, int> pair_index;
+        for (int q = 0; q < out.n_pairs; ++q) pair_index[std::make_pair(out.pair_map[3 * q], out.pair_map[3 * q + 1])] = q;
+        struct Block {
+            int ti, tj;
+            int idx[16];
+        };
+        std::vector<Block> blocks;
+        for (int ti = 0; ti < T; ++ti)
+            for (int tj = ti; tj < T; ++tj) {
+                Block b;
+                b.ti = ti;
+                b.tj = tj;
+                int real = 0;
+                for (int k = 0; k < 4; ++k)
+                    for (int m = 0; m < 4; ++m) {
+                        int q = out.n_pairs;  // the zero slot
+                        const int a = tile_atom(ti, k), c = tile_atom(tj, m);
+                        if (a >= 0 && c >= 0 && a != c && (ti != tj || k < m)) {
+                            auto it = pair_index.find(std::make_pair(std::min(a, c), std::max(a, c)));
+                            if (it != pair_index.end()) {
+                                q = it->second;
+                                ++real;
+                            }
+                        }
+                        b.idx[4 * k + m] = q;
+                    }
+                if (real) blocks.push_back(b);
+            }
+        // positions: greedy packing of up to L tile-disjoint blocks, busiest tiles first; a few deterministic perturbations of
+        // the priorities, the shortest schedule wins
+        std::vector<std::vector<int>> best;
+        for (int attempt = 0; attempt < 64; ++attempt) {
+            unsigned rng = 12345u + 7919u * (unsigned)attempt;
+            std::vector<int> deg(T, 0);
+            std::vector<char> done(blocks.size(), 0);
+            for (const Block &b : blocks) {
+                deg[b.ti]++;
+                if (b.tj != b.ti) deg[b.tj]++;
+            }
+            size_t left = blocks.size();
+            std::vector<std::vector<int>> sched;
+            while (left > 0) {
+                std::vector<std::pair<int, int>> cand;  // (-priority, block)
+                for (size_t i = 0; i < blocks.size(); ++i)
+                    if (!done[i]) {
+                        rng = rng * 1664525u + 1013904223u;
+                        const int jitter = attempt ? (int)((rng >> 24) & 3) : 0;
+                        cand.push_back(std::make_pair(-(4 * (deg[blocks[i].ti] + deg[blocks[i].tj]) + jitter), (int)i));
+                    }
+                std::sort(cand.begin(), cand.end());
+                std::vector<int> cur;
+                std::set<int> used;
+                for (auto &c : cand) {
+                    if ((int)cur.size() >= L) break;
+                    const Block &b = blocks[c.second];
+                    if (used.count(b.ti) || used.count(b.tj)) continue;
+                    cur.push_back(c.second);
+                    used.insert(b.ti);
+                    used.insert(b.tj);
+                }
+                for (int i : cur) {
+                    done[i] = 1;
+                    --left;
+                    deg[blocks[i].ti]--;
+                    if (blocks[i].tj != blocks[i].ti) deg[blocks[i].tj]--;
+                }
+                sched.push_back(cur);
+            }
+            if (best.empty() || sched.size() < best.size()) best = sched;
+        }
+        const int dummy = N * AO;  // rows of the padding atom behind the tile (zero coordinates, never-read forces)
+        for (auto &pos : best)
+            for (int l = 0; l < L; ++l) {
+                int rec[16];
+                for (int k = 0; k < 8; ++k) rec[k] = dummy;
+                for (int k = 0; k < 8; ++k) rec[8 + k] = out.n_pairs | (out.n_pairs << 16);
+                if (l < (int)pos.size()) {
+                    const Block &b = blocks[pos[l]];
+                    for (int k = 0; k < 4; ++k) {
+                        const int a = tile_atom(b.ti, k), c = tile_atom(b.tj, k);
+                        rec[k] = a < 0 ? dummy : a * AO;
+                        rec[4 + k] = c < 0 ? dummy : c * AO;
+                    }
+                    for (int k = 0; k < 8; ++k) rec[8 + k] = b.idx[2 * k] | (b.idx[2 * k + 1] << 16);
+                }
+                block_tab.insert(block_tab.end(), rec, rec + 16);
+            }
+        out.n_pair_pos = (int)best.size();
+        out.n_entries = (int)blocks.size();
+    }
+
     auto build_units = [&](int chunk) {
         std::vector<Unit> units;
         for (int it = 0; it < n_itiles; ++it) {
@@ -428,7 +538,9 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
     };
     std::vector<Unit> units;
     std::vector<std::vector<int>> segs;
-    if (L == 1 || total_entries == 0) {
+    if (use_blocks) {
+        // pair blocks replace the segments
+    } else if (L == 1 || total_entries == 0) {
         units = build_units(INT_MAX);
         build_segments(units, segs);
     } else {
@@ -494,7 +606,7 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
         seg_hdr[seg_hdr.size() - 2] = n_e;
     }
     out.n_segs = (int)segs.size();
-    out.n_entry_slots = slots;
+    out.n_entry_slots = use_blocks ? out.n_pair_pos * L : slots;
 
     // ------------------------------------------------------------------ tables + blob ---------------------------------
     std::vector<int> star_hdr, axis_hdr;
@@ -529,6 +641,7 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
     out.off_seg_tile = append(seg_tile);
     out.off_entries = append(entries);
     out.off_tper = append(std::vector<int>(tors_per, tors_per + n_torsions));
+    out.off_blocks = append(block_tab);
     align4();
     return true;
 }
@@ -651,6 +764,34 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
                     ++q;
                 }
             }
+        }
+    }
+    // pair blocks (team mode): tiles of one position are disjoint across the lanes, every interacting pair appears once
+    for (int pos = 0; pos < p.n_pair_pos; ++pos) {
+        std::set<int> touched;
+        for (int l = 0; l < L; ++l) {
+            const int *r = b + p.off_blocks + 16 * (pos * L + l);
+            std::set<int> mine;
+            int at[8];
+            for (int k = 0; k < 8; ++k) {
+                if (r[k] % AO) return 50;
+                at[k] = r[k] / AO;
+                if (at[k] < 0 || at[k] > N) return 51;
+                if (at[k] < N) mine.insert(at[k]);
+            }
+            for (int a : mine)
+                if (!touched.insert(a).second) return 52;  // two lanes of a team on the same atom
+            for (int k = 0; k < 4; ++k)
+                for (int m = 0; m < 4; ++m) {
+                    const int w = r[8 + (4 * k + m) / 2];
+                    const int q = ((4 * k + m) & 1) ? (w >> 16) & 0xffff : w & 0xffff;
+                    if (q == p.n_pairs) continue;  // zero slot
+                    if (q > p.n_pairs) return 53;
+                    const int a = at[k], c = at[4 + m];
+                    if (a >= N || c >= N || a == c) return 54;
+                    if (p.pair_map[3 * q] != std::min(a, c) || p.pair_map[3 * q + 1] != std::max(a, c)) return 55;
+                    seen_p[q]++;
+                }
         }
     }
     for (int v : seen_p)
