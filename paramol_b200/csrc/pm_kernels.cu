@@ -122,6 +122,11 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     }
 }
 
+#ifndef PM_BLK_UNROLL
+#define PM_BLK_UNROLL 1  // rows of a pair block per loop iteration (1: rolled, 4: fully unrolled)
+#endif
+constexpr int kBlkUnroll = PM_BLK_UNROLL;
+
 // The pair of a 4 x 4 block: identical to pm_pair except that |d|^2 is kept above 2^-100 by an integer max on its high word (one
 // ALU instruction, not an FP64 one).  Block slots that do not interact carry zero parameters and may pair an atom with itself
 // (diagonal blocks, padding atoms): with the guard such a slot evaluates to exactly zero energy and force instead of 0 * inf.
@@ -200,7 +205,7 @@ __device__ __forceinline__ double pm_axis_cells(const int *__restrict__ cells, c
         }                                              \
     }
 
-// MAXW = warps per CTA the variant is compiled for: 16 (128 registers per thread) or 12 (168 registers, no spills).
+// MAXW = warps per CTA the variant is compiled for: 16 (128 registers per thread), 14 (144) or 12 (168 registers, no spills).
 // Measured on B200: when shared memory admits at most 12 warps anyway, the 168-register variant is 5-10 % faster.
 template <int CPW, bool WITH_F, int MAXW, bool RF = false>
 __global__ void __launch_bounds__(MAXW * 32, 1)
@@ -534,37 +539,33 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             }
 
             // ================= nonbonded, teams: 4 x 4 register blocks on disjoint tile pairs ====================
-            if (L > 1 && !RF) {
-                const int4 *s_blk = reinterpret_cast<const int4 *>(s_int + g.off_blocks);
+            if (L >= 4 && !RF) {
                 for (int pos = 0; pos < g.n_pair_pos; ++pos) {
-                    const int4 *rec = s_blk + (pos * L + tl) * 4;
-                    const int4 ia = rec[0], ja = rec[1], q0 = rec[2], q1 = rec[3];
-                    const int io[4] = {ia.x, ia.y, ia.z, ia.w}, jo[4] = {ja.x, ja.y, ja.z, ja.w};
-                    const unsigned qi[8] = {(unsigned)q0.x, (unsigned)q0.y, (unsigned)q0.z, (unsigned)q0.w,
-                                            (unsigned)q1.x, (unsigned)q1.y, (unsigned)q1.z, (unsigned)q1.w};
-                    pm_d3 xi[4], xj[4], ai[4], aj[4];
+                    const int *rec = s_int + g.off_blocks + (pos * L + tl) * 16;
+                    const int4 ja = *reinterpret_cast<const int4 *>(rec + 4);
+                    const int jo[4] = {ja.x, ja.y, ja.z, ja.w};
+                    pm_d3 xj[4], aj[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        xi[k] = pm_ldo<CPW>(xc_base, io[k]);
-                        xj[k] = pm_ldo<CPW>(xc_base, jo[k]);
-                        ai[k] = pm_d3{0.0, 0.0, 0.0};
-                        aj[k] = pm_d3{0.0, 0.0, 0.0};
+                    for (int m = 0; m < 4; ++m) {
+                        xj[m] = pm_ldo<CPW>(xc_base, jo[m]);
+                        aj[m] = pm_d3{0.0, 0.0, 0.0};
                     }
-#pragma unroll
+                    // rows of the block one at a time (a rolled loop: the body -- four independent pairs -- stays small enough for
+                    // the instruction cache; all register indices are static)
+#pragma unroll kBlkUnroll
                     for (int k = 0; k < 4; ++k) {
+                        const int io = rec[k];
+                        const int2 qq = *reinterpret_cast<const int2 *>(rec + 8 + 2 * k);
+                        const unsigned q[4] = {(unsigned)qq.x & 0xffffu, (unsigned)qq.x >> 16, (unsigned)qq.y & 0xffffu, (unsigned)qq.y >> 16};
+                        const pm_d3 xi = pm_ldo<CPW>(xc_base, io);
+                        pm_d3 ai{0.0, 0.0, 0.0};
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const int s16 = 4 * k + m;
-                            const unsigned q = (s16 & 1) ? (qi[s16 >> 1] >> 16) : (qi[s16 >> 1] & 0xffffu);
-                            pm_pair_blk<WITH_F>(xi[k], xj[m], s_ppair + 3 * q, e_nb, ai[k], aj[m]);
-                        }
+                        for (int m = 0; m < 4; ++m) pm_pair_blk<WITH_F>(xi, xj[m], s_ppair + 3 * q[m], e_nb, ai, aj[m]);
+                        if (WITH_F) pm_addo<CPW>(fc_base, io, ai);
                     }
                     if (WITH_F) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            pm_addo<CPW>(fc_base, io[k], ai[k]);
-                            pm_subo<CPW>(fc_base, jo[k], aj[k]);
-                        }
+                        for (int m = 0; m < 4; ++m) pm_subo<CPW>(fc_base, jo[m], aj[m]);
                     }
                     __syncwarp();
                 }
@@ -850,7 +851,7 @@ static pm_ef_fn pm_pick_kernel_w(int cpw, int wf) {
 }
 static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw, int rf = 0) {
     if (rf) return wf ? pm_ef_kernel<32, true, 12, true> : pm_ef_kernel<32, false, 12, true>;  // CPW 32 only
-    return maxw <= 12 ? pm_pick_kernel_w<12>(cpw, wf) : pm_pick_kernel_w<16>(cpw, wf);
+    return maxw <= 12 ? pm_pick_kernel_w<12>(cpw, wf) : maxw <= 14 ? pm_pick_kernel_w<14>(cpw, wf) : pm_pick_kernel_w<16>(cpw, wf);
 }
 
 extern "C" const char *pm_last_error(void) { return g_err.c_str(); }
@@ -971,27 +972,31 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     if (cpw != 0 && cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: conf_per_tile must be 0 (auto), 32, 16, 8 or 4");
     if (rf) cpw = 32;  // the reaction-field variant is instantiated for one lane per conformation only
     PmHostProgram host;
-    const int n_derived_est = 2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * (N * (N - 1) / 2) + 2;
+    bool built = false;
     if (!cpw) {
-        // fewest lanes per conformation that still gives >= 9 warps per SM (measured sweet spot); else the CPW
-        // with most warps
+        // fewest lanes per conformation that still gives >= 9 warps per SM (measured sweet spot); else the CPW with most
+        // warps.  Planned with the real program of every candidate (building one takes milliseconds).
         int best_w = -1;
         for (int c = 32; c >= 4; c >>= 1) {
+            PmHostProgram cand;
+            if (!pm_build_program(N, c, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx, t->torsion_per,
+                                  cls, cand))
+                return pm_fail("pm_create: degenerate bonded term (repeated atom)");
+            const int n_derived = (2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * cand.n_pairs + 1) & ~1;
             size_t sh, pw;
             int w;
-            pm_plan(4096 + 40 * N * (32 / c), n_derived_est, N, c, max_smem, 1, &sh, &pw, &w);
-            if (w >= 9) {
-                cpw = c;
-                break;
-            }
-            if (w > best_w) {
+            pm_plan((int)cand.blob.size(), n_derived, N, c, max_smem, 1, &sh, &pw, &w);
+            if (w >= 9 || w > best_w) {
                 best_w = w;
                 cpw = c;
+                host = cand;
+                built = true;
+                if (w >= 9) break;
             }
         }
     }
-    if (!pm_build_program(N, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
-                          t->torsion_per, cls, host))
+    if (!built && !pm_build_program(N, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
+                                    t->torsion_per, cls, host))
         return pm_fail("pm_create: degenerate bonded term (repeated atom)");
 
     pm_handle_s *h = new pm_handle_s();
@@ -1104,7 +1109,10 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
         pm_plan(g.n_int, g.n_derived, N, cpw, max_smem, wf, &sh, &pw, &w);
         const char *envw = getenv("PM_WARPS");
         if (envw && *envw && atoi(envw) > 0 && atoi(envw) < w) w = atoi(envw);
-        h->maxw[wf] = (w <= 12 || rf) ? 12 : 16;
+        // register budget of the variant: 168 (<= 12 warps), 144 (13-14 warps) or 128 registers per thread
+        h->maxw[wf] = (w <= 12 || rf) ? 12 : w <= 14 ? 14 : 16;
+        const char *envm = getenv("PM_MAXW");   // sweeps only
+        if (envm && *envm && !rf && atoi(envm) >= w && (atoi(envm) == 12 || atoi(envm) == 14 || atoi(envm) == 16)) h->maxw[wf] = atoi(envm);
         if (rf && w > 12) w = 12;
         h->warps[wf] = w;
         h->smem_total[wf] = w > 0 ? sh + pw * (size_t)w : 0;

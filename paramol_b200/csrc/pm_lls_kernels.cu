@@ -63,6 +63,7 @@ struct LlsDev {  // device view of a plan
     const double *sd;     // [M] sin(delta)
     const double *mean;   // [M] subtracted from the raw column
     const double *scale;  // [M] multiplies the centred column
+    const double2 *acos_tab;  // (cos, sin)(q pi / PM_ACOS_N): pm_acos_cs
     int n_atoms, cpt, n_terms, n_cols;
 };
 
@@ -74,6 +75,7 @@ struct pm_lls_s {
     int device, n_atoms, cpt, n_terms, n_cols, n_sm, n_panels;
     LlsTerm *terms_dev;
     double *cols_dev;  // [5][M]: p0, cos delta, sin delta, mean, scale
+    double2 *acos_dev;
     std::vector<LlsTerm> terms;
     LlsPanels panels;
 };
@@ -83,8 +85,8 @@ struct pm_lls_s {
 // ---------------------------------------------------------------------------------------------------------------------
 // LD(atom) -> pm_d3.  q is the internal coordinate (bonds, angles; 0 for torsions), v0 / v1 the raw (uncentred) columns:
 // 1/2 (q - p0)^2 (least_square.py:516-517, 566-567) or 1 + cos(n phi - delta) (:614-615).  Conventions of Utils/geometry.py: the angle
-// is arccos of the clipped cosine of the unit vectors (here atan2(|v1 x v2|, v1.v2): the same angle, well conditioned near 0 and
-// pi); the dihedral is the atan2 formula of calculate_dihedral -- cos phi and sin phi are its normalised arguments, cos n phi and
+// is arccos of the clipped cosine of the unit vectors (here recovered from cosine AND sine, pm_acos_cs: the same angle, well
+// conditioned near 0 and pi); the dihedral is the atan2 formula of calculate_dihedral -- cos phi and sin phi are its normalised arguments, cos n phi and
 // sin n phi follow by n complex multiplications, so no inverse trigonometric function is needed at all.
 template <class LD>
 __device__ __forceinline__ void lls_term_values(const LlsTerm &t, LD ld, const LlsDev &P, double &q, double &v0, double &v1) {
@@ -100,7 +102,11 @@ __device__ __forceinline__ void lls_term_values(const LlsTerm &t, LD ld, const L
         const pm_d3 x1 = ld(t.a1);
         const pm_d3 u = pm_sub(ld(t.a0), x1), w = pm_sub(ld(t.a2), x1);
         const pm_d3 cr = pm_cross(u, w);
-        q = atan2(sqrt(pm_dot(cr, cr)), pm_dot(u, w));
+        // theta from cos = u.w / (|u||w|) and sin = |u x w| / (|u||w|) through the (cos, sin) table (pm_device.cuh): no libm atan2 / acos
+        const double n2 = pm_dot(u, u) * pm_dot(w, w), c2 = pm_dot(cr, cr);
+        const double inv = n2 > 0.0 ? pm_rsqrt(n2) : 0.0;
+        const double sn = c2 > 0.0 ? c2 * pm_rsqrt(c2) * inv : 0.0;
+        q = pm_acos_cs(fmin(1.0, fmax(-1.0, pm_dot(u, w) * inv)), sn, P.acos_tab);
         const double e0 = q - P.p0[c0], e1 = q - P.p0[c1];
         v0 = 0.5 * e0 * e0;
         v1 = 0.5 * e1 * e1;
@@ -276,16 +282,16 @@ __device__ __forceinline__ void pml_dmma(double (&c)[2], double a, double b) {
 // Columns [128 panel, 128 panel + 128) of conformations [s0, s0 + 32) into pt[column][conformation]: lane = conformation, the warps
 // share the panel's terms.  Entry = rowscale_s * scale_j * (raw_sj - mean_j); column M is rowscale_s * b_s; conformations beyond S
 // and columns beyond M are zero (the latter are zeroed once, when the kernel starts).
-__device__ __forceinline__ void lls_generate_panel(const LlsDev &P, int t0, int t1, int panel, const double *__restrict__ coords, long s0,
-                                                   long S, const double *__restrict__ rs, const double *__restrict__ b,
-                                                   double *__restrict__ pt, int warp, int n_warps, int lane) {
+__device__ __forceinline__ void lls_generate_panel(const LlsDev &P, const LlsTerm *__restrict__ terms, int n_t, int panel,
+                                                   const double *__restrict__ coords, long s0, long S, const double *__restrict__ rs,
+                                                   const double *__restrict__ b, double *__restrict__ pt, int warp, int n_warps, int lane) {
     const long s = s0 + lane;
     const bool live = s < S;
     const LlsGlobalLoad ld = lls_conf(coords, live ? s : S - 1, P.n_atoms, P.cpt);
     const double r = live ? (rs ? rs[s] : 1.0) : 0.0;
     const int lo = panel * LLS_PANEL;
-    for (int t = t0 + warp; t < t1; t += n_warps) {
-        const LlsTerm tm = P.terms[t];
+    for (int t = warp; t < n_t; t += n_warps) {
+        const LlsTerm tm = terms[t];
         double q, v0, v1;
         lls_term_values(tm, ld, P, q, v0, v1);
         const int j0 = tm.col - lo, j1 = j0 + 1;
@@ -311,9 +317,35 @@ __global__ void __launch_bounds__(LLS_NORMAL_THREADS, 1)
     }
     const int J = I + rem;
     const bool diag = I == J;
-    // buffers: [2][panel I | panel J]
+    // buffers: [2][panel I | panel J], then the metadata of the two panels: terms, column parameters (one column of margin on the
+    // left for a term that straddles the panel boundary), the (cos, sin) table
     double *buf[2] = {lsm, lsm + 2 * PANEL_D};
+    double *meta = lsm + 4 * PANEL_D;                       // [2 panels][5][LLS_PANEL + 2]
+    double2 *s_acos = reinterpret_cast<double2 *>(meta + 2 * 5 * (LLS_PANEL + 2));
+    LlsTerm *s_terms = reinterpret_cast<LlsTerm *>(s_acos + PM_ACOS_N + 1);  // [2][LLS_PANEL + 1]
     for (int i = tid; i < 4 * PANEL_D; i += LLS_NORMAL_THREADS) lsm[i] = 0.0;
+    for (int i = tid; i <= PM_ACOS_N; i += LLS_NORMAL_THREADS) s_acos[i] = P.acos_tab[i];
+    LlsDev PP[2];
+    int n_t[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int pnl = side ? J : I, lo = pnl * LLS_PANEL - 1;
+        double *m = meta + side * 5 * (LLS_PANEL + 2);
+        const double *src[5] = {P.p0, P.cd, P.sd, P.mean, P.scale};
+        for (int i = tid; i < 5 * (LLS_PANEL + 2); i += LLS_NORMAL_THREADS) {
+            const int a = i / (LLS_PANEL + 2), c = lo + (i - a * (LLS_PANEL + 2));
+            m[i] = (c >= 0 && c < P.n_cols) ? src[a][c] : 0.0;
+        }
+        n_t[side] = R.t1[pnl] - R.t0[pnl];
+        for (int i = tid; i < n_t[side]; i += LLS_NORMAL_THREADS) s_terms[side * (LLS_PANEL + 1) + i] = P.terms[R.t0[pnl] + i];
+        PP[side] = P;  // column arrays re-based so that the absolute column index still works
+        PP[side].p0 = m - lo;
+        PP[side].cd = m + (LLS_PANEL + 2) - lo;
+        PP[side].sd = m + 2 * (LLS_PANEL + 2) - lo;
+        PP[side].mean = m + 3 * (LLS_PANEL + 2) - lo;
+        PP[side].scale = m + 4 * (LLS_PANEL + 2) - lo;
+        PP[side].acos_tab = s_acos;
+    }
     __syncthreads();
 
     const int wr = warp >> 2, wc = warp & 3;  // 4 x 4 warps, 32 x 32 outputs each
@@ -326,16 +358,16 @@ __global__ void __launch_bounds__(LLS_NORMAL_THREADS, 1)
     const long n_chunks = (S + LLS_KC - 1) / LLS_KC;
     long ch = z;
     if (ch < n_chunks) {
-        lls_generate_panel(P, R.t0[I], R.t1[I], I, coords, ch * LLS_KC, S, rs, b, buf[0], warp, n_warps, lane);
-        if (!diag) lls_generate_panel(P, R.t0[J], R.t1[J], J, coords, ch * LLS_KC, S, rs, b, buf[0] + PANEL_D, warp, n_warps, lane);
+        lls_generate_panel(PP[0], s_terms, n_t[0], I, coords, ch * LLS_KC, S, rs, b, buf[0], warp, n_warps, lane);
+        if (!diag) lls_generate_panel(PP[1], s_terms + LLS_PANEL + 1, n_t[1], J, coords, ch * LLS_KC, S, rs, b, buf[0] + PANEL_D, warp, n_warps, lane);
     }
     __syncthreads();
     int cur = 0;
     for (; ch < n_chunks; ch += n_split) {
         const long nxt = ch + n_split;
         if (nxt < n_chunks) {  // the next 32 conformations into the other buffer while this one is contracted
-            lls_generate_panel(P, R.t0[I], R.t1[I], I, coords, nxt * LLS_KC, S, rs, b, buf[cur ^ 1], warp, n_warps, lane);
-            if (!diag) lls_generate_panel(P, R.t0[J], R.t1[J], J, coords, nxt * LLS_KC, S, rs, b, buf[cur ^ 1] + PANEL_D, warp, n_warps, lane);
+            lls_generate_panel(PP[0], s_terms, n_t[0], I, coords, nxt * LLS_KC, S, rs, b, buf[cur ^ 1], warp, n_warps, lane);
+            if (!diag) lls_generate_panel(PP[1], s_terms + LLS_PANEL + 1, n_t[1], J, coords, nxt * LLS_KC, S, rs, b, buf[cur ^ 1] + PANEL_D, warp, n_warps, lane);
         }
         const double *pa = buf[cur] + (32 * wr + (lane >> 2)) * LLS_RS + (lane & 3);
         const double *pb = buf[cur] + (diag ? 0 : PANEL_D) + (32 * wc + (lane >> 2)) * LLS_RS + (lane & 3);
@@ -396,6 +428,7 @@ static LlsDev lls_dev(pm_lls p) {
     d.sd = p->cols_dev + 2 * (size_t)p->n_cols;
     d.mean = p->cols_dev + 3 * (size_t)p->n_cols;
     d.scale = p->cols_dev + 4 * (size_t)p->n_cols;
+    d.acos_tab = p->acos_dev;
     d.n_atoms = p->n_atoms;
     d.cpt = p->cpt;
     d.n_terms = p->n_terms;
@@ -435,6 +468,7 @@ extern "C" int pm_lls_create(int device, int n_atoms, int conf_per_tile, int n_t
     p->n_terms = n_terms;
     p->terms_dev = nullptr;
     p->cols_dev = nullptr;
+    p->acos_dev = nullptr;
     p->n_sm = 148;
     cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
     int col = 0;
@@ -481,13 +515,22 @@ extern "C" int pm_lls_create(int device, int n_atoms, int conf_per_tile, int n_t
         p->panels.t0[q] = t0 < t1 ? t0 : 0;
         p->panels.t1[q] = t0 < t1 ? t1 : 0;
     }
-    if (cudaMalloc(&p->terms_dev, sizeof(LlsTerm) * n_terms) != cudaSuccess ||
+    std::vector<double> tab(2 * (PM_ACOS_N + 1));
+    for (int q = 0; q <= PM_ACOS_N; ++q) {
+        const double th = (double)q * (PM_PI / PM_ACOS_N);
+        tab[2 * q] = cos(th);
+        tab[2 * q + 1] = sin(th);
+    }
+    if (cudaMalloc(&p->acos_dev, sizeof(double) * tab.size()) != cudaSuccess ||
+        cudaMemcpy(p->acos_dev, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&p->terms_dev, sizeof(LlsTerm) * n_terms) != cudaSuccess ||
         cudaMalloc(&p->cols_dev, sizeof(double) * 5 * (size_t)col) != cudaSuccess ||
         cudaMemcpy(p->terms_dev, p->terms.data(), sizeof(LlsTerm) * n_terms, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(p->cols_dev, 0, sizeof(double) * 5 * (size_t)col) != cudaSuccess) {
         const std::string why = cudaGetErrorString(cudaGetLastError());
         if (p->terms_dev) cudaFree(p->terms_dev);
         if (p->cols_dev) cudaFree(p->cols_dev);
+        if (p->acos_dev) cudaFree(p->acos_dev);
         delete p;
         return pm_fail_msg("pm_lls_create: " + why);
     }
@@ -563,7 +606,8 @@ extern "C" int pm_lls_normal(pm_lls p, const double *coords_dev, long n_conf, co
     PML_CUDA(cudaSetDevice(p->device));
     const int n_blk = p->n_panels * (p->n_panels + 1) / 2;
     const int n_split = lls_split(p, n_conf);
-    const size_t smem = sizeof(double) * 4 * (size_t)LLS_PANEL * LLS_RS;
+    const size_t smem = sizeof(double) * (4 * (size_t)LLS_PANEL * LLS_RS + 2 * 5 * (LLS_PANEL + 2)) + sizeof(double2) * (PM_ACOS_N + 1) +
+                        sizeof(LlsTerm) * 2 * (LLS_PANEL + 1);
     PML_CUDA(cudaFuncSetAttribute((const void *)pm_lls_normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t st = (cudaStream_t)stream;
     pm_lls_normal_kernel<<<n_blk * n_split, LLS_NORMAL_THREADS, smem, st>>>(lls_dev(p), p->panels, p->n_panels, n_split, coords_dev, n_conf,
@@ -581,6 +625,7 @@ extern "C" int pm_lls_destroy(pm_lls p) {
     cudaSetDevice(p->device);
     cudaFree(p->terms_dev);
     cudaFree(p->cols_dev);
+    cudaFree(p->acos_dev);
     delete p;
     return 0;
 }

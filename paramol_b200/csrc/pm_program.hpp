@@ -18,7 +18,7 @@
 //   pair segment : an i-tile of up to 4 atoms held in registers by one lane plus a list of (j, mask, pair-base) entries.
 //            Tiles are cut into chunks so that the L lanes of a team get equal work; inside a segment the entries are
 //            ordered so that no two lanes of a team update the same j in the same step.  (One lane per conformation only.)
-//   pair block   : teams (L > 1) run the pair phase as 4 x 4 register blocks instead: atoms are dealt into tiles of 4
+//   pair block   : teams of L >= 4 lanes run the pair phase as 4 x 4 register blocks instead: atoms are dealt into tiles of 4
 //            (tile t = atoms t, t + T, t + 2T, t + 3T, so that the rows the lanes of a team touch spread over the shared-memory
 //            banks), a block is a pair of tiles (ti <= tj) with its 16 pair-parameter indices; pairs that do not interact
 //            (excluded, padding atoms, the lower triangle of a diagonal block) point at a zero parameter slot, so every lane runs
@@ -396,7 +396,9 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
     // ---- team mode: 4 x 4 blocks on disjoint tile pairs ---------------------------------------------------------------
     std::vector<int> block_tab;
     const char *pb_env = getenv("PM_PAIR_BLOCKS");
-    const bool use_blocks = L > 1 && out.n_pairs > 0 && out.n_pairs < 65535 && !(pb_env && pb_env[0] == '0');
+    // (measured on B200: with 2 lanes per conformation the masked segments are still ahead -- caffeine 385 vs 362 M conformations/s;
+    // from 4 lanes on the blocks win -- norfloxacin 142 -> 150, lig60 63 -> 71)
+    const bool use_blocks = L >= 4 && out.n_pairs > 0 && out.n_pairs < 65535 && !(pb_env && pb_env[0] == '0');
     if (use_blocks) {
         const int T = (N + PMH_IT - 1) / PMH_IT;
         auto tile_atom = [&](int t, int k) {
