@@ -156,6 +156,20 @@ int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec, const doub
                    const double *weights_dev, double d_shift, double *partials_dev, double *scratch_dev, pm_comm comm,
                    double *emm_dev, double *fres_dev, void *stream);
 
+/* ---- energy-only batches: geometry evaluated once, reused by every parameter vector (K2) ----------------------------- */
+/* E[p][s] = sum_t C[p][t] G[t][s]: every MM energy term is linear in coefficients C (from the derived tables of the n_vec vectors)
+ * once the geometry features G (r^2, r, theta^2, theta, cos / sin(n phi), r^-12, r^-6, 1/r) of a conformation are known, so a batch
+ * of trial vectors -- Monte Carlo / simulated annealing proposals, the evaluations of a finite-difference gradient, WHAM passes;
+ * ParaMol/Optimizers/monte_carlo.py:89-101, gradient_descent.py:104-122 -- costs ONE pass over the geometry plus a dense FP64
+ * contraction on the tensor-core path instead of n_vec full term passes.  Output as pm_eval_reduce with with_forces = 0:
+ * partials_dev [n_vec][PM_NPARTIAL] ([4] = 0), summed over the ranks of `comm` when given; emm_dev [n_vec][n_conf] optional.
+ * NoCutoff systems only (pm_energy_batch_supported).  scratch_dev: pm_energy_batch_scratch_doubles(h, n_vec, n_conf) doubles. */
+int pm_energy_batch_supported(pm_handle h);
+long pm_energy_batch_scratch_doubles(pm_handle h, int n_vec, long n_conf);
+int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev, long n_conf,
+                           const double *eref_dev, const double *weights_dev, double d_shift, double *partials_dev,
+                           double *scratch_dev, pm_comm comm, double *emm_dev, void *stream);
+
 /* ---- intra-node communicator (one process per GPU, NVLink / NVSwitch peer memory) -------------------------------- */
 /* pm_comm_create allocates this rank's inbox on `device` and returns its 64-byte CUDA IPC handle in handle_out; the host
  * layer exchanges the handles (torch.distributed all_gather) and passes all of them, in rank order, to pm_comm_connect, which

@@ -556,6 +556,34 @@ class DeviceEnsemble:
                    "pm_eval_reduce")
         return partials, emm, fres
 
+    def energy_batch_supported(self):
+        """True when ``pm_energy_batch_reduce`` serves this topology (NoCutoff, coordinate tile fits the shared memory)."""
+        return bool(self.topology._L.pm_energy_batch_supported(self.topology._h))
+
+    def energy_batch_reduce(self, derived, d_shift=0.0, weights="own", comm=None, want_emm=False):
+        """
+        ``pm_energy_batch_reduce``: energies of a BATCH of parameter vectors with the geometry evaluated once per conformation
+        (E = C G on the FP64 tensor-core path) and the energy sums of ``pm_reduce_objective`` ([4] = 0); for energy-only
+        objectives, WHAM passes and finite-difference gradients of the energy term.  Returns (partials [P, 8] CUDA -- global sums
+        when ``comm`` is given --, emm [P, S] or None).
+        """
+        torch = _torch()
+        topo = self.topology
+        n_vec = int(derived.shape[0])
+        need = int(topo._L.pm_energy_batch_scratch_doubles(topo._h, n_vec, self.n_conf))
+        if getattr(self, "_eg_scratch", None) is None or self._eg_scratch.numel() < need:
+            self._eg_scratch = torch.empty(need, dtype=torch.float64, device=self.device)
+        partials = self._buf("partials", (n_vec, NPARTIAL))
+        w = self.weights if isinstance(weights, str) else weights
+        emm = self._buf("emm", (n_vec, self.n_conf)) if want_emm else None
+        _lib.check(topo._L.pm_energy_batch_reduce(topo._h, derived.data_ptr(), n_vec, self.coord_tiles.data_ptr(), self.n_conf,
+                                                  self.eref.data_ptr() if self.eref is not None else None,
+                                                  w.data_ptr() if w is not None else None, float(d_shift), partials.data_ptr(),
+                                                  self._eg_scratch.data_ptr(), comm.handle if comm is not None else None,
+                                                  emm.data_ptr() if emm is not None else None, _stream_ptr(self.device)),
+                   "pm_energy_batch_reduce")
+        return partials, emm
+
     # ---- delta evaluation ---------------------------------------------------------------------------------
     def set_delta_base(self, slots_row, derived_row, emm_row, fres_row, fmm_tiles_row):
         """Keep copies of the per-conformation results of ONE fully evaluated vector as the base of later delta evaluations."""

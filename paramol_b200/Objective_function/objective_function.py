@@ -65,6 +65,10 @@ class ObjectiveFunction:
         (~1e-13 relative); off by default.
     """
 
+    #: energy-only batches of at least this many vectors go through the contraction kernel (``pm_energy_batch_reduce``); below it the
+    #: per-vector term pass is cheaper than building the coefficient matrix and padding the block of 128 vectors
+    ENERGY_BATCH_MIN_VECTORS = 16
+
     def __init__(self, restart_settings, parameter_space, properties, systems, platform_name="B200", parallel=False,
                  weighting_method="uniform", weighting_temperature=300.0, checkpoint_freq=1000, fused=True,
                  cache_nonbonded=False, delta_evaluation=False):
@@ -627,7 +631,11 @@ class ObjectiveFunction:
                 comm = st.get("comm")
                 if comm is not None and n_vec > comm.max_vec:
                     comm = None
-                part, _, _ = ens.evaluate_reduce(derived, with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
+                if not st["need_f"] and n_vec >= self.ENERGY_BATCH_MIN_VECTORS and ens.energy_batch_supported():
+                    # energy-only batch: the geometry of a conformation is evaluated once and reused by every vector (K2)
+                    part, _ = ens.energy_batch_reduce(derived, d_shift=st["d_shift"], comm=comm)
+                else:
+                    part, _, _ = ens.evaluate_reduce(derived, with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
                 if comm is not None or not multi_rank:
                     global_parts[s_idx] = part
                     partial_list.append("global")

@@ -68,6 +68,11 @@ SIGNATURES = {
     "pm_eval_reduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long,
                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "pm_energy_batch_supported": (ctypes.c_int, [ctypes.c_void_p]),
+    "pm_energy_batch_scratch_doubles": (ctypes.c_long, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long]),
+    "pm_energy_batch_reduce": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
     "pm_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.POINTER(ctypes.c_void_p)]),
     "pm_comm_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libparamol_b200.so")
-SOURCES = ["pm_kernels.cu", "pm_fit_kernels.cu", "pm_grad_kernels.cu", "pm_delta_kernels.cu", "pm_spec.cu", "pm_comm.cu", "pm_lls_kernels.cu"]
+SOURCES = ["pm_kernels.cu", "pm_fit_kernels.cu", "pm_grad_kernels.cu", "pm_delta_kernels.cu", "pm_spec.cu", "pm_comm.cu", "pm_lls_kernels.cu", "pm_egemm_kernels.cu"]
 HEADERS = ["pm_device.cuh", "pm_program.hpp", "pm_internal.hpp", os.path.join("..", "..", "include", "paramol_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

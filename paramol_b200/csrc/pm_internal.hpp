@@ -69,6 +69,8 @@ struct pm_handle_s {
     void (*grad_free)(void *);
     void *spec_state;               // owned by pm_spec.cu: a topology-specialised E+F kernel, or null
     void (*spec_free)(void *);
+    void *egemm_state;              // owned by pm_egemm_kernels.cu: feature table of the energy-only batch contraction, or null
+    void (*egemm_free)(void *);
 };
 
 int pm_fail_msg(const std::string &msg);  // sets pm_last_error(), returns 1 (pm_kernels.cu)

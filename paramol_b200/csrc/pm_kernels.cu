@@ -1013,6 +1013,8 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     h->grad_state = nullptr;
     h->grad_free = nullptr;
     h->spec_state = nullptr;
+    h->egemm_state = nullptr;
+    h->egemm_free = nullptr;
     h->spec_free = nullptr;
     h->bond_idx.assign(t->bond_idx, t->bond_idx + 2 * (size_t)t->n_bonds);
     h->angle_idx.assign(t->angle_idx, t->angle_idx + 3 * (size_t)t->n_angles);
@@ -1136,6 +1138,7 @@ extern "C" int pm_destroy(pm_handle h) {
     cudaFree(h->d_acos);
     if (h->grad_state && h->grad_free) h->grad_free(h->grad_state);
     if (h->spec_state && h->spec_free) h->spec_free(h->spec_state);
+    if (h->egemm_state && h->egemm_free) h->egemm_free(h->egemm_state);
     delete h;
     return 0;
 }

@@ -334,3 +334,43 @@ def test_fused_eval_reduce_equals_eval_then_reduce(golden_dir, name, n_conf, n_v
         if not with_forces:
             bare[:, 4] = 0.0
         assert np.array_equal(bare, got)   # deterministic: same launch geometry, same order
+
+
+@pytest.mark.parametrize("name,n_conf,n_vec,weighted", [("aniline", 1000, 5, True), ("lig60", 4100, 130, False), ("caffeine", 333, 16, True),
+                                                        ("lig33", 129, 257, False), ("ethane", 64, 3, True)])
+def test_energy_batch_contraction_vs_energy_kernel_and_oracle(golden_dir, name, n_conf, n_vec, weighted):
+    """``pm_energy_batch_reduce`` (geometry features once per conformation, E = C G on DMMA) against the energy-only E kernel for
+    every vector of the batch (1e-11 of the largest energy: the expansion of the harmonic terms cancels three digits) and, for a
+    few vectors, against the oracle evaluated with that vector's parameters; the energy sums against ``pm_eval_reduce``.  Batch
+    sizes on both sides of the block of 128 vectors, ragged conformation tiles."""
+    import torch
+    from oracle import oracle as O
+    from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(5)
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    Eref = rng.normal(50.0, 5.0, n_conf)
+    topo = DeviceTopology(s)
+    base = topo.slots_from_system(s)
+    slots = base[None] * (1.0 + 0.02 * rng.uniform(-1, 1, (n_vec, len(base))))
+    slots[0] = base
+    ens = DeviceEnsemble(topo, X, None, Eref)
+    if weighted:
+        w = rng.uniform(0.1, 1.0, n_conf)
+        ens.set_weights(w / w.sum())
+    assert ens.energy_batch_supported()
+    derived = topo.prepare(torch.from_numpy(slots).cuda())
+    want_p, emm_want, _ = ens.evaluate_reduce(derived, with_forces=False, d_shift=50.0, want_emm=True)
+    want_p, emm_want = want_p.cpu().numpy().copy(), emm_want.cpu().numpy().copy()
+    got_p, emm = ens.energy_batch_reduce(derived, d_shift=50.0, want_emm=True)
+    got_p, emm = got_p.cpu().numpy(), emm.cpu().numpy()
+    scale = np.abs(emm_want).max()
+    assert np.abs(emm - emm_want).max() <= 1e-11 * max(scale, 1.0), np.abs(emm - emm_want).max() / scale
+    want_p[:, 4] = 0.0
+    tol = 1e-10 * np.maximum(np.abs(want_p), np.abs(want_p).max(axis=1, keepdims=True) * 1e-3) + 1e-9
+    assert np.all(np.abs(got_p - want_p) <= tol), (got_p[0], want_p[0])
+    bare = ens.energy_batch_reduce(derived, d_shift=50.0)[0].cpu().numpy()
+    assert np.array_equal(bare, got_p)
+    for p in (0, n_vec - 1):
+        E, _ = O.energies_forces(_system_with_slots(s, slots[p]), X, n_threads=4)
+        assert _close_ef(emm[p], E), np.abs(emm[p] - E).max()
