@@ -186,7 +186,9 @@ class LinearLeastSquare:
         # regularisation and symmetry rows of the reference (E x = f) enter the normal equations as E^T E and E^T f; E is a diagonal
         # block plus rows e_i - e_j, so it is kept sparse (the dense rows are only built for the orthogonal fallback)
         E, f = self._extra_rows_sparse(system)
-        N = G[:M, :M] + (E.T @ E).toarray()
+        N = np.array(G[:M, :M], copy=True)
+        ete = (E.T @ E).tocoo()                       # a diagonal plus a handful of off-diagonal entries
+        np.add.at(N, (ete.row, ete.col), ete.data)
         rhs = G[:M, M] + E.T @ f
         x = self._solve_refined(plan, N, rhs, E, f, row_scale, B, col_scale)
         lap("solve_and_refine_s")

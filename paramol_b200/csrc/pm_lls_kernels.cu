@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -398,6 +399,128 @@ __global__ void __launch_bounds__(LLS_NORMAL_THREADS, 1)
         }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3 -> K4 through an L2-resident slab (the default route of pm_lls_normal)
+// ---------------------------------------------------------------------------------------------------------------------
+// In the fused kernel above a panel is regenerated by every block that needs it (6-7 times for 742 columns) and its generation --
+// latency-bound scattered coordinate loads, ~100 instructions per value -- keeps the FP64 pipe 15 % busy (ncu,
+// profiles/r2_lls_normal_summary.csv: 13.4 ms).  Here the columns of a GROUP of conformations are generated ONCE into a slab sized
+// to stay in the 126 MB L2 (<= 48 MB; layout [chunk of 32 conformations][panel][128 columns][36], i.e. already in the padded
+// shared-memory layout of the contraction), and the contraction streams the two panels of its block with one TMA bulk copy each
+// per chunk (double-buffered, mbarrier completion) -- its inner loop is loads of fragments and DMMA only.  The slab is overwritten
+// by the next group, so the [S][M] matrix still never exists; what reaches HBM is the eviction traffic of a buffer that fits L2.
+__global__ void __launch_bounds__(256)
+    pm_lls_slab_kernel(LlsDev P, int n_panels, const double *__restrict__ coords, long S, long conf0, int n_chunks,
+                       const double *__restrict__ rs, const double *__restrict__ b, double *__restrict__ slab) {
+    extern __shared__ __align__(16) double lsm[];
+    double2 *s_acos = reinterpret_cast<double2 *>(lsm);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    for (int i = tid; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = P.acos_tab[i];
+    __syncthreads();
+    LlsDev Q = P;
+    Q.acos_tab = s_acos;
+    constexpr size_t PANEL_D = (size_t)LLS_PANEL * LLS_RS;
+    for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const long s = conf0 + (long)ch * LLS_KC + lane;
+        const bool live = s < S;
+        const LlsGlobalLoad ld = lls_conf(coords, live ? s : S - 1, P.n_atoms, P.cpt);
+        const double r = live ? (rs ? rs[s] : 1.0) : 0.0;
+        double *out = slab + (size_t)ch * n_panels * PANEL_D + lane;
+        for (int t = warp; t < P.n_terms; t += n_warps) {
+            const LlsTerm tm = P.terms[t];
+            double q, v0, v1;
+            lls_term_values(tm, ld, Q, q, v0, v1);
+            out[(size_t)tm.col * LLS_RS] = r * P.scale[tm.col] * (v0 - P.mean[tm.col]);   // column j of panel j / 128 sits at j * 36
+            if (tm.ncol > 1) out[(size_t)(tm.col + 1) * LLS_RS] = r * P.scale[tm.col + 1] * (v1 - P.mean[tm.col + 1]);
+        }
+        // the right-hand side as column M, zeros behind it
+        for (int j = P.n_cols + warp; j < n_panels * LLS_PANEL; j += n_warps)
+            out[(size_t)j * LLS_RS] = (j == P.n_cols && live && b) ? r * b[s] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(LLS_NORMAL_THREADS, 1)
+    pm_lls_syrk_kernel(int n_panels, int n_split, const double *__restrict__ slab, int n_chunks, int accumulate, double *__restrict__ partial) {
+    extern __shared__ __align__(128) double lsm[];
+    constexpr int PANEL_D = LLS_PANEL * LLS_RS;
+    constexpr uint32_t PANEL_BYTES = PANEL_D * sizeof(double);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int blk = blockIdx.x / n_split, z = blockIdx.x - blk * n_split;
+    int I = 0, rem = blk;
+    while (rem >= n_panels - I) {
+        rem -= n_panels - I;
+        ++I;
+    }
+    const int J = I + rem;
+    const bool diag = I == J;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(lsm + 4 * PANEL_D);
+    if (tid == 0) {
+        pm_mbar_init(&bar[0], 1);
+        pm_mbar_init(&bar[1], 1);
+        pm_fence_mbar_init();
+    }
+    __syncthreads();
+    const int wr = warp >> 2, wc = warp & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    auto issue = [&](int ch, int stage) {  // one thread: the two panels of chunk ch into buffer `stage`
+        const double *src = slab + (size_t)ch * n_panels * PANEL_D;
+        double *dst = lsm + (size_t)stage * 2 * PANEL_D;
+        pm_mbar_expect_tx(&bar[stage], diag ? PANEL_BYTES : 2 * PANEL_BYTES);
+        pm_bulk_g2s(dst, src + (size_t)I * PANEL_D, PANEL_BYTES, &bar[stage]);
+        if (!diag) pm_bulk_g2s(dst + PANEL_D, src + (size_t)J * PANEL_D, PANEL_BYTES, &bar[stage]);
+    };
+    uint32_t parity = 0;  // bit s: phase of barrier s
+    int ch = z;
+    if (ch < n_chunks && tid == 0) issue(ch, 0);
+    int cur = 0;
+    for (; ch < n_chunks; ch += n_split) {
+        if (ch + n_split < n_chunks && tid == 0) {
+            pm_fence_proxy_async();  // the generic-proxy reads of that buffer (previous iteration) are ordered before the copy
+            issue(ch + n_split, cur ^ 1);
+        }
+        pm_mbar_wait(&bar[cur], (parity >> cur) & 1u);
+        parity ^= 1u << cur;
+        const double *bcur = lsm + (size_t)cur * 2 * PANEL_D;
+        const double *pa = bcur + (32 * wr + (lane >> 2)) * LLS_RS + (lane & 3);
+        const double *pb = bcur + (diag ? 0 : PANEL_D) + (32 * wc + (lane >> 2)) * LLS_RS + (lane & 3);
+#pragma unroll
+        for (int k4 = 0; k4 < LLS_KC / 4; ++k4) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = pa[(8 * i) * LLS_RS + 4 * k4];
+                bb[i] = pb[(8 * i) * LLS_RS + 4 * k4];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pml_dmma(acc[i][j], a[i], bb[j]);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    double *out = partial + ((size_t)z * (n_panels * (n_panels + 1) / 2) + blk) * (LLS_PANEL * LLS_PANEL);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = 32 * wr + 8 * i + (lane >> 2), c = 32 * wc + 8 * j + 2 * (lane & 3);
+            double2 *dst = reinterpret_cast<double2 *>(out + (size_t)r * LLS_PANEL + c);
+            double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (accumulate) {
+                const double2 old = *dst;
+                v.x += old.x;
+                v.y += old.y;
+            }
+            *dst = v;
+        }
+}
+
 // G[(M+1)][(M+1)] (full, symmetric) from the partial blocks, slices added in order
 __global__ void pm_lls_block_sum(const double *__restrict__ partial, int n_panels, int n_split, int n, double *__restrict__ g) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -558,11 +681,26 @@ extern "C" int pm_lls_set_columns(pm_lls p, const double *p0, const double *mean
     return 0;
 }
 
+// chunks of 32 conformations per slab group: the slab stays below LLS_SLAB_BYTES (L2-resident)
+#define LLS_SLAB_BYTES (48L << 20)
+static long lls_group_chunks(pm_lls p, long n_conf) {
+    const long n_chunks = (n_conf + LLS_KC - 1) / LLS_KC;
+    long g = LLS_SLAB_BYTES / ((long)p->n_panels * LLS_PANEL * LLS_RS * (long)sizeof(double));
+    if (g < 8) g = 8;
+    return g < n_chunks ? g : n_chunks;
+}
+
+static bool lls_fused_route() {
+    const char *e = getenv("PM_LLS_FUSED");
+    return e && e[0] == '1';
+}
+
 extern "C" long pm_lls_scratch_doubles(pm_lls p, long n_conf) {
     if (!p || n_conf < 1) return -1;
     const long stat = (long)lls_stat_grid(p, n_conf) * ((long)p->n_cols + 2L * p->n_terms);
     const long n_blk = (long)p->n_panels * (p->n_panels + 1) / 2;
-    const long normal = (long)lls_split(p, n_conf) * n_blk * LLS_PANEL * LLS_PANEL;
+    const long normal = (long)lls_split(p, n_conf) * n_blk * LLS_PANEL * LLS_PANEL +
+                        lls_group_chunks(p, n_conf) * p->n_panels * LLS_PANEL * LLS_RS;
     return stat > normal ? stat : normal;
 }
 
@@ -606,13 +744,31 @@ extern "C" int pm_lls_normal(pm_lls p, const double *coords_dev, long n_conf, co
     PML_CUDA(cudaSetDevice(p->device));
     const int n_blk = p->n_panels * (p->n_panels + 1) / 2;
     const int n_split = lls_split(p, n_conf);
-    const size_t smem = sizeof(double) * (4 * (size_t)LLS_PANEL * LLS_RS + 2 * 5 * (LLS_PANEL + 2)) + sizeof(double2) * (PM_ACOS_N + 1) +
-                        sizeof(LlsTerm) * 2 * (LLS_PANEL + 1);
-    PML_CUDA(cudaFuncSetAttribute((const void *)pm_lls_normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t st = (cudaStream_t)stream;
-    pm_lls_normal_kernel<<<n_blk * n_split, LLS_NORMAL_THREADS, smem, st>>>(lls_dev(p), p->panels, p->n_panels, n_split, coords_dev, n_conf,
-                                                                           rowscale_dev, b_dev, scratch_dev);
-    PML_CUDA(cudaGetLastError());
+    if (lls_fused_route()) {  // the single-kernel route (generation inside the contraction), kept for comparison
+        const size_t smem = sizeof(double) * (4 * (size_t)LLS_PANEL * LLS_RS + 2 * 5 * (LLS_PANEL + 2)) + sizeof(double2) * (PM_ACOS_N + 1) +
+                            sizeof(LlsTerm) * 2 * (LLS_PANEL + 1);
+        PML_CUDA(cudaFuncSetAttribute((const void *)pm_lls_normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pm_lls_normal_kernel<<<n_blk * n_split, LLS_NORMAL_THREADS, smem, st>>>(lls_dev(p), p->panels, p->n_panels, n_split, coords_dev, n_conf,
+                                                                               rowscale_dev, b_dev, scratch_dev);
+        PML_CUDA(cudaGetLastError());
+    } else {
+        const long n_chunks = (n_conf + LLS_KC - 1) / LLS_KC, per_group = lls_group_chunks(p, n_conf);
+        double *slab = scratch_dev + (size_t)n_split * n_blk * LLS_PANEL * LLS_PANEL;
+        const size_t smem_syrk = sizeof(double) * 4 * (size_t)LLS_PANEL * LLS_RS + 64;
+        PML_CUDA(cudaFuncSetAttribute((const void *)pm_lls_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_syrk));
+        const size_t smem_gen = sizeof(double2) * (PM_ACOS_N + 1);
+        for (long c0 = 0, group = 0; c0 < n_chunks; c0 += per_group, ++group) {
+            const int n_here = (int)(n_chunks - c0 < per_group ? n_chunks - c0 : per_group);
+            const int gen_grid = n_here < 8 * p->n_sm ? n_here : 8 * p->n_sm;
+            pm_lls_slab_kernel<<<gen_grid, 256, smem_gen, st>>>(lls_dev(p), p->n_panels, coords_dev, n_conf, c0 * LLS_KC, n_here, rowscale_dev,
+                                                               b_dev, slab);
+            PML_CUDA(cudaGetLastError());
+            pm_lls_syrk_kernel<<<n_blk * n_split, LLS_NORMAL_THREADS, smem_syrk, st>>>(p->n_panels, n_split, slab, n_here, group > 0 ? 1 : 0,
+                                                                                      scratch_dev);
+            PML_CUDA(cudaGetLastError());
+        }
+    }
     const int n = p->n_cols + 1;
     const long total = (long)n * n;
     pm_lls_block_sum<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scratch_dev, p->n_panels, n_split, n, g_dev);
