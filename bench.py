@@ -335,8 +335,20 @@ def measure(arm, args, trial, world, dev, local_rank, barrier, max_over_ranks, s
         e_all1.record()
         barrier()
     t_dev = max_over_ranks(e_all0.elapsed_time(e_all1) * 1e-3)
-    t_kernel = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3)
-    return t_e2e, t_dev, t_kernel, f_vals, clocks
+    t_reduce = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])) * 1e-3)   # pm_eval_reduce as a whole
+    # ======================= (3) the dominant kernel alone (roofline): pm_eval = constant-table copy + E+F kernel =================
+    derived = topo.prepare(slots_dev)
+    for _ in range(3):
+        ens.evaluate(derived, with_forces=True, want_fres=True)
+    torch.cuda.synchronize()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:
+        a.record()
+        ens.evaluate(derived, with_forces=True, want_fres=True)
+        b.record()
+    torch.cuda.synchronize()
+    t_kernel = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in kev])) * 1e-3)
+    return t_e2e, t_dev, (t_kernel, t_reduce), f_vals, clocks
 
 
 def run_ours(args):
@@ -377,7 +389,7 @@ def run_ours(args):
     arm = Arm(args, mm, xb, lo, hi, local_rank)
     rng = np.random.default_rng(0)
     trial = [arm.x_init * (1.0 + 0.01 * rng.uniform(-1, 1, arm.x_init.shape)) for _ in range(args.warmup + args.steps)]
-    t_e2e, t_dev, t_kernel, f_vals, clocks = measure(arm, args, trial, world, dev, local_rank, barrier, max_over_ranks, True)
+    t_e2e, t_dev, (t_kernel, t_reduce), f_vals, clocks = measure(arm, args, trial, world, dev, local_rank, barrier, max_over_ranks, True)
     topo = arm.topo
     comm_kind = pdist.comm_kind(local_rank)
     comm_timeouts = arm.of._state[0]["comm"].timeouts() if arm.of._state[0].get("comm") is not None else 0
@@ -403,7 +415,7 @@ def run_ours(args):
         arm.system._ensemble = None
         torch.cuda.empty_cache()
         warm = Arm(args, mm, xb, rank * S_total, (rank + 1) * S_total, local_rank)
-        w_e2e, w_dev, w_kernel, _, _ = measure(warm, args, trial, world, dev, local_rank, barrier, max_over_ranks, False)
+        w_e2e, w_dev, (w_kernel, _), _, _ = measure(warm, args, trial, world, dev, local_rank, barrier, max_over_ranks, False)
         weak = {"scaling": "weak", "conformations_per_gpu": S_total, "value": world * S_total * args.steps / w_dev,
                 "ms_per_step": 1e3 * w_dev / args.steps, "e2e_value": world * S_total * args.steps / w_e2e,
                 "e2e_ms_per_step": 1e3 * w_e2e / args.steps, "kernel_ms": 1e3 * w_kernel}
@@ -483,7 +495,9 @@ def run_ours(args):
                      "frac_of_nominal": achieved_tf / fp64_nominal,
                      "precision_note": "FP64 storage and arithmetic (objective tolerance 1e-8, DESIGN.md section 3): against the FP32 CUDA-core peak SURVEY 8(d) named the same kernel is half this fraction",
                      "flops_per_conformation": flops_conf, "kernel_ms": 1e3 * t_kernel,
-                     "kernel_ms_note": "pm_eval_reduce: constant-table copy + E+F kernel + residual sums + row-sum kernel (with the all-reduce at N > 1), CUDA events on the launch stream",
+                     "kernel_ms_note": "the E+F kernel alone (pm_eval: constant-table copy + kernel), CUDA events on the launch stream, timed in a separate loop of the same length right after the step loop",
+                     "eval_reduce_ms": 1e3 * t_reduce,
+                     "eval_reduce_ms_note": "pm_eval_reduce inside the step loop: E+F kernel + residual sums + row-sum kernel (with the all-reduce at N > 1)",
                      "kernel_share_of_step": t_kernel * args.steps / t_dev, "launch": info,
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved_gbs / hbm_peak, "bytes_per_conformation": bytes_conf, "peak_source": hbm_src}},

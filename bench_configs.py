@@ -204,7 +204,7 @@ def config4(S=200_000, n_atoms=60):
     t_fit = time.perf_counter() - t0
     return dict(workload="LLS lig%d: S=%d conformations x M=%d columns" % (n_atoms, S, len(x_fit)), full_fit_s=t_fit,
                 full_fit_first_call_s=t_first, reduction=lls.reduction, timings=dict(getattr(lls, "timings", {})),
-                note="full fit = column table + means + fused design-matrix/normal-equation kernel + zero-parameter energy pass + solve")
+                note="full fit = term table, column means (pm_lls_colstats), zero-parameter energy pass, normal equations (pm_lls_slab + pm_lls_syrk on DMMA), Cholesky solve + iterative refinement (pm_lls_residual, pm_lls_colstats)")
 
 
 def config5(fp64_peak, S=50_000, G=500, N=60):

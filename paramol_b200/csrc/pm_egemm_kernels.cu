@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -37,9 +38,10 @@
 
 #define EG_PB 128      // parameter vectors per CTA block
 #define EG_ST 64       // conformations per tile
-#define EG_KC 16       // features per step (4 DMMA k-steps)
-#define EG_CS 20       // row stride of the coefficient chunk in shared memory (= 4 mod 8 doubles)
-#define EG_GS 72       // row stride of the feature chunk (= 8 mod 16 doubles)
+// features per step: KC = 16 (4 DMMA k-steps) by default, 32 as a sweep option;
+// row stride of the coefficient chunk in shared memory = KC + 4 (= 4 mod 8 doubles: conflict-free A fragments)
+#define EG_GS 68       // row stride of the feature chunk (= 4 mod 16 doubles: the four feature rows a half-warp reads as B fragments
+                       // fall into disjoint bank ranges; 72 measured 42 % excess wavefronts)
 #define EG_THREADS 512
 
 struct EgTerm {  // 32 bytes
@@ -57,7 +59,8 @@ struct EgFeat {  // how a coefficient is made from the derived table
 };
 
 struct pm_egemm_s {
-    int n_terms, n_feat, n_chunks;  // n_feat = 16 * n_chunks
+    int kc;                         // features per step (16 or 32)
+    int n_terms, n_feat, n_chunks;  // n_feat = kc * n_chunks
     EgTerm *terms_dev;
     int *chunk_ptr_dev;  // [n_chunks + 1] first term of every chunk
     EgFeat *feat_dev;    // [n_feat]
@@ -188,11 +191,13 @@ __device__ __forceinline__ void eg_features(const EgTerm tm, const double *__res
     }
 }
 
+template <int EG_KC>
 __global__ void __launch_bounds__(EG_THREADS, 1)
     pm_egemm_kernel(int n_atoms, int cpt, const EgTerm *__restrict__ terms, const int *__restrict__ chunk_ptr, int n_chunks, int n_feat,
                     const double *__restrict__ C, const double2 *__restrict__ acos_tab, const double *__restrict__ coords, long S,
                     const double *__restrict__ eref, const double *__restrict__ wts, double d_shift, int n_vec, int n_z,
                     double *__restrict__ rows, double *__restrict__ emm) {
+    constexpr int EG_CS = EG_KC + 4;
     extern __shared__ __align__(16) double sm[];
     const int tile_d = 3 * n_atoms * EG_ST;
     double *xs = sm;                                   // [tile_d] coordinates of the 64 conformations (tile layout)
@@ -227,17 +232,22 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
         __syncthreads();
 
         // chunk c: coefficients Cb[:, 16 c .. 16 c + 16) and the features of its terms
-        auto load_c = [&](int c, double (&v)[4]) {  // 128 x 16 doubles = 512 threads x 4
-            const int row = tid >> 2, k0 = (tid & 3) * 4;
-            const double2 a = *reinterpret_cast<const double2 *>(Cb + (size_t)row * n_feat + c * EG_KC + k0);
-            const double2 b = *reinterpret_cast<const double2 *>(Cb + (size_t)row * n_feat + c * EG_KC + k0 + 2);
-            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        constexpr int CV = EG_KC / 4;  // doubles of the coefficient chunk per thread (128 rows x KC doubles over 512 threads)
+        auto load_c = [&](int c, double (&v)[CV]) {
+            const int row = tid >> 2, k0 = (tid & 3) * CV;
+            const double2 *src = reinterpret_cast<const double2 *>(Cb + (size_t)row * n_feat + c * EG_KC + k0);
+#pragma unroll
+            for (int q = 0; q < CV / 2; ++q) {
+                const double2 a = src[q];
+                v[2 * q] = a.x;
+                v[2 * q + 1] = a.y;
+            }
         };
-        auto store_c = [&](int buf, const double (&v)[4]) {
-            const int row = tid >> 2, k0 = (tid & 3) * 4;
-            double *dst = Cs + (size_t)buf * EG_PB * EG_CS + row * EG_CS + k0;
-            *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
-            *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+        auto store_c = [&](int buf, const double (&v)[CV]) {
+            const int row = tid >> 2, k0 = (tid & 3) * CV;
+            double2 *dst = reinterpret_cast<double2 *>(Cs + (size_t)buf * EG_PB * EG_CS + row * EG_CS + k0);
+#pragma unroll
+            for (int q = 0; q < CV / 2; ++q) dst[q] = make_double2(v[2 * q], v[2 * q + 1]);
         };
         auto generate = [&](int c, int buf) {
             const int t0 = chunk_ptr[c], t1 = chunk_ptr[c + 1];
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
             }
         };
         {
-            double v[4];
+            double v[CV];
             load_c(0, v);
             store_c(0, v);
             generate(0, 0);
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
         __syncthreads();
         for (int c = 0; c < n_chunks; ++c) {
             const int cur = c & 1;
-            double v[4];
+            double v[CV];
             const bool more = c + 1 < n_chunks;
             if (more) {
                 load_c(c + 1, v);       // in flight while this chunk is contracted
@@ -335,9 +345,15 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
 // ---------------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------------
+static size_t pm_egemm_smem(int n_atoms, int kc);
+
 static pm_egemm_s *pm_egemm_plan(pm_handle h) {
     if (h->egemm_state) return (pm_egemm_s *)h->egemm_state;
     const PmProg &g = h->prog;
+    // features per step: 32 halves the CTA barriers but measured 3 % slower than 16 on config 3 (16.1 vs 15.6 ms): the step is bound
+    // by the imbalance between generating and contracting warps, not by the barrier count; PM_EGEMM_KC=32 selects it for sweeps
+    const char *kc_env = getenv("PM_EGEMM_KC");
+    const int EG_KC = (kc_env && atoi(kc_env) == 32 && pm_egemm_smem(g.n_atoms, 32) <= (size_t)h->max_smem) ? 32 : 16;
     std::vector<EgTerm> terms;
     std::vector<EgFeat> feats;
     std::vector<int> chunk_ptr(1, 0);
@@ -380,6 +396,7 @@ static pm_egemm_s *pm_egemm_plan(pm_handle h) {
     for (; row < EG_KC; ++row) feats.push_back(EgFeat{6, 0});
     chunk_ptr.push_back((int)terms.size());
     pm_egemm_s *e = new pm_egemm_s();
+    e->kc = EG_KC;
     e->n_terms = (int)terms.size();
     e->n_feat = (int)feats.size();
     e->n_chunks = e->n_feat / EG_KC;
@@ -404,8 +421,8 @@ static pm_egemm_s *pm_egemm_plan(pm_handle h) {
     return e;
 }
 
-static size_t pm_egemm_smem(int n_atoms) {
-    return sizeof(double) * ((size_t)3 * n_atoms * EG_ST + 2 * EG_PB * EG_CS + 2 * EG_KC * EG_GS + 4 * EG_PB * 4) +
+static size_t pm_egemm_smem(int n_atoms, int kc) {
+    return sizeof(double) * ((size_t)3 * n_atoms * EG_ST + 2 * EG_PB * (kc + 4) + 2 * (size_t)kc * EG_GS + 4 * EG_PB * 4) +
            sizeof(double2) * (PM_ACOS_N + 1);
 }
 
@@ -420,14 +437,14 @@ static int pm_egemm_nz(pm_handle h, int n_vec, long n_conf) {
 extern "C" int pm_energy_batch_supported(pm_handle h) {
     if (!h) return 0;
     return !h->rf && h->prog.n_pairs + h->prog.n_bonds + h->prog.n_angles + h->prog.n_torsions > 0 &&
-           pm_egemm_smem(h->prog.n_atoms) <= (size_t)h->max_smem;
+           pm_egemm_smem(h->prog.n_atoms, 16) <= (size_t)h->max_smem;
 }
 
 extern "C" long pm_energy_batch_scratch_doubles(pm_handle h, int n_vec, long n_conf) {
     if (!h || n_vec < 1 || n_conf < 1) return -1;
     const int n_pb = (n_vec + EG_PB - 1) / EG_PB;
     const long t_max = 2L * h->prog.n_bonds + 2L * h->prog.n_angles + 2L * h->prog.n_torsions + 3L * h->prog.n_pairs + 1;
-    const long n_feat = ((t_max * 16 / 15 + 4 * EG_KC) / EG_KC) * EG_KC;  // upper bound of the padded feature count
+    const long n_feat = ((t_max * 16 / 15 + 4 * 32) / 32) * 32;  // upper bound of the padded feature count
     return (long)n_pb * EG_PB * n_feat + (long)n_vec * pm_egemm_nz(h, n_vec, n_conf) * 5;
 }
 
@@ -438,11 +455,12 @@ extern "C" int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, in
     if (n_vec < 1 || n_conf < 1) return pm_fail_msg("pm_energy_batch_reduce: empty batch");
     if (h->rf) return pm_fail_msg("pm_energy_batch_reduce: the reaction-field variant is not linear in the pair coefficients; use pm_eval_reduce");
     if (comm && n_vec > pm_comm_max_vec(comm)) return pm_fail_msg("pm_energy_batch_reduce: more parameter vectors than the communicator was created for");
-    const size_t smem = pm_egemm_smem(h->prog.n_atoms);
-    if (smem > (size_t)h->max_smem) return pm_fail_msg("pm_energy_batch_reduce: molecule too large for the coordinate tile of this kernel generation");
+    if (pm_egemm_smem(h->prog.n_atoms, 16) > (size_t)h->max_smem)
+        return pm_fail_msg("pm_energy_batch_reduce: molecule too large for the coordinate tile of this kernel generation");
     PMG_CUDA(cudaSetDevice(h->device));
     pm_egemm_s *e = pm_egemm_plan(h);
     if (!e) return pm_fail_msg("pm_energy_batch_reduce: could not build the feature table");
+    const size_t smem = pm_egemm_smem(h->prog.n_atoms, e->kc);
     cudaStream_t st = (cudaStream_t)stream;
     const int n_pb = (n_vec + EG_PB - 1) / EG_PB, n_z = pm_egemm_nz(h, n_vec, n_conf);
     double *C = scratch_dev;
@@ -451,9 +469,10 @@ extern "C" int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, in
     pm_egemm_coef_kernel<<<n_pb * EG_PB, 256, 0, st>>>(derived_dev, n_vec, g.n_derived, e->feat_dev, e->n_feat, g.doff_bond, g.n_bonds, g.doff_angle,
                                                        g.n_angles, g.doff_tors, g.n_torsions, C);
     PMG_CUDA(cudaGetLastError());
-    PMG_CUDA(cudaFuncSetAttribute((const void *)pm_egemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pm_egemm_kernel<<<n_pb * n_z, EG_THREADS, smem, st>>>(g.n_atoms, g.cpw, e->terms_dev, e->chunk_ptr_dev, e->n_chunks, e->n_feat, C, g.acos_tab,
-                                                          coord_tiles_dev, n_conf, eref_dev, weights_dev, d_shift, n_vec, n_z, rows, emm_dev);
+    auto kernel = e->kc == 32 ? pm_egemm_kernel<32> : pm_egemm_kernel<16>;
+    PMG_CUDA(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<n_pb * n_z, EG_THREADS, smem, st>>>(g.n_atoms, g.cpw, e->terms_dev, e->chunk_ptr_dev, e->n_chunks, e->n_feat, C, g.acos_tab,
+                                                 coord_tiles_dev, n_conf, eref_dev, weights_dev, d_shift, n_vec, n_z, rows, emm_dev);
     PMG_CUDA(cudaGetLastError());
     return pm_reduce_rows(rows, n_z, n_vec, n_conf, partials_dev, comm, st);
 }
