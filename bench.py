@@ -289,6 +289,7 @@ def measure(arm, args, trial, world, dev, local_rank, barrier, max_over_ranks, s
     """(t_e2e, t_dev, t_kernel, objective values, clocks) of one arm: K timed steps after W warm-up steps, both ways."""
     import torch
     of, ens, topo = arm.of, arm.ens, arm.topo
+    barrier()   # the ranks finish building their shards at different times; the in-kernel collective waits at most a few seconds
     # ======================= (1) e2e through the public API, host parameter vectors ===========================================
     for x in trial[:args.warmup]:
         of.f(x)

@@ -174,7 +174,7 @@ int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, int n_vec, co
 /* pm_comm_create allocates this rank's inbox on `device` and returns its 64-byte CUDA IPC handle in handle_out; the host
  * layer exchanges the handles (torch.distributed all_gather) and passes all of them, in rank order, to pm_comm_connect, which
  * maps the peers' inboxes.  max_vec bounds n_vec of the calls that use the communicator.  All ranks must issue the same
- * sequence of communicating calls (SPMD); a peer that never arrives makes the kernel give up after ~2 s, poison the result with
+ * sequence of communicating calls (SPMD); a peer that never arrives makes the kernel give up after ~6 s, poison the result with
  * NaN and count a timeout (pm_comm_timeouts) instead of hanging the GPU.
  * pm_comm_allreduce: the same one-shot sum for an arbitrary small buffer (n <= 8 * max_vec doubles), in place. */
 int pm_comm_create(int device, int rank, int world, int max_vec, void *handle_out, pm_comm *out);

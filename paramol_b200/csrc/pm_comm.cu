@@ -35,7 +35,7 @@
 #define PMC_ENTRY 9                 // doubles per inbox entry: 8 values + 1 flag
 #define PMC_MAX_WORLD 16
 #define PMC_THREADS 160             // 5 warps: one per reduced quantity
-#define PMC_TIMEOUT_CYCLES 4000000000LL
+#define PMC_TIMEOUT_CYCLES 12000000000LL  // ~6 s at 1.97 GHz
 
 struct pm_comm_s {
     int device, rank, world, max_vec;

@@ -39,6 +39,9 @@ __device__ __forceinline__ void pm_bulk_g2s(void *dst_smem, const void *src_gmem
 __device__ __forceinline__ void pm_bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void pm_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pm_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool pm_mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

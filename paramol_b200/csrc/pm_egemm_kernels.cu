@@ -49,7 +49,7 @@ struct EgTerm {  // 32 bytes
     int kind;  // 0 bond (r^2, r), 1 angle (theta^2, theta), 2 torsion (cos n phi, sin n phi), 3 pair (r^-12, r^-6, 1/r), 4 constant (1)
     int per;   // periodicity (torsions)
     int row;   // first feature row inside its chunk
-    int pad;
+    int pad;   // index of that chunk
 };
 
 struct EgFeat {  // how a coefficient is made from the derived table
@@ -342,6 +342,283 @@ __global__ void __launch_bounds__(EG_THREADS, 1)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the same contraction with generation in bursts and the coefficients streamed by TMA (default)
+// ---------------------------------------------------------------------------------------------------------------------
+// In pm_egemm_kernel every warp generates, stages and contracts chunk by chunk with one CTA barrier per 16 features: the non-DMMA
+// work of a chunk (a few latency-bound items on a few warps) and its DMMAs never overlap, and ncu shows 14 % of the executed
+// instructions (the DMMAs) accounting for half of the time.  A producer / consumer split (4 or 8 generating warps feeding 16
+// contracting warps through mbarriers) was built and measured SLOWER (18.0 / 14.2 ms against 15.3): the producers' dependent FP64
+// chains queue behind the consumers' DMMAs on the shared pipe (a slot every ~64 cycles), so generation becomes the critical path;
+// with generation switched off the consumers run at 9.4 ms.  What works is the opposite: generate in BURSTS.  All 16 warps generate
+// the features of a BURST of chunks (up to 8: what fits beside the staged coordinates) at once (tens of independent items in flight,
+// four interleaved dependency chains per warp, nobody on the pipe: the latency is paid once per burst), one barrier, then they contract the burst chunk by chunk with NO CTA barrier: the coefficient chunks arrive by TMA bulk
+// copies (the coefficient kernel writes them chunk-major and padded, 20 KB contiguous each) into a ring of stages handed over
+// with mbarriers (full: the copy's bytes; empty: 16 warp arrivals).  The tile's coordinates are staged in shared memory TRANSPOSED
+// ([3 N][64], conformation fastest): in the tile layout the eight tiles a warp reads sit 3 N cpt doubles apart, i.e. in the same banks
+// (8-way conflicts: 13.6 -> 12.0 ms); molecules too large for that read them from global memory.
+// Measured on config 3 (ms): chunk-by-chunk 15.3 | producer / consumer 18.0 (4 producers), 14.2 (8) | bursts 13.5 | bursts overlapped
+// with the contraction by two warp groups 15.5 | bursts + staged transposed coordinates 12.0 | the contraction alone 9.5-9.9.
+#define EGP_KC 16
+#define EGP_CS 20
+#define EGB_STAGES 3      // coefficient-chunk ring
+#define EGB_THREADS 512
+
+// features of one term for conformation `s` read from the tiled ensemble in global memory -> rows of the burst buffer
+__device__ __forceinline__ void eg_features_global(const EgTerm tm, const double *__restrict__ base, int cpt,
+                                                   const double2 *__restrict__ s_acos, double *__restrict__ out) {
+    auto ld = [&](int a) {
+        const double *p = base + (size_t)(3 * a) * cpt;
+        return pm_d3{p[0], p[cpt], p[2 * cpt]};
+    };
+    if (tm.kind == 3) {
+        const pm_d3 d = pm_sub(ld(tm.a0), ld(tm.a1));
+        const double r2 = pm_dot(d, d);
+        const double rinv = pm_rsqrt(r2);
+        const double u = rinv * rinv, u3 = u * u * u;
+        out[0] = u3 * u3;
+        out[EG_GS] = u3;
+        out[2 * EG_GS] = rinv;
+    } else if (tm.kind == 0) {
+        const pm_d3 d = pm_sub(ld(tm.a0), ld(tm.a1));
+        const double r2 = pm_dot(d, d);
+        out[0] = r2;
+        out[EG_GS] = r2 * pm_rsqrt(r2);
+    } else if (tm.kind == 1) {
+        const pm_d3 xc = ld(tm.a1);
+        const pm_d3 da = pm_sub(xc, ld(tm.a0)), db = pm_sub(xc, ld(tm.a2));
+        const double ra2 = pm_dot(da, da), rb2 = pm_dot(db, db), dot = pm_dot(da, db);
+        const double rr = pm_rsqrt(ra2) * pm_rsqrt(rb2);
+        const double cosine = fmin(1.0, fmax(-1.0, dot * rr));
+        const double rp2 = fmax(fma(-dot, dot, ra2 * rb2), 0.0);
+        const bool tiny = rp2 <= 1.0e-12;
+        const double sine = tiny ? sqrt(rp2) * rr : rp2 * pm_rsqrt(rp2) * rr;
+        const double th = pm_acos_cs(cosine, sine, s_acos);
+        out[0] = th * th;
+        out[EG_GS] = th;
+    } else if (tm.kind == 2) {
+        const pm_d3 xj = ld(tm.a1), xk = ld(tm.a2);
+        const pm_d3 d0 = pm_sub(ld(tm.a0), xj), d1 = pm_sub(xk, xj), d2 = pm_sub(xk, ld(tm.a3));
+        const pm_d3 c1 = pm_cross(d0, d1), c2 = pm_cross(d1, d2);
+        const double nb2 = pm_dot(d1, d1);
+        const double rb = nb2 * pm_rsqrt(nb2);
+        const double inv12 = pm_rsqrt(pm_dot(c1, c1)) * pm_rsqrt(pm_dot(c2, c2));
+        const double cphi = pm_dot(c1, c2) * inv12;
+        const double sphi = rb * pm_dot(d0, c2) * inv12;
+        double cn = tm.per > 0 ? cphi : 1.0, sn = tm.per > 0 ? sphi : 0.0;
+        for (int mm = 1; mm < tm.per; ++mm) {
+            const double c_new = fma(cn, cphi, -(sn * sphi));
+            sn = fma(sn, cphi, cn * sphi);
+            cn = c_new;
+        }
+        out[0] = cn;
+        out[EG_GS] = sn;
+    } else {
+        out[0] = 1.0;
+    }
+}
+
+__global__ void __launch_bounds__(EGB_THREADS, 1)
+    pm_egemm_burst_kernel(int n_atoms, int cpt, const EgTerm *__restrict__ terms, const int *__restrict__ chunk_ptr, int n_chunks,
+                          const double *__restrict__ Cc, const double2 *__restrict__ acos_tab, const double *__restrict__ coords, long S,
+                          const double *__restrict__ eref, const double *__restrict__ wts, double d_shift, int n_vec, int n_z,
+                          int n_sc, int stage_x, int skip_gen, double *__restrict__ rows, double *__restrict__ emm) {
+    extern __shared__ __align__(128) double sm[];
+    double *Cs = sm;                                               // [EGB_STAGES][EG_PB][EGP_CS]
+    double *Gs = Cs + EGB_STAGES * EG_PB * EGP_CS;                 // [n_sc * EGP_KC][EG_GS]: the features of a burst of n_sc chunks
+    double *racc = Gs + (size_t)n_sc * EGP_KC * EG_GS;             // [4][EG_PB][4]
+    double2 *s_acos = reinterpret_cast<double2 *>(racc + 4 * EG_PB * 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_acos + PM_ACOS_N + 1);  // full[stage], empty[stage]
+    double *xs = reinterpret_cast<double *>(bars + 16);            // [3 N 64] the tile's coordinates (stage_x) -- else they are read from global memory
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pb = blockIdx.x / n_z, z = blockIdx.x - pb * n_z;
+    const int wr = warp >> 2, wc = warp & 3;  // 4 x 4 warps: 32 vectors x 16 conformations each
+    for (int i = tid; i <= PM_ACOS_N; i += EGB_THREADS) s_acos[i] = acos_tab[i];
+    for (int i = tid; i < 4 * EG_PB * 4; i += EGB_THREADS) racc[i] = 0.0;
+    for (int i = tid; i < n_sc * EGP_KC * EG_GS; i += EGB_THREADS) Gs[i] = 0.0;  // padding feature rows stay zero (finite)
+    if (tid == 0) {
+        for (int s = 0; s < EGB_STAGES; ++s) {
+            pm_mbar_init(&bars[s], 1);                       // full: the issuing lane (+ the copy's bytes)
+            pm_mbar_init(&bars[8 + s], EGB_THREADS / 32);    // empty: one arrival per warp
+        }
+        pm_fence_mbar_init();
+    }
+    __syncthreads();
+    const long n_stiles = (S + EG_ST - 1) / EG_ST;
+    const double *Cb = Cc + (size_t)pb * n_chunks * (EG_PB * EGP_CS);
+    long g_issue = 0, g_use = 0;  // chunks whose copy has been issued / that have been contracted (stage = g % EGB_STAGES)
+    auto issue = [&](int c) {     // thread 0: coefficient chunk c of this block into the next stage of the ring
+        const int s = (int)(g_issue % EGB_STAGES);
+        const uint32_t use = (uint32_t)(g_issue / EGB_STAGES);
+        if (use > 0) pm_mbar_wait(&bars[8 + s], (use - 1) & 1u);   // all warps are done with what the stage held
+        pm_fence_proxy_async();
+        pm_mbar_expect_tx(&bars[s], (uint32_t)(EG_PB * EGP_CS * sizeof(double)));
+        pm_bulk_g2s(Cs + (size_t)s * EG_PB * EGP_CS, Cb + (size_t)c * (EG_PB * EGP_CS), (uint32_t)(EG_PB * EGP_CS * sizeof(double)), &bars[s]);
+        ++g_issue;
+    };
+
+    auto conf_base = [&](long sc) {
+        if (sc >= S) sc = S - 1;   // columns beyond S are generated from the last conformation and never used
+        const long tile = sc / cpt;
+        return coords + (size_t)tile * 3 * n_atoms * cpt + (sc - tile * cpt);
+    };
+    for (long st = z; st < n_stiles; st += n_z) {
+        const long s0 = st * EG_ST;
+        double acc[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double *xb0 = conf_base(s0 + lane), *xb1 = conf_base(s0 + 32 + lane);
+        int xstride = cpt;   // doubles between the rows (x, y, z of the atoms) of a conformation
+        if (tid == 0)
+            for (int c = 0; c < EGB_STAGES - 1 && c < n_chunks; ++c) issue(c);   // the ring runs EGB_STAGES - 1 chunks ahead
+        if (stage_x) {
+            // the 64 conformations of the tile are contiguous in the tiled layout: stage them once (the generation reads every atom
+            // ~N times; from global memory that is L2 traffic, because the shared-memory footprint leaves almost no L1)
+            __syncthreads();  // nobody generates from the previous tile's coordinates any more
+            // staged TRANSPOSED, [3 N][64] with the conformation fastest: the lanes of a warp (consecutive conformations) then read
+            // consecutive doubles -- in the tile layout [3 N][cpt] the 8 tiles of a warp sit 3 N cpt doubles apart, i.e. in the same banks
+            const int tile_d = 3 * n_atoms * EG_ST, per_tile = 3 * n_atoms * cpt;
+            const long first = s0 / cpt * (long)per_tile;
+            long avail = ((S + cpt - 1) / cpt) * (long)per_tile - first;
+            if (avail > tile_d) avail = tile_d;
+            for (int i = tid; i < tile_d; i += EGB_THREADS) {
+                const int t = i / per_tile, rem = i - t * per_tile, r = rem / cpt, c = rem - r * cpt;
+                xs[r * EG_ST + t * cpt + c] = i < avail ? coords[first + i] : 1.0 + 0.37 * (i % 97);
+            }
+            xb0 = xs + lane;
+            xb1 = xs + 32 + lane;
+            xstride = EG_ST;
+        }
+        for (int c0 = 0; c0 < n_chunks; c0 += n_sc) {
+            const int c1 = c0 + n_sc < n_chunks ? c0 + n_sc : n_chunks;
+            __syncthreads();  // every warp has finished contracting the previous burst: its features may be overwritten
+            {
+                // items = (term, half of the 64 conformations); a warp takes FOUR items per pass and, when all four are pairs (87 % of
+                // the features), evaluates them as four interleaved dependency chains
+                const int t0 = chunk_ptr[c0], n_items = skip_gen ? 0 : 2 * (chunk_ptr[c1] - t0);
+                for (int i0 = 4 * warp; i0 < n_items; i0 += 4 * (EGB_THREADS / 32)) {
+                    EgTerm tm[4];
+                    bool all_pairs = i0 + 3 < n_items;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        tm[q] = terms[t0 + ((i0 + q < n_items ? i0 + q : i0) >> 1)];
+                        all_pairs = all_pairs && tm[q].kind == 3;
+                    }
+                    if (all_pairs) {
+                        double r2[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double *xb = ((i0 + q) & 1) ? xb1 : xb0;
+                            const double *pa = xb + (size_t)(3 * tm[q].a0) * xstride, *pc = xb + (size_t)(3 * tm[q].a1) * xstride;
+                            const double dx = pa[0] - pc[0], dy = pa[xstride] - pc[xstride], dz = pa[2 * xstride] - pc[2 * xstride];
+                            r2[q] = fma(dz, dz, fma(dy, dy, dx * dx));
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double rinv = pm_rsqrt(r2[q]);
+                            const double u = rinv * rinv, u3 = u * u * u;
+                            double *out = Gs + ((tm[q].pad - c0) * EGP_KC + tm[q].row) * EG_GS + 32 * ((i0 + q) & 1) + lane;
+                            out[0] = u3 * u3;
+                            out[EG_GS] = u3;
+                            out[2 * EG_GS] = rinv;
+                        }
+                    } else {
+                        for (int q = 0; q < 4 && i0 + q < n_items; ++q)
+                            eg_features_global(tm[q], ((i0 + q) & 1) ? xb1 : xb0, xstride, s_acos,
+                                               Gs + ((tm[q].pad - c0) * EGP_KC + tm[q].row) * EG_GS + 32 * ((i0 + q) & 1) + lane);
+                    }
+                }
+            }
+            __syncthreads();  // the burst's features are complete
+            for (int c = c0; c < c1; ++c, ++g_use) {
+                if (tid == 0 && c + EGB_STAGES - 1 < n_chunks) issue(c + EGB_STAGES - 1);
+                const int s = (int)(g_use % EGB_STAGES);
+                pm_mbar_wait(&bars[s], (uint32_t)(g_use / EGB_STAGES) & 1u);
+                const double *pa = Cs + (size_t)s * EG_PB * EGP_CS + (32 * wr + (lane >> 2)) * EGP_CS + (lane & 3);
+                const double *pg = Gs + ((c - c0) * EGP_KC + (lane & 3)) * EG_GS + 16 * wc + (lane >> 2);
+#pragma unroll
+                for (int k4 = 0; k4 < EGP_KC / 4; ++k4) {
+                    double a[4], bq[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = pa[(8 * i) * EGP_CS + 4 * k4];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) bq[j] = pg[(4 * k4) * EG_GS + 8 * j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) eg_dmma(acc[i][j], a[i], bq[j]);
+                }
+                __syncwarp();
+                if (lane == 0) pm_mbar_arrive(&bars[8 + s]);
+            }
+        }
+        // epilogue: E[p][s] for p = 128 pb + 32 wr + 8 i + lane / 4, s = s0 + 16 wc + 8 j + 2 (lane % 4) + {0, 1}
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pl = 32 * wr + 8 * i + (lane >> 2);
+            const long p = (long)pb * EG_PB + pl;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const long sc = s0 + 16 * wc + 8 * j + 2 * (lane & 3) + e;
+                    if (sc < S && p < n_vec) {
+                        const double en = acc[i][j][e];
+                        if (emm != nullptr) emm[(size_t)p * S + sc] = en;
+                        const double d = (eref != nullptr ? eref[sc] : 0.0) - en - d_shift;
+                        const double ws = wts != nullptr ? wts[sc] : 1.0;
+                        q0 += d;
+                        q1 = fma(ws, d, q1);
+                        q2 = fma(ws * d, d, q2);
+                        q3 += ws;
+                    }
+                }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+                q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+                q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+            }
+            if ((lane & 3) == 0) {
+                double *r = racc + ((size_t)wc * EG_PB + pl) * 4;
+                r[0] += q0;
+                r[1] += q1;
+                r[2] += q2;
+                r[3] += q3;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < EG_PB * 5; i += EGB_THREADS) {
+        const int pl = i / 5, q = i - pl * 5;
+        const long p = (long)pb * EG_PB + pl;
+        if (p < n_vec) {
+            double v = 0.0;
+            if (q < 4)
+                for (int gq = 0; gq < 4; ++gq) v += racc[((size_t)gq * EG_PB + pl) * 4 + q];
+            rows[((size_t)p * n_z + z) * 5 + q] = v;
+        }
+    }
+}
+
+// the coefficient matrix chunk-major and padded for the bulk copies of the pipeline: Cc[block][chunk][128][20]
+__global__ void pm_egemm_chunk_kernel(const double *__restrict__ C, int n_feat, int n_chunks, double *__restrict__ Cc) {
+    const size_t total = (size_t)gridDim.y * n_chunks * EG_PB * EGP_CS;
+    (void)total;
+    const int pbk = blockIdx.y;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_chunks * EG_PB * EGP_CS; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % EGP_CS);
+        const size_t rc = i / EGP_CS;
+        const int row = (int)(rc % EG_PB), c = (int)(rc / EG_PB);
+        Cc[(size_t)pbk * n_chunks * EG_PB * EGP_CS + i] = k < EGP_KC ? C[((size_t)pbk * EG_PB + row) * n_feat + (size_t)c * EGP_KC + k] : 0.0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------------
@@ -366,7 +643,7 @@ static pm_egemm_s *pm_egemm_plan(pm_handle h) {
         }
         EgTerm t;
         t.a0 = a0; t.a1 = a1; t.a2 = a2; t.a3 = a3;
-        t.kind = kind; t.per = per; t.row = row; t.pad = 0;
+        t.kind = kind; t.per = per; t.row = row; t.pad = (int)chunk_ptr.size() - 1;
         terms.push_back(t);
         for (int k = 0; k < n_f; ++k) feats.push_back(f[k]);
         row += n_f;
@@ -426,6 +703,30 @@ static size_t pm_egemm_smem(int n_atoms, int kc) {
            sizeof(double2) * (PM_ACOS_N + 1);
 }
 
+static size_t pm_egemm_burst_smem(int n_sc, int n_atoms_staged) {
+    return sizeof(double) * ((size_t)EGB_STAGES * EG_PB * EGP_CS + (size_t)n_sc * EGP_KC * EG_GS + 4 * EG_PB * 4 + (size_t)3 * n_atoms_staged * EG_ST) +
+           sizeof(double2) * (PM_ACOS_N + 1) + 16 * sizeof(uint64_t);
+}
+
+// burst size (chunks of 16 features) and whether the tile's coordinates are staged in shared memory: the largest burst up to 8 that
+// fits beside the staged coordinates; molecules whose tile leaves room for fewer than 2 chunks read coordinates from global memory
+static void pm_egemm_burst_plan(pm_handle h, int *n_sc, int *stage_x) {
+    for (int sc = 8; sc >= 2; --sc)
+        if (pm_egemm_burst_smem(sc, h->prog.n_atoms) <= (size_t)h->max_smem) {
+            *n_sc = sc;
+            *stage_x = 1;
+            return;
+        }
+    *n_sc = 8;
+    *stage_x = 0;
+}
+
+// 1: generation in bursts + TMA-streamed coefficients (default); 0: the chunk-by-chunk kernel (PM_EGEMM_BURST=0, sweeps)
+static int pm_egemm_use_burst() {
+    const char *e = getenv("PM_EGEMM_BURST");
+    return !(e && e[0] == '0');
+}
+
 static int pm_egemm_nz(pm_handle h, int n_vec, long n_conf) {
     const int n_pb = (n_vec + EG_PB - 1) / EG_PB;
     long z = h->n_sm / n_pb;
@@ -437,7 +738,7 @@ static int pm_egemm_nz(pm_handle h, int n_vec, long n_conf) {
 extern "C" int pm_energy_batch_supported(pm_handle h) {
     if (!h) return 0;
     return !h->rf && h->prog.n_pairs + h->prog.n_bonds + h->prog.n_angles + h->prog.n_torsions > 0 &&
-           pm_egemm_smem(h->prog.n_atoms, 16) <= (size_t)h->max_smem;
+           (pm_egemm_use_burst() || pm_egemm_smem(h->prog.n_atoms, 16) <= (size_t)h->max_smem);
 }
 
 extern "C" long pm_energy_batch_scratch_doubles(pm_handle h, int n_vec, long n_conf) {
@@ -445,7 +746,8 @@ extern "C" long pm_energy_batch_scratch_doubles(pm_handle h, int n_vec, long n_c
     const int n_pb = (n_vec + EG_PB - 1) / EG_PB;
     const long t_max = 2L * h->prog.n_bonds + 2L * h->prog.n_angles + 2L * h->prog.n_torsions + 3L * h->prog.n_pairs + 1;
     const long n_feat = ((t_max * 16 / 15 + 4 * 32) / 32) * 32;  // upper bound of the padded feature count
-    return (long)n_pb * EG_PB * n_feat + (long)n_vec * pm_egemm_nz(h, n_vec, n_conf) * 5;
+    // C row-major, its chunk-major padded copy (x 20/16), the rows
+    return (long)n_pb * EG_PB * n_feat + (long)n_pb * EG_PB * (n_feat / 16) * EGP_CS + (long)n_vec * pm_egemm_nz(h, n_vec, n_conf) * 5;
 }
 
 extern "C" int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, int n_vec, const double *coord_tiles_dev, long n_conf,
@@ -455,20 +757,35 @@ extern "C" int pm_energy_batch_reduce(pm_handle h, const double *derived_dev, in
     if (n_vec < 1 || n_conf < 1) return pm_fail_msg("pm_energy_batch_reduce: empty batch");
     if (h->rf) return pm_fail_msg("pm_energy_batch_reduce: the reaction-field variant is not linear in the pair coefficients; use pm_eval_reduce");
     if (comm && n_vec > pm_comm_max_vec(comm)) return pm_fail_msg("pm_energy_batch_reduce: more parameter vectors than the communicator was created for");
-    if (pm_egemm_smem(h->prog.n_atoms, 16) > (size_t)h->max_smem)
-        return pm_fail_msg("pm_energy_batch_reduce: molecule too large for the coordinate tile of this kernel generation");
+    if (!pm_egemm_use_burst() && pm_egemm_smem(h->prog.n_atoms, 16) > (size_t)h->max_smem)
+        return pm_fail_msg("pm_energy_batch_reduce: molecule too large for the coordinate tile of the chunk-by-chunk kernel");
     PMG_CUDA(cudaSetDevice(h->device));
     pm_egemm_s *e = pm_egemm_plan(h);
     if (!e) return pm_fail_msg("pm_energy_batch_reduce: could not build the feature table");
     const size_t smem = pm_egemm_smem(h->prog.n_atoms, e->kc);
     cudaStream_t st = (cudaStream_t)stream;
     const int n_pb = (n_vec + EG_PB - 1) / EG_PB, n_z = pm_egemm_nz(h, n_vec, n_conf);
+    const int n_stages = (e->kc == EGP_KC && pm_egemm_use_burst()) ? EGB_STAGES : 0;
     double *C = scratch_dev;
-    double *rows = scratch_dev + (size_t)n_pb * EG_PB * e->n_feat;
+    double *Cc = C + (size_t)n_pb * EG_PB * e->n_feat;
+    double *rows = Cc + (n_stages ? (size_t)n_pb * e->n_chunks * EG_PB * EGP_CS : 0);
     const PmProg &g = h->prog;
     pm_egemm_coef_kernel<<<n_pb * EG_PB, 256, 0, st>>>(derived_dev, n_vec, g.n_derived, e->feat_dev, e->n_feat, g.doff_bond, g.n_bonds, g.doff_angle,
                                                        g.n_angles, g.doff_tors, g.n_torsions, C);
     PMG_CUDA(cudaGetLastError());
+    if (n_stages) {
+        pm_egemm_chunk_kernel<<<dim3(64, n_pb), 256, 0, st>>>(C, e->n_feat, e->n_chunks, Cc);
+        PMG_CUDA(cudaGetLastError());
+        int n_sc = 8, stage_x = 0;
+        pm_egemm_burst_plan(h, &n_sc, &stage_x);
+        const size_t smem_b = pm_egemm_burst_smem(n_sc, stage_x ? g.n_atoms : 0);
+        PMG_CUDA(cudaFuncSetAttribute((const void *)pm_egemm_burst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        pm_egemm_burst_kernel<<<n_pb * n_z, EGB_THREADS, smem_b, st>>>(g.n_atoms, g.cpw, e->terms_dev, e->chunk_ptr_dev, e->n_chunks, Cc, g.acos_tab,
+                                                                       coord_tiles_dev, n_conf, eref_dev, weights_dev, d_shift, n_vec, n_z,
+                                                                       n_sc, stage_x, getenv("PM_EGEMM_NOGEN") ? 1 : 0, rows, emm_dev);   // (NOGEN: timing experiments)
+        PMG_CUDA(cudaGetLastError());
+        return pm_reduce_rows(rows, n_z, n_vec, n_conf, partials_dev, comm, st);
+    }
     auto kernel = e->kc == 32 ? pm_egemm_kernel<32> : pm_egemm_kernel<16>;
     PMG_CUDA(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<n_pb * n_z, EG_THREADS, smem, st>>>(g.n_atoms, g.cpw, e->terms_dev, e->chunk_ptr_dev, e->n_chunks, e->n_feat, C, g.acos_tab,
