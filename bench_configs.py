@@ -165,7 +165,7 @@ def config3(fp64_peak, P=256, S=100_000, n_atoms=60):
                 conf_evals_per_s=P * S / (ms * 1e-3), objective_evals_per_s=P / (ms * 1e-3),
                 energy_only_ms=ms_e, energy_only_conf_evals_per_s=P * S / (ms_e * 1e-3),
                 energy_batch_contraction=dict(ms=ms_g, conf_evals_per_s=P * S / (ms_g * 1e-3), features=n_feat,
-                                              kernel="pm_egemm_kernel (DMMA.8x8x4), geometry features generated once per conformation",
+                                              kernel="pm_egemm_burst_kernel (DMMA.8x8x4): geometry features generated once per conformation in bursts, coefficients streamed by TMA",
                                               roofline=dict(bound="fp64", achieved=tf_g, peak=fp64_peak, unit="TFLOP/s", frac=tf_g / fp64_peak,
                                                             note="2 P S T flop of the contraction / time; the term-pass kernel above does the same job in energy_only_ms")),
                 roofline=dict(bound="fp64", achieved=tf, peak=fp64_peak, unit="TFLOP/s", frac=tf / fp64_peak, flops_per_conformation=fl),

@@ -206,7 +206,11 @@ class ParaMolSystem:
             rows.append(self.engine.current_slots())
         ens = self.device_ensemble()
         derived = ens.topology.prepare(torch.from_numpy(np.ascontiguousarray(np.stack(rows))).to(ens.device))
-        emm, _, _ = ens.evaluate(derived, with_forces=False)
+        if derived.shape[0] >= 16 and ens.energy_batch_supported():
+            # many generations: geometry once per conformation, energies by the batch contraction (pm_energy_batch_reduce)
+            _, emm = ens.energy_batch_reduce(derived, want_emm=True)
+        else:
+            emm, _, _ = ens.evaluate(derived, with_forces=False)
         exp_energies = np.exp(-0.5 * emm.cpu().numpy())
         weights = exp_energies / np.sum(exp_energies, axis=1, keepdims=True)
         prev_weight = weights[current_gen, :]
