@@ -75,6 +75,41 @@ def main():
             assert torch.equal(gt, ref_g), "ranks disagree on the gradient"
             if rank == 0:
                 np.save(os.path.join(REPO, "gpurun_out", "dist_grad_%s_w%d.npy" % (weighting, world)), g)
+    # ---- energy-only batches (pm_energy_batch_reduce, the cross-GPU sum inside the row-sum kernel) and the LLS fit (one all-reduce
+    # each of extrema, column sums, normal equations and refinement gradients): sharded == all conformations on one GPU
+    from paramol_b200.MM_engines.least_square import LinearLeastSquare
+    for shard in (True, False):
+        import contextlib
+        from paramol_b200.Utils import dist as pdist
+        # the unsharded reference runs with every distributed helper switched to single-rank behaviour (both ranks compute it)
+        with (contextlib.nullcontext() if shard else pdist.local_only()):
+            engine = B200Engine(True, topology_format="AMBER", crd_format="AMBER", top_file=os.path.join(GOLDEN, "aniline.prmtop"),
+                                crd_file=os.path.join(GOLDEN, "aniline.inpcrd"))
+            system = ParaMolSystem("aniline", engine, 14, ref_coordinates=X.copy(), ref_energies=E.copy(), ref_forces=F.copy())
+            system.force_field.create_force_field(opt_bonds=True, opt_angles=True, opt_torsions=True)
+            if shard:
+                system.shard_for_rank()
+            ps = ParameterSpace()
+            _, x0 = ps.get_optimizable_parameters([system])
+            x0 = np.asarray(x0)
+            e_prop = EnergyProperty([system])
+            e_prop.calculate_variance()
+            ps.calculate_prior_widths("default")
+            of = ObjectiveFunction(None, ps, [e_prop, Regularization(x0.copy(), ps.prior_widths, "L2")], [system], weighting_method="uniform",
+                                   checkpoint_freq=10 ** 9)
+            rngx = np.random.default_rng(5)
+            trial = np.stack([x0 * (1.0 + 0.01 * rngx.uniform(-1, 1, x0.shape)) for _ in range(20)])   # >= 16: the contraction route
+            vals = np.asarray(of.f_batch(trial))
+            ps.update_systems([system], x0)
+            ps.get_optimizable_parameters([system], symmetry_constrained=False)
+            lls = LinearLeastSquare(ps, True, method="L2", scaling_factor=1.0, hyperbolic_beta=0.01, weighting_method="uniform",
+                                    weighting_temperature=300.0)
+            lls.fit_parameters_lls([system])
+            fitted = np.asarray(lls._parameters, dtype=np.float64)
+        if rank == 0:
+            tag = "shard" if shard else "full"
+            np.save(os.path.join(REPO, "gpurun_out", "dist_ebatch_%s_w%d.npy" % (tag, world)), vals)
+            np.save(os.path.join(REPO, "gpurun_out", "dist_lls_%s_w%d.npy" % (tag, world)), fitted)
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d ok" % rank)

@@ -29,7 +29,9 @@ def _run(world):
     out = {w: np.load(os.path.join(REPO, "gpurun_out", "dist_values_%s_w%d.npy" % (w, world)))
            for w in ("uniform", "boltzmann", "non_boltzmann")}
     grads = {w: np.load(os.path.join(REPO, "gpurun_out", "dist_grad_%s_w%d.npy" % (w, world))) for w in ("uniform", "boltzmann")}
-    return out, grads
+    extra = {k: np.load(os.path.join(REPO, "gpurun_out", "dist_%s_w%d.npy" % (k, world)))
+             for k in ("ebatch_shard", "ebatch_full", "lls_shard", "lls_full")}
+    return out, grads, extra
 
 
 def test_sharded_objective_equals_single_gpu():
@@ -37,8 +39,11 @@ def test_sharded_objective_equals_single_gpu():
     n_gpu = torch.cuda.device_count()
     if n_gpu < 2:
         pytest.skip("needs at least 2 GPUs")
-    single, single_g = _run(1)
-    multi, multi_g = _run(2)
+    single, single_g, _ = _run(1)
+    multi, multi_g, extra = _run(2)
+    # energy-only batch through the contraction kernel and the LLS fit: 2 ranks on shards == rank 0 alone on everything
+    assert np.all(np.abs(extra["ebatch_shard"] - extra["ebatch_full"]) <= 1e-10 * np.abs(extra["ebatch_full"]))
+    assert np.abs(extra["lls_shard"] - extra["lls_full"]).max() <= 1e-8 * np.abs(extra["lls_full"]).max()
     for w in single_g:   # analytic gradient: the shards' term gradients are summed by one allreduce
         assert np.abs(single_g[w] - multi_g[w]).max() <= 1e-10 * np.abs(single_g[w]).max(), w
     for w in single:
