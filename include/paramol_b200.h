@@ -69,7 +69,9 @@ int pm_device_count(void);
 
 /* ---- handle ------------------------------------------------------------------------------------ */
 /* Replaces OpenMMEngine.init_openmm / Context creation (ParaMol/MM_engines/openmm.py:161-254).
- * conf_per_tile: conformations per tile (32, 16, 8 or 4), or 0 to let the library choose per topology.  The
+ * conf_per_tile: conformations per tile (32, 16, 8 or 4: a conformation is evaluated by a team of 32 / conf_per_tile lanes of one
+ * warp), -8: tiles of 32 conformations evaluated by teams of 8 WARPS (one lane per conformation, the warps share the tile), or 0 to
+ * let the library choose per topology.  The
  * topology-specialised kernels (pm_set_specialized) need 32. */
 int pm_create(const pm_topology *topo, int device, int conf_per_tile, pm_handle *out);
 int pm_destroy(pm_handle h);

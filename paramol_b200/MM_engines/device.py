@@ -87,7 +87,8 @@ class DeviceTopology:
     device : int or None
         CUDA device index (default: current device).
     conf_per_tile : int or None
-        Conformations per tile (32, 16, 8, 4); None lets the library choose (``pm_create(..., conf_per_tile=0, ...)``).
+        Conformations per tile (32, 16, 8, 4: teams of 32 / conf_per_tile lanes per conformation), -8 (tiles of 32 conformations
+        shared by teams of 8 warps), or None to let the library choose (``pm_create(..., conf_per_tile=0, ...)``).
 
     ``specialize_status`` says which E+F kernel serves full evaluations: "installed" (generated for this topology), "not eligible"
     (molecule too large / reaction field / switched off) or the reason the generated kernel could not be built or installed.

@@ -60,6 +60,7 @@ struct pm_handle_s {
     int *d_pair_map;
     double2 *d_acos;
     int warps[2];  // [with_forces]
+    int team_warps;  // 0: a team is 32 / cpw lanes of one warp; 8: a team is 8 warps sharing a tile of 32 conformations
     int maxw[2];   // kernel variant (registers per thread) per [with_forces]
     int rf;        // reaction-field variant
     size_t smem_total[2];

@@ -193,10 +193,11 @@ __device__ __forceinline__ double pm_axis_cells(const int *__restrict__ cells, c
     return A;
 }
 
-// Force write-back of one step.  One lane per conformation (L == 1): plain.  Teams: the records of a step that share a
-// colour touch disjoint atoms (pm_program.hpp), colours are serialised with __syncwarp between them.
+// Force write-back of one step.  One lane per conformation (L == 1): plain.  Teams of lanes: the records of a step that share a
+// colour touch disjoint atoms (pm_program.hpp), colours are serialised with __syncwarp between them.  Teams of WARPS (WT): the
+// records of a step are disjoint by construction (one colour), the step ends with a barrier of the team.
 #define PM_ORDERED(n_col, colour, cond, ...)           \
-    if (L == 1) {                                      \
+    if (L == 1 || WT) {                                \
         if (cond) __VA_ARGS__                          \
     } else {                                           \
         for (int _c = 0; _c < (n_col); ++_c) {         \
@@ -207,16 +208,29 @@ __device__ __forceinline__ double pm_axis_cells(const int *__restrict__ cells, c
 
 // MAXW = warps per CTA the variant is compiled for: 16 (128 registers per thread), 14 (144) or 12 (168 registers, no spills).
 // Measured on B200: when shared memory admits at most 12 warps anyway, the 168-register variant is 5-10 % faster.
-template <int CPW, bool WITH_F, int MAXW, bool RF = false>
+// TW > 1 ("teams of warps", CPW = 32): a tile of 32 conformations is shared by TW WARPS; lane = conformation, so every index and
+// parameter read is warp-uniform and no branch diverges (as with one lane per conformation), while the shared-memory state per
+// conformation in flight stays 48 N bytes (as with teams of lanes).  The TW warps of a team take the records of a step like the
+// lanes of a lane-team do, with a named barrier where those use __syncwarp.
+template <int CPW, bool WITH_F, int MAXW, bool RF = false, int TW = 1>
 __global__ void __launch_bounds__(MAXW * 32, 1)
     pm_ef_kernel(PmProg g, const double *__restrict__ derived, int n_vec, const double *__restrict__ xt,
                  const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm,
                  double *__restrict__ fres, double *__restrict__ fmm_t, PmRed red) {
-    constexpr int L = 32 / CPW;
+    constexpr bool WT = TW > 1;
+    static_assert(!WT || CPW == 32, "teams of warps work on tiles of 32 conformations");
+    constexpr int L = WT ? TW : 32 / CPW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const int col = lane % CPW;  // conformation inside the tile
-    const int tl = lane / CPW;   // team lane
+    const int col = WT ? lane : lane % CPW;       // conformation inside the tile
+    const int tl = WT ? warp % TW : lane / CPW;   // member of the team
+    const int team = WT ? warp / TW : warp, n_teams = WT ? n_warps / TW : n_warps;
+    auto team_sync = [&]() {
+        if (WT)
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * TW) : "memory");
+        else
+            __syncwarp();
+    };
     const int N = g.n_atoms;
     const int tile_d = 3 * N * CPW;
 
@@ -232,25 +246,27 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     off = (off + 127) & ~(size_t)127;
     // a tile is followed by the three rows of the padding atom (pair blocks of teams; zero coordinates, forces never read)
     const int tile_p = tile_d + 3 * CPW;
-    const size_t per_warp = 128 + (size_t)tile_p * sizeof(double) * (WITH_F ? 2 : 1);
-    unsigned char *wbase = smem_raw + off + per_warp * warp;
+    const size_t per_warp = 128 + (size_t)tile_p * sizeof(double) * (WITH_F ? 2 : 1) + (WT ? (size_t)TW * 64 * sizeof(double) : 0);
+    unsigned char *wbase = smem_raw + off + per_warp * team;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
-    double *racc = reinterpret_cast<double *>(wbase + 64);  // fused residual reduction: this warp's 5 running sums
+    double *racc = reinterpret_cast<double *>(wbase + 64);  // fused residual reduction: this team's 5 running sums
     double *xs = reinterpret_cast<double *>(wbase + 128);
     double *fs = xs + tile_p;  // only touched when WITH_F
+    double *tsc = xs + tile_p * (WITH_F ? 2 : 1);  // teams of warps: [TW][32][2] partial (energy, residual) of the members
     const bool want_res = WITH_F && fref_t != nullptr;
 
     for (int i = threadIdx.x; i < g.n_int; i += blockDim.x) s_int[i] = g.ints[i];
     for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = g.acos_tab[i];
     for (int i = threadIdx.x; i < 9 * N; i += blockDim.x) s_metric[i] = g.metric[i];
-    if (lane == 0) {
+    if (lane == 0 && (!WT || tl == 0)) {
         pm_mbar_init(bar, 1);
         pm_fence_mbar_init();
     }
-    if (lane < 3 * CPW) {
-        xs[tile_d + lane] = 0.0;
-        if (WITH_F) fs[tile_d + lane] = 0.0;
-    }
+    if (!WT || tl == 0)
+        for (int k = lane; k < 3 * CPW; k += 32) {
+            xs[tile_d + k] = 0.0;
+            if (WITH_F) fs[tile_d + k] = 0.0;
+        }
     uint32_t parity = 0;
 
     const int2 *s_star_tab = reinterpret_cast<const int2 *>(s_int + g.off_star_tab);
@@ -264,8 +280,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const int4 *s_seg_tile = reinterpret_cast<const int4 *>(s_int + g.off_seg_tile);
     const int2 *s_entries = reinterpret_cast<const int2 *>(s_int + g.off_entries);
 
-    const long warp_stride = (long)gridDim.x * n_warps;
-    const long first_tile = (long)blockIdx.x * n_warps + warp;
+    const long warp_stride = (long)gridDim.x * n_teams;
+    const long first_tile = (long)blockIdx.x * n_teams + team;
 
     for (int p = 0; p < n_vec; ++p) {
         __syncthreads();  // everybody done with the previous derived table (and the int blob is staged)
@@ -282,12 +298,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
         const double2 *s_pangle = reinterpret_cast<const double2 *>(s_der + g.doff_angle);
         const double2 *s_ptors = reinterpret_cast<const double2 *>(s_der + g.doff_tors);
         const double *s_ppair = s_der + g.doff_pair;
-        if (red.rows != nullptr && lane < 5) racc[lane] = 0.0;
+        if (red.rows != nullptr && lane < 5 && (!WT || tl == 0)) racc[lane] = 0.0;
 
         for (long tile = first_tile; tile < n_tiles; tile += warp_stride) {
             // ---- coordinates of CPW conformations: one TMA bulk copy into this warp's tile ---------
             const bool nb_cached = g.nb_e != nullptr;
-            if (lane == 0) {
+            if (lane == 0 && (!WT || tl == 0)) {
                 pm_fence_proxy_async();
                 const uint32_t tile_bytes = (uint32_t)(tile_d * sizeof(double));
                 pm_mbar_expect_tx(bar, (WITH_F && nb_cached) ? 2 * tile_bytes : tile_bytes);
@@ -302,11 +318,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * tile_d, (uint32_t)(tile_d * sizeof(double)));
             }
             if (WITH_F && !nb_cached) {
-                for (int k = lane; k < tile_d; k += 32) fs[k] = 0.0;
+                if (WT)
+                    for (int k = tl * 32 + lane; k < tile_d; k += 32 * L) fs[k] = 0.0;
+                else
+                    for (int k = lane; k < tile_d; k += 32) fs[k] = 0.0;
             }
             pm_mbar_wait(bar, parity);
             parity ^= 1;
-            __syncwarp();
+            team_sync();
 
             double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
             if (nb_cached && tl == 0 && tile * CPW + col < n_conf) e_nb = g.nb_e[tile * CPW + col];
@@ -403,6 +422,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, center, fc);
                     })
                 }
+                if (WT) team_sync();  // the next step's records may touch the atoms this step's members just updated
             }
 
             // ================= axes: every torsion around a rotation axis j-k (trig-free) ================
@@ -456,9 +476,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     }
                 }
                 pm_d3 Fj{0.0, 0.0, 0.0}, Fk{0.0, 0.0, 0.0};
-                const int ni_loop = L > 1 ? (hdr >> 8) : nI;
+                const int ni_loop = (L > 1 && !WT) ? (hdr >> 8) : nI;   // (teams of lanes: the longest record of the step)
                 for (int pi = 0; pi < ni_loop; ++pi) {
-                    const bool act = L == 1 || (live && pi < nI);
+                    const bool act = L == 1 || WT || (live && pi < nI);
                     int ai = 0;
                     pm_d3 fi{0.0, 0.0, 0.0};
                     if (act) {
@@ -468,7 +488,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         const pm_d3 c1 = pm_cross(d0, d1);
                         const double s1 = pm_rsqrt(pm_dot(c1, c1));
                         double A = 0.0;
-                        if (L == 1 && simple) {  // (with teams the lanes of a step would diverge between the two paths)
+                        if ((L == 1 || WT) && simple) {  // (with teams of lanes the lanes of a step would diverge between the two paths)
                             if (nL == 2)
                                 A = pm_axis_cells<2, WITH_F>(cells, s_axis_terms, s_ptors, c1, d0, s1, rb, c2, s2, B, e_tors);
                             else if (nL == 3)
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, ak, Fk);
                     })
                 }
+                if (WT) team_sync();
             }
 
             // ================= nonbonded, teams: 4 x 4 register blocks on disjoint tile pairs ====================
@@ -568,7 +589,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #pragma unroll
                         for (int m = 0; m < 4; ++m) pm_subo<CPW>(fc_base, jo[m], aj[m]);
                     }
-                    __syncwarp();
+                    team_sync();
                 }
             }
             // ================= nonbonded: plain pairs and scaled 1-4 exceptions, register-tiled over i ========
@@ -643,7 +664,20 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     res += fma(t2, dz, fma(t1, dy, t0 * dx));
                 }
             }
-            if (L > 1) {
+            if (WT) {
+                // the members' partial energies and residuals of each conformation: through shared memory, added in member order
+                tsc[(tl * 32 + lane) * 2] = e_total;
+                tsc[(tl * 32 + lane) * 2 + 1] = res;
+                team_sync();
+                if (tl == 0) {
+                    e_total = 0.0;
+                    res = 0.0;
+                    for (int m = 0; m < L; ++m) {
+                        e_total += tsc[(m * 32 + lane) * 2];
+                        res += tsc[(m * 32 + lane) * 2 + 1];
+                    }
+                }
+            } else if (L > 1) {
 #pragma unroll
                 for (int o = CPW; o < 32; o <<= 1) {
                     e_total += __shfl_xor_sync(0xffffffffu, e_total, o);
@@ -654,8 +688,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 if (emm != nullptr) emm[(size_t)p * n_conf + sconf] = e_total;
                 if (WITH_F && fres != nullptr) fres[(size_t)p * n_conf + sconf] = res;
             }
-            if (red.rows != nullptr) {
-                // fused pm_reduce_objective: the five weighted sums of this tile join the warp's running sums (fixed order:
+            if (red.rows != nullptr && (!WT || tl == 0)) {
+                // fused pm_reduce_objective: the five weighted sums of this tile join the team's running sums (fixed order:
                 // deterministic for a given launch geometry); no [P][S] arrays are written or re-read
                 double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
                 if (tl == 0 && sconf < n_conf) {
@@ -682,13 +716,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             }
             if (WITH_F && fmm_t != nullptr) {
                 double *fo = fmm_t + ((size_t)p * n_tiles + tile) * tile_d;
-                for (int k = lane; k < tile_d; k += 32) fo[k] = fs[k];
+                if (WT)
+                    for (int k = tl * 32 + lane; k < tile_d; k += 32 * L) fo[k] = fs[k];
+                else
+                    for (int k = lane; k < tile_d; k += 32) fo[k] = fs[k];
             }
-            __syncwarp();
+            team_sync();  // the tile (and, for teams of warps, the scratch of the members) is free again
         }
-        if (red.rows != nullptr) {
+        if (red.rows != nullptr && (!WT || tl == 0)) {
             __syncwarp();
-            if (lane < 5) red.rows[(((size_t)p * gridDim.x + blockIdx.x) * n_warps + warp) * 5 + lane] = racc[lane];
+            if (lane < 5) red.rows[(((size_t)p * gridDim.x + blockIdx.x) * n_teams + team) * 5 + lane] = racc[lane];
         }
     }
 }
@@ -850,7 +887,12 @@ static pm_ef_fn pm_pick_kernel_w(int cpw, int wf) {
         default: return nullptr;
     }
 }
-static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw, int rf = 0) {
+#define PM_TEAM_WARPS 8  // members of a team of warps (the one size compiled)
+static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw, int rf = 0, int team_warps = 0) {
+    if (team_warps > 1) {  // teams of PM_TEAM_WARPS warps: 8 warps per CTA (168 registers) or 16 (128 registers)
+        if (maxw <= 12) return wf ? pm_ef_kernel<32, true, 8, false, PM_TEAM_WARPS> : pm_ef_kernel<32, false, 8, false, PM_TEAM_WARPS>;
+        return wf ? pm_ef_kernel<32, true, 16, false, PM_TEAM_WARPS> : pm_ef_kernel<32, false, 16, false, PM_TEAM_WARPS>;
+    }
     if (rf) return wf ? pm_ef_kernel<32, true, 12, true> : pm_ef_kernel<32, false, 12, true>;  // CPW 32 only
     return maxw <= 12 ? pm_pick_kernel_w<12>(cpw, wf) : maxw <= 14 ? pm_pick_kernel_w<14>(cpw, wf) : pm_pick_kernel_w<16>(cpw, wf);
 }
@@ -867,18 +909,24 @@ extern "C" int pm_device_count(void) {
 }
 
 // shared-memory plan for a given CPW: bytes shared by the CTA, per-warp bytes, warps that fit
-static void pm_plan(int n_int, int n_derived, int N, int cpw, int max_smem, int wf, size_t *shared, size_t *per_warp, int *warps) {
+static void pm_plan(int n_int, int n_derived, int N, int cpw, int max_smem, int wf, size_t *shared, size_t *per_warp, int *warps,
+                    int team_warps = 0) {
     size_t off = ((size_t)n_int * sizeof(int) + 15) & ~(size_t)15;
     off += (size_t)(PM_ACOS_N + 1) * sizeof(double2);
     off += ((size_t)9 * N * sizeof(double) + 15) & ~(size_t)15;
     off += (size_t)(n_derived + 4) * sizeof(double);
     off = (off + 127) & ~(size_t)127;
-    const size_t pw = 128 + (size_t)3 * (N + 1) * cpw * sizeof(double) * (wf ? 2 : 1);  // tile + the rows of the padding atom
-    long w = ((long)max_smem - (long)off) / (long)pw;
+    size_t pw = 128 + (size_t)3 * (N + 1) * cpw * sizeof(double) * (wf ? 2 : 1);  // tile + the rows of the padding atom
+    if (team_warps > 1) pw += (size_t)team_warps * 64 * sizeof(double);           // + the members' partial (energy, residual) per conformation
+    long w = ((long)max_smem - (long)off) / (long)pw;                             // tiles (= teams, or warps) that fit
+    if (team_warps > 1) {
+        if (w > PM_MAX_WARPS / team_warps) w = PM_MAX_WARPS / team_warps;
+        w *= team_warps;                                                          // warps
+    }
     if (w > PM_MAX_WARPS) w = PM_MAX_WARPS;
     if (w < 0) w = 0;
     *shared = off;
-    *per_warp = pw;
+    *per_warp = pw;   // per TEAM for teams of warps
     *warps = (int)w;
 }
 
@@ -913,18 +961,23 @@ static int pm_classify(const pm_topology *t, std::vector<int> &cls) {
 // stats10 as pm_program_info.  Returns 0 when the program is valid.
 extern "C" int pm_program_check(const pm_topology *t, int cpw, int *stats10) {
     if (!t) return pm_fail("pm_program_check: null argument");
-    if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_program_check: cpw must be 32, 16, 8 or 4");
+    int team_warps = 0;
+    if (cpw == -PM_TEAM_WARPS) {  // teams of warps on tiles of 32 conformations
+        cpw = 32;
+        team_warps = PM_TEAM_WARPS;
+    }
+    if (cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_program_check: cpw must be 32, 16, 8, 4 or -8");
     if (t->n_atoms < 1 || t->n_atoms > 65535) return pm_fail("pm_program_check: n_atoms out of range");
     std::vector<int> cls;
     if (pm_classify(t, cls)) return 1;
     PmHostProgram p;
     if (!pm_build_program(t->n_atoms, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
-                          t->torsion_per, cls, p))
+                          t->torsion_per, cls, p, team_warps))
         return pm_fail("pm_program_check: degenerate bonded term (repeated atom)");
     const int rc = pm_validate_program(p, t->n_atoms, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions,
                                        t->torsion_idx, cls);
     if (stats10) {
-        const int v[10] = {cpw, 32 / cpw, p.n_stars, p.n_star_steps, p.n_axes, p.n_axis_steps, p.n_segs, p.n_entries,
+        const int v[10] = {cpw, p.L, p.n_stars, p.n_star_steps, p.n_axes, p.n_axis_steps, p.n_segs, p.n_entries,
                            p.n_entry_slots, (int)p.blob.size()};
         memcpy(stats10, v, sizeof(v));
     }
@@ -969,9 +1022,17 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     // ---- choose CPW (conformations per warp; L = 32 / CPW lanes per conformation) ---------------------------
     // The derived-table size does not depend on L, the program size only weakly: plan with the L = 1 program.
     const int max_smem = (int)prop.sharedMemPerBlockOptin;
-    int cpw = conf_per_tile;
-    if (cpw != 0 && cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4) return pm_fail("pm_create: conf_per_tile must be 0 (auto), 32, 16, 8 or 4");
-    if (rf) cpw = 32;  // the reaction-field variant is instantiated for one lane per conformation only
+    int cpw = conf_per_tile, team_warps = 0;
+    if (cpw == -PM_TEAM_WARPS) {  // tiles of 32 conformations shared by teams of PM_TEAM_WARPS warps
+        cpw = 32;
+        team_warps = PM_TEAM_WARPS;
+    }
+    if (cpw != 0 && cpw != 32 && cpw != 16 && cpw != 8 && cpw != 4)
+        return pm_fail("pm_create: conf_per_tile must be 0 (auto), 32, 16, 8, 4, or -8 (teams of 8 warps on tiles of 32)");
+    if (rf) {  // the reaction-field variant is instantiated for one lane per conformation only
+        cpw = 32;
+        team_warps = 0;
+    }
     PmHostProgram host;
     bool built = false;
     if (!cpw) {
@@ -995,9 +1056,31 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
                 if (w >= 9) break;
             }
         }
+        // Large molecules that need teams of lanes anyway: teams of 8 WARPS on tiles of 32 conformations instead, if two such teams
+        // (16 warps) fit -- every branch is uniform and every index a broadcast, as with one lane per conformation, but every step
+        // ends with a barrier of the team.  Measured on B200 (M conformations/s, lanes vs warps): lig50 113 vs 119, lig60 72.6 vs
+        // 73.7 (one team), norfloxacin 164 vs 127, lig33 248 vs 153, caffeine 386 vs 171: the barriers only pay once the pair phase
+        // (balanced 16-pair blocks) dominates, i.e. from about 46 atoms on.
+        const char *et = getenv("PM_TEAM_WARPS_AUTO");
+        if (cpw <= 8 && N >= 46 && !(et && et[0] == '0')) {
+            PmHostProgram cand;
+            if (pm_build_program(N, 32, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx, t->torsion_per, cls,
+                                 cand, PM_TEAM_WARPS)) {
+                const int n_derived = (2 * t->n_bonds + 2 * t->n_angles + 4 * t->n_torsions + 3 * cand.n_pairs + 1) & ~1;
+                size_t sh, pw;
+                int w;
+                pm_plan((int)cand.blob.size(), n_derived, N, 32, max_smem, 1, &sh, &pw, &w, PM_TEAM_WARPS);
+                if (w >= 2 * PM_TEAM_WARPS) {
+                    cpw = 32;
+                    team_warps = PM_TEAM_WARPS;
+                    host = cand;
+                }
+            }
+        }
     }
-    if (!built && !pm_build_program(N, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx,
-                                    t->torsion_per, cls, host))
+    if ((!built || (team_warps && host.team_warps != team_warps)) &&
+        !pm_build_program(N, cpw, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx, t->torsion_per, cls, host,
+                          team_warps))
         return pm_fail("pm_create: degenerate bonded term (repeated atom)");
 
     pm_handle_s *h = new pm_handle_s();
@@ -1011,6 +1094,7 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     h->d_acos = nullptr;
     h->host = host;
     h->rf = rf;
+    h->team_warps = team_warps;
     h->grad_state = nullptr;
     h->grad_free = nullptr;
     h->spec_state = nullptr;
@@ -1028,7 +1112,7 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     g.n_torsions = t->n_torsions;
     g.n_pairs = host.n_pairs;
     g.cpw = cpw;
-    g.L = 32 / cpw;
+    g.L = team_warps ? team_warps : 32 / cpw;
     g.n_star_steps = host.n_star_steps;
     g.n_axis_steps = host.n_axis_steps;
     g.n_segs = host.n_segs;
@@ -1109,23 +1193,23 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     for (int wf = 0; wf < 2; ++wf) {
         size_t sh, pw;
         int w;
-        pm_plan(g.n_int, g.n_derived, N, cpw, max_smem, wf, &sh, &pw, &w);
+        pm_plan(g.n_int, g.n_derived, N, cpw, max_smem, wf, &sh, &pw, &w, team_warps);
         const char *envw = getenv("PM_WARPS");
-        if (envw && *envw && atoi(envw) > 0 && atoi(envw) < w) w = atoi(envw);
+        if (envw && *envw && atoi(envw) > 0 && atoi(envw) < w) w = team_warps ? (atoi(envw) / team_warps) * team_warps : atoi(envw);
         // register budget of the variant: 168 (<= 12 warps), 144 (13-14 warps) or 128 registers per thread
         h->maxw[wf] = (w <= 12 || rf) ? 12 : w <= 14 ? 14 : 16;
         const char *envm = getenv("PM_MAXW");   // sweeps only
-        if (envm && *envm && !rf && atoi(envm) >= w && (atoi(envm) == 12 || atoi(envm) == 14 || atoi(envm) == 16)) h->maxw[wf] = atoi(envm);
+        if (envm && *envm && !rf && !team_warps && atoi(envm) >= w && (atoi(envm) == 12 || atoi(envm) == 14 || atoi(envm) == 16)) h->maxw[wf] = atoi(envm);
         if (rf && w > 12) w = 12;
         h->warps[wf] = w;
-        h->smem_total[wf] = w > 0 ? sh + pw * (size_t)w : 0;
+        h->smem_total[wf] = w > 0 ? sh + pw * (size_t)(team_warps ? w / team_warps : w) : 0;
     }
     if (h->warps[1] < 1 || h->warps[0] < 1) {
         cleanup();
         return pm_fail("pm_create: molecule too large for the shared-memory tiles of this kernel generation");
     }
-    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 1, h->maxw[1], rf), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
-    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 0, h->maxw[0], rf), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 1, h->maxw[1], rf, team_warps), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[1]));
+    PM_CUDA_H(cudaFuncSetAttribute(pm_pick_kernel(cpw, 0, h->maxw[0], rf, team_warps), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_total[0]));
     *out = h;
     return 0;
 }
@@ -1218,7 +1302,7 @@ extern "C" int pm_prepare_params(pm_handle h, const double *slots_dev, int n_vec
 // rows of the fused reduction one launch of the interpreting E(+F) kernel writes per parameter vector (one per warp of the grid)
 static long pm_red_rows(pm_handle h, int with_forces, long n_conf) {
     const int wf = with_forces ? 1 : 0;
-    const int warps = h->warps[wf];
+    const int warps = h->team_warps ? h->warps[wf] / h->team_warps : h->warps[wf];  // tiles in flight per CTA (teams, or warps)
     const long n_tiles = pm_n_tiles(h, n_conf);
     long grid = h->n_sm;
     if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
@@ -1249,9 +1333,9 @@ static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const
                             with_forces ? 1 : 0, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
-    const int warps = h->warps[wf];
+    const int warps = h->warps[wf], units = h->team_warps ? warps / h->team_warps : warps;  // tiles in flight per CTA
     long grid = h->n_sm;
-    if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
+    if (grid * units > n_tiles) grid = (n_tiles + units - 1) / units;
     if (grid < 1) grid = 1;
     PmProg prog = h->prog;
     if (mode == 1) {
@@ -1263,7 +1347,7 @@ static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const
         prog.nb_e = nb_e_dev;
         prog.nb_f_tiles = nb_f_tiles_dev;
     }
-    pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf], h->rf);
+    pm_ef_fn fn = pm_pick_kernel(h->prog.cpw, wf, h->maxw[wf], h->rf, h->team_warps);
     fn<<<(unsigned)grid, warps * 32, h->smem_total[wf], (cudaStream_t)stream>>>(prog, derived_dev, n_vec, coord_tiles_dev,
                                                                                 wf ? fref_tiles_dev : nullptr, n_conf, n_tiles, emm_dev,
                                                                                 wf ? fres_dev : nullptr, wf ? fmm_tiles_dev : nullptr, red);

@@ -38,6 +38,7 @@
 
 struct PmHostProgram {
     int n_atoms = 0, L = 1, cpw = 32;
+    int team_warps = 0;         // > 1: teams of warps (see pm_build_program)
     std::vector<int> blob;      // everything the kernel stages into shared memory
     std::vector<int> pair_map;  // (i, j, exception or -1) per interacting pair, kernel order
     int n_pairs = 0;
@@ -61,7 +62,7 @@ struct Item {
 // colour touch disjoint atoms; the kernel computes all records of a step in parallel and serialises only the force
 // write-back by colour.  hdr[step] = number of colours.  Records are taken in order of decreasing cost (balance), each
 // slot preferring, among the next few candidates, the one that conflicts least with the records already in the step.
-inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_steps, std::vector<int> &hdr) {
+inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_steps, std::vector<int> &hdr, bool strict = false) {
     std::vector<int> table;
     hdr.clear();
     const int n = (int)items.size();
@@ -89,7 +90,9 @@ inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_s
         std::vector<int> chosen;
         for (int slot = 0; slot < L && left > 0; ++slot) {
             int best = -1, best_conf = INT_MAX, seen = 0;
-            for (int oi = 0; oi < n && seen < 2 * L; ++oi) {
+            // strict (teams of WARPS: the records of a step are written back concurrently, with one barrier per step): only
+            // records that touch none of the atoms already in the step, searched over everything that is left
+            for (int oi = 0; oi < n && (strict || seen < 2 * L); ++oi) {
                 const int i = order[oi];
                 if (done[i]) continue;
                 ++seen;
@@ -101,6 +104,7 @@ inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_s
                 }
                 if (conf == 0) break;
             }
+            if (strict && best_conf > 0) break;  // nothing disjoint is left: close the step
             chosen.push_back(best);
             done[best] = 1;
             --left;
@@ -131,9 +135,13 @@ inline std::vector<int> schedule(const std::vector<Item> &items, int L, int *n_s
 
 // cls[i*N+j]: 0 plain pair, 1 excluded, 2+e active exception e
 inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, int n_angles, const int *angle_idx, int n_torsions,
-                             const int *tors_idx, const int *tors_per, const std::vector<int> &cls, PmHostProgram &out) {
+                             const int *tors_idx, const int *tors_per, const std::vector<int> &cls, PmHostProgram &out, int team_warps = 0) {
     out = PmHostProgram();
-    const int L = 32 / cpw;
+    // team_warps > 1: a team is that many WARPS sharing one tile of 32 conformations (lane = conformation, cpw = 32); the tables are
+    // those of a team of L members, but the records of a step must be disjoint (one colour)
+    const bool warp_team = team_warps > 1;
+    const int L = warp_team ? team_warps : 32 / cpw;
+    out.team_warps = warp_team ? team_warps : 0;
     out.n_atoms = N;
     out.L = L;
     out.cpw = cpw;
@@ -612,8 +620,8 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
 
     // ------------------------------------------------------------------ tables + blob ---------------------------------
     std::vector<int> star_hdr, axis_hdr;
-    std::vector<int> star_tab = pmh::schedule(star_items, L, &out.n_star_steps, star_hdr);
-    std::vector<int> axis_tab = pmh::schedule(axis_items, L, &out.n_axis_steps, axis_hdr);
+    std::vector<int> star_tab = pmh::schedule(star_items, L, &out.n_star_steps, star_hdr, warp_team);
+    std::vector<int> axis_tab = pmh::schedule(axis_items, L, &out.n_axis_steps, axis_hdr, warp_team);
     // axis step header: colours | (largest number of i-substituents in the step << 8)
     for (int st = 0; st < out.n_axis_steps; ++st) {
         int max_ni = 0;
@@ -663,6 +671,7 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
     for (int s = 0; s < p.n_star_steps; ++s) {
         std::map<int, std::set<int>> used_by_colour;
         const int n_col = b[p.off_star_hdr + s];
+        if (p.team_warps > 1 && n_col != 1) return 18;  // teams of warps write back concurrently
         for (int l = 0; l < L; ++l) {
             const int rec = b[p.off_star_tab + 2 * (s * L + l)], colour = b[p.off_star_tab + 2 * (s * L + l) + 1];
             if (rec < 0) continue;
@@ -700,6 +709,7 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
     for (int s = 0; s < p.n_axis_steps; ++s) {
         std::map<int, std::set<int>> used_by_colour;
         const int n_col = b[p.off_axis_hdr + s] & 0xff, max_ni = b[p.off_axis_hdr + s] >> 8;
+        if (p.team_warps > 1 && n_col != 1) return 28;
         for (int l = 0; l < L; ++l) {
             const int rec = b[p.off_axis_tab + 2 * (s * L + l)], colour = b[p.off_axis_tab + 2 * (s * L + l) + 1];
             if (rec < 0) continue;

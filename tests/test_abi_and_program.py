@@ -52,12 +52,12 @@ def _molecules(golden_dir):
 def test_topology_program_invariants(golden_dir):
     L = _lib.lib()
     for name, s in _molecules(golden_dir):
-        for cpw in (32, 16, 8, 4):
+        for cpw in (32, 16, 8, 4, -8):   # -8: teams of 8 warps on tiles of 32 conformations
             topo, keep = _topology(s)
             stats = np.zeros(10, dtype=np.int32)
             rc = L.pm_program_check(ctypes.byref(topo), cpw, stats.ctypes.data_as(c_int_p))
             assert rc == 0, (name, cpw, L.pm_last_error())
-            assert stats[0] == cpw and stats[1] == 32 // cpw
+            assert (stats[0], stats[1]) == ((32, 8) if cpw < 0 else (cpw, 32 // cpw))
             # padding of the pair schedule stays moderate
             if stats[7] > 0:
                 assert stats[8] <= 2 * stats[7] + 8 * stats[1], (name, cpw, stats)

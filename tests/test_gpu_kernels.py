@@ -31,10 +31,10 @@ def _system(golden_dir, name):
             read_inpcrd(os.path.join(golden_dir, name + ".inpcrd")))
 
 
-def _run(sys_, X, Fref=None, Eref=None, metric=None, slots=None):
+def _run(sys_, X, Fref=None, Eref=None, metric=None, slots=None, conf_per_tile=None):
     import torch
     from paramol_b200.MM_engines.device import DeviceTopology, DeviceEnsemble
-    topo = DeviceTopology(sys_)
+    topo = DeviceTopology(sys_, conf_per_tile=conf_per_tile)
     if metric is not None:
         topo.set_force_metric(metric)
     ens = DeviceEnsemble(topo, X, Fref, Eref)
@@ -374,3 +374,32 @@ def test_energy_batch_contraction_vs_energy_kernel_and_oracle(golden_dir, name, 
     for p in (0, n_vec - 1):
         E, _ = O.energies_forces(_system_with_slots(s, slots[p]), X, n_threads=4)
         assert _close_ef(emm[p], E), np.abs(emm[p] - E).max()
+
+
+@pytest.mark.parametrize("name,n_conf", [("lig50", 203), ("lig60", 131), ("norfloxacin", 96), ("lig33", 77), ("caffeine", 65), ("aniline", 40)])
+def test_warp_team_mode_parity_vs_oracle(golden_dir, name, n_conf, monkeypatch):
+    """Teams of 8 WARPS on tiles of 32 conformations (``conf_per_tile = -8``: lane = conformation, the members of a team are warps
+    that share the tile, a named barrier per step): energies, forces, the energy-only kernel and the residual epilogue against the
+    oracle, plus the fused reduction against ``pm_eval`` + ``pm_reduce_objective``; ragged last tile."""
+    import torch
+    from oracle import oracle as O
+    monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "0")
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(4321)
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    E, F = O.energies_forces(s, X, n_threads=4)
+    Fref = F + rng.normal(0, 50.0, F.shape)
+    metric = np.tile(np.eye(3).ravel(), (s.n_atoms, 1)) * rng.uniform(0.5, 2.0, (s.n_atoms, 1))
+    r = _run(s, X, Fref, E + rng.normal(0, 5, E.shape), metric, conf_per_tile=-8)
+    assert r["topo"].program_info()["lanes_per_conformation"] == 8 and r["topo"].conf_per_tile == 32
+    assert np.abs(r["emm"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    assert np.abs(r["fmm"][0] - F).max() < 1e-9 * np.abs(F).max()
+    assert np.abs(r["emm_energy_only_kernel"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    d = F - Fref
+    res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
+    assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
+    ens, derived = r["ens"], r["derived"]
+    emm, fres, _ = ens.evaluate(derived, with_forces=True, want_fres=True)
+    want = ens.reduce(emm, fres, d_shift=1.5).cpu().numpy().copy()
+    got = ens.evaluate_reduce(derived, with_forces=True, d_shift=1.5)[0].cpu().numpy()
+    assert np.all(np.abs(got - want) <= 1e-12 * np.maximum(np.abs(want), np.abs(want).max() * 1e-4)), (got, want)
