@@ -80,8 +80,9 @@ def lig50(fp64_peak, S=1 << 18, n_atoms=50, reps=10):
     tf = fl * S / (ms * 1e-3) / 1e12
     return dict(workload="lig%d (synthetic drug-like ligand, %d atoms) x %d conformations, 1 parameter vector, E+F+residual+reduction"
                 % (n_atoms, n_atoms, S), ms_per_step=ms, conformations_per_s=S / (ms * 1e-3),
-                roofline=dict(bound="fp64", kernel="pm_ef_spec_kernel" if topo.specialized else "pm_ef_kernel<%d lanes per conformation>"
-                              % topo.program_info()["lanes_per_conformation"], achieved=tf, peak=fp64_peak, unit="TFLOP/s",
+                roofline=dict(bound="fp64", kernel="pm_ef_spec_kernel" if topo.specialized else
+                              ("pm_ef_kernel<teams of %d warps on tiles of 32 conformations>" if (topo.conf_per_tile == 32 and topo.program_info()["lanes_per_conformation"] > 1)
+                               else "pm_ef_kernel<%d lanes per conformation>") % topo.program_info()["lanes_per_conformation"], achieved=tf, peak=fp64_peak, unit="TFLOP/s",
                               frac=tf / fp64_peak, flops_per_conformation=fl, note="fraction of the whole step, launches included"),
                 launch=topo.launch_info(True), program=topo.program_info())
 

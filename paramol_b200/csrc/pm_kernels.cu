@@ -258,10 +258,28 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     for (int i = threadIdx.x; i < g.n_int; i += blockDim.x) s_int[i] = g.ints[i];
     for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = g.acos_tab[i];
     for (int i = threadIdx.x; i < 9 * N; i += blockDim.x) s_metric[i] = g.metric[i];
+    uint64_t *tbar = bar + 1;  // teams of warps: "the force updates of a step are complete" (one arrival per member)
     if (lane == 0 && (!WT || tl == 0)) {
         pm_mbar_init(bar, 1);
+        if (WT) pm_mbar_init(tbar, TW);
         pm_fence_mbar_init();
     }
+    // Teams of warps order the force updates of consecutive steps with a SPLIT barrier: a member computes its record of step r
+    // (coordinates only), waits until every member has finished the updates of step r - 1, updates, and arrives for step r -- so
+    // the wait overlaps with the member's own arithmetic instead of ending every step (energy-only kernels need no ordering).
+    uint32_t n_arr = 0;
+    int tile_round = 0;
+    auto round_wait = [&]() {
+        if (WT && WITH_F && tile_round > 0) pm_mbar_wait(tbar, (n_arr - 1) & 1u);
+    };
+    auto round_arrive = [&]() {
+        if (WT && WITH_F) {
+            __syncwarp();
+            if (lane == 0) pm_mbar_arrive(tbar);
+            ++n_arr;
+            ++tile_round;
+        }
+    };
     if (!WT || tl == 0)
         for (int k = lane; k < 3 * CPW; k += 32) {
             xs[tile_d + k] = 0.0;
@@ -326,6 +344,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             pm_mbar_wait(bar, parity);
             parity ^= 1;
             team_sync();
+            tile_round = 0;
 
             double e_bond = 0.0, e_angle = 0.0, e_tors = 0.0, e_nb = 0.0;
             if (nb_cached && tl == 0 && tile * CPW + col < n_conf) e_nb = g.nb_e[tile * CPW + col];
@@ -409,6 +428,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 }
                 if (WITH_F) {
                     // write-back: records of one colour touch disjoint atoms; colours are serialised
+                    round_wait();
                     PM_ORDERED(n_col, te.y, rec >= 0, {
                         pm_d3 fc{0.0, 0.0, 0.0};
                         _Pragma("unroll") for (int k = 0; k < 4; ++k) {
@@ -422,7 +442,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, center, fc);
                     })
                 }
-                if (WT) team_sync();  // the next step's records may touch the atoms this step's members just updated
+                round_arrive();  // the next step's records may touch the atoms this step's members just updated
             }
 
             // ================= axes: every torsion around a rotation axis j-k (trig-free) ================
@@ -476,6 +496,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     }
                 }
                 pm_d3 Fj{0.0, 0.0, 0.0}, Fk{0.0, 0.0, 0.0};
+                round_wait();  // (the substituent forces are written inside the loop below)
                 const int ni_loop = (L > 1 && !WT) ? (hdr >> 8) : nI;   // (teams of lanes: the longest record of the step)
                 for (int pi = 0; pi < ni_loop; ++pi) {
                     const bool act = L == 1 || WT || (live && pi < nI);
@@ -556,7 +577,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, ak, Fk);
                     })
                 }
-                if (WT) team_sync();
+                round_arrive();
             }
 
             // ================= nonbonded, teams: 4 x 4 register blocks on disjoint tile pairs ====================
@@ -583,13 +604,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_d3 ai{0.0, 0.0, 0.0};
 #pragma unroll
                         for (int m = 0; m < 4; ++m) pm_pair_blk<WITH_F>(xi, xj[m], s_ppair + 3 * q[m], e_nb, ai, aj[m]);
+                        if (WT && k == 0) round_wait();  // the first row's pairs are evaluated while the previous step drains
                         if (WITH_F) pm_addo<CPW>(fc_base, io, ai);
                     }
                     if (WITH_F) {
 #pragma unroll
                         for (int m = 0; m < 4; ++m) pm_subo<CPW>(fc_base, jo[m], aj[m]);
                     }
-                    team_sync();
+                    if (WT)
+                        round_arrive();
+                    else
+                        __syncwarp();
                 }
             }
             // ================= nonbonded: plain pairs and scaled 1-4 exceptions, register-tiled over i ========
@@ -647,6 +672,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
             }
 
             // ================= epilogue: per-conformation energy and force residual ==========================
+            round_wait();  // teams of warps: the updates of the last step are complete
             const long sconf = tile * CPW + col;
             double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
             double res = 0.0;
@@ -1070,6 +1096,8 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
                 size_t sh, pw;
                 int w;
                 pm_plan((int)cand.blob.size(), n_derived, N, 32, max_smem, 1, &sh, &pw, &w, PM_TEAM_WARPS);
+                // (one team per CTA: lig60 single vector 78.5 vs 72.4 M conformations/s, but batches over 100 000 conformations lose 1.4 %
+                // to the quantisation of 3125 tiles over 148 teams per vector -- two teams required)
                 if (w >= 2 * PM_TEAM_WARPS) {
                     cpw = 32;
                     team_warps = PM_TEAM_WARPS;
