@@ -13,12 +13,12 @@ measurement is repeated with 2^20 conformations PER GPU and reported under ``wea
 
 Printed JSON line (rank 0):
   value      conformation E+F evaluations / s, whole job, parameters and conformations resident in HBM
-             (pm_prepare_params + pm_eval_reduce per step: the E+F kernel with the fused residual reduction, then the row-sum
-             kernel that is also the all-reduce over NVLink peer memory; CUDA-event timed, max over ranks)
+             (pm_prepare_params + pm_eval_reduce per step: the E+F kernel, the residual sums, then the row-sum kernel that is also
+             the all-reduce over NVLink peer memory; CUDA-event timed, max over ranks)
   e2e        the same metric through the public API ``ObjectiveFunction.f(x)`` with a HOST parameter vector: numpy
              plumbing, pinned H2D of the slot row, one CUDA-graph replay, D2H of the 8 global sums, every step
-  roofline   dominant kernel (pm_ef_spec_kernel for small molecules, else pm_ef_kernel): algorithmic FP64 flops / CUDA-event time
-             against the DFMA peak measured live on this GPU (the kernel is FP64-pipe bound; the nominal pipe
+  roofline   dominant kernel (pm_ef_spec_kernel for small molecules, else pm_ef_kernel), timed ALONE with CUDA events in a loop of
+             the same length right after the step loop: algorithmic FP64 flops / that time against the DFMA peak measured live on this GPU (the kernel is FP64-pipe bound; the nominal pipe
              peak 148 SM x 64 DFMA x 2 x f_SM is printed beside it); ``frac_of_step`` divides by the whole step instead of the
              kernel; ``hbm`` holds the same kernel against the measured copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline  the FP64 CPU port of the reference path (oracle/oracle.c, OpenMP over conformations, all host cores) on exactly

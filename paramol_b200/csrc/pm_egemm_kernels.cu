@@ -132,7 +132,6 @@ __device__ __forceinline__ void eg_dmma(double (&c)[2], double a, double b) {
 }
 
 // features of one term for the conformation in column `col` of the staged coordinate tile -> rows tm.row .. of the chunk
-template <int CPT_DYNAMIC = 0>
 __device__ __forceinline__ void eg_features(const EgTerm tm, const double *__restrict__ xs, int n_atoms, int cpt, int conf,
                                             const double2 *__restrict__ s_acos, double *__restrict__ g /* &Gs[0][conf] */) {
     const int tile = conf / cpt;
