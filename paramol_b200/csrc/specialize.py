@@ -134,19 +134,24 @@ class KernelSource:
                 done_bond.add(t)
                 o = self.off_bond + 2 * t
                 self.emit("{ const double dl = fma(q%d, i%d, -%s); const double kd = %s * dl; e_bond = fma(0.5 * kd, dl, e_bond);" % (n, n, self.P(o), self.P(o + 1))
-                          + (" const double g = kd * i%d; pm_axpy(f%d, g, d%d); pm_axpy(fc, -g, d%d); }" % (n, n, n, n) if self.wf else " }"))
+                          + (" pm_axpy(f%d, kd * i%d, d%d); }" % (n, n, n) if self.wf else " }"))
             for (t, a, b) in angle_at[c]:
                 o = self.off_angle + 2 * t
-                # d0 = x_centre - x_a, d1 = x_centre - x_b  (ReferenceAngleBondIxn; see pm_delta_kernels.cu for the same algebra)
-                self.emit("{ const pm_d3 pc = pm_cross(d%d, d%d); const double pp2 = pm_dot(pc, pc); const double i01 = i%d * i%d;" % (a, b, a, b))
-                self.emit("  const double ip = pm_rsqrt(fmax(pp2, 1.0e-12)); const double th = pm_acos_cs(pm_dot(d%d, d%d) * i01, pp2 * ip * i01, s_acos);" % (a, b))
+                # d_a = x_centre - x_a, d_b = x_centre - x_b (ReferenceAngleBondIxn).  As in the generic kernel: sin from the Lagrange
+                # identity |d_a x d_b|^2 = |d_a|^2 |d_b|^2 - (d_a.d_b)^2 and the forces from the triple-product rule
+                # d_a x (d_a x d_b) = d_a (d_a.d_b) - d_b |d_a|^2, so no cross product is formed (20 FP64 operations fewer per angle)
+                self.emit("{ const double dt = pm_dot(d%d, d%d); const double i01 = i%d * i%d; const double pp2 = fmax(fma(-dt, dt, q%d * q%d), 0.0);" % (a, b, a, b, a, b))
+                self.emit("  const double ip = pm_rsqrt(fmax(pp2, 1.0e-12)); const double th = pm_acos_cs(dt * i01, pp2 * ip * i01, s_acos);")
                 self.emit("  const double dl = th - %s; const double dd = %s * dl; e_angle = fma(0.5 * dd, dl, e_angle);" % (self.P(o), self.P(o + 1)))
                 if self.wf:
-                    self.emit("  const double ta = dd * ip * (i%d * i%d), tc = -dd * ip * (i%d * i%d);" % (a, a, b, b))
-                    self.emit("  const pm_d3 c0 = pm_cross(d%d, pc), c2 = pm_cross(d%d, pc);" % (a, b))
-                    self.emit("  pm_axpy(f%d, ta, c0); pm_axpy(f%d, tc, c2); pm_axpy(fc, -ta, c0); pm_axpy(fc, -tc, c2); }" % (a, b))
+                    self.emit("  const double w = dd * ip, wd = w * dt; const double al = wd * (i%d * i%d), be = wd * (i%d * i%d);" % (a, a, b, b))
+                    self.emit("  pm_axpy(f%d, al, d%d); pm_axpy(f%d, -w, d%d); pm_axpy(f%d, be, d%d); pm_axpy(f%d, -w, d%d); }" % (a, a, a, b, b, b, b, a))
                 else:
                     self.emit("}")
+            if self.wf and need:
+                # the centre takes minus the sum of its neighbours' forces (once per star instead of once per term)
+                for comp in ("x", "y", "z"):
+                    self.emit("fc.%s = -(%s);" % (comp, " + ".join("f%d.%s" % (n, comp) for n in need)))
             self.addf(c, "fc")
             for n in need:
                 self.addf(n, "f%d" % n)
