@@ -118,6 +118,7 @@ def config1(n_calls=200):
     t0 = time.perf_counter()
     vals = [of.f(x) for x in trial]
     us_f = (time.perf_counter() - t0) / n_calls * 1e6
+    of.f_batch(np.stack(trial))   # warm: the batch buffers are allocated on the first call
     t0 = time.perf_counter()
     of.f_batch(np.stack(trial))
     us_batch = (time.perf_counter() - t0) / n_calls * 1e6

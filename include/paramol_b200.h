@@ -293,6 +293,14 @@ int pm_lls_normal(pm_lls p, const double *coords_dev, long n_conf, const double 
                   double *scratch_dev, void *stream);
 int pm_lls_destroy(pm_lls p);
 
+/* ---- single-vector objective call (the host side of ObjectiveFunction.f, ParaMol/Objective_function/objective_function.py:75-160) - */
+/* An instantiated CUDA graph (a cudaGraphExec_t) captured over: pinned slots row -> device, pm_prepare_params, pm_eval_reduce,
+ * partial sums -> pinned host.  pm_graph_launch copies in_host [n_in] into pin_in (the graph's pinned input) and launches the graph
+ * on stream; pm_graph_wait waits for stream and copies pin_out [n_out] to out_host.  Between the two the caller is free to do its
+ * host-only work (the regularisation term).  All pointers are HOST pointers. */
+int pm_graph_launch(void *graph_exec, void *stream, const double *in_host, double *pin_in, long n_in);
+int pm_graph_wait(void *stream, const double *pin_out, long n_out, double *out_host);
+
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* Measured FMA-pipe peak of the current device: runs a register-only FMA kernel and returns FLOP/s
  * (2 flop per FMA) in *flops and the kernel time in *ms.  fp64 = 1: DFMA, 0: FFMA. */

@@ -22,12 +22,14 @@ without mutating the parameter space.  ``fused=False`` keeps the reference's str
 to the host through ``ParaMolSystem.get_*_ensemble`` and reduced by the numpy property formulas); it exists for
 parity tests of the seam, not for speed.
 """
+import ctypes
 import logging
 import os
 import time
 
 import numpy as np
 
+from .. import _lib
 from ..Utils import dist as _dist
 
 NPARTIAL = 8
@@ -566,6 +568,12 @@ class ObjectiveFunction:
                 g["pin_out"].copy_(part, non_blocking=True)
             g["graph"] = graph
             g["part_dev"] = part
+            # raw handles for pm_graph_call (one C call per objective evaluation: stage, launch, wait, read back)
+            g["exec"] = ctypes.c_void_p(graph.raw_cuda_graph_exec())
+            g["dev_index"] = ens.device.index or 0
+            g["pin_in_ptr"] = ctypes.c_void_p(g["pin_in"].data_ptr())
+            g["pin_out_ptr"] = ctypes.c_void_p(g["pin_out"].data_ptr())
+            g["out"] = np.zeros((1, NPARTIAL))
             g["global"] = comm is not None or _dist.world_size() == 1    # the sums in pin_out are already global
         finally:
             ens._buffers, ens._scratch = saved_bufs, saved_scratch
@@ -601,12 +609,18 @@ class ObjectiveFunction:
                     st["graph"] = self._capture_graph(st, ens)
                 if "graph" in st:
                     g = st["graph"]
-                    g["pin_in"].copy_(torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64)))
-                    g["graph"].replay()
+                    row = np.ascontiguousarray(slots, dtype=np.float64)
                     if not g["global"]:   # NCCL fallback: the partial sums stay on the device for the allreduce
+                        g["pin_in"].copy_(torch.from_numpy(row))
+                        g["graph"].replay()
                         partial_list.append(g["part_dev"])
-                    else:                 # one replay + one stream synchronisation, on one GPU as on eight
-                        graph_rows[s_idx] = g["pin_out"]
+                    else:
+                        # one C call: slots -> pinned staging, graph launch on torch's current stream (ordered after whatever
+                        # was queued there); the wait and the read-back follow the host-only terms below
+                        g["stream_ptr"] = ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(g["dev_index"]))
+                        _lib.check(_lib.lib().pm_graph_launch(g["exec"], g["stream_ptr"], row.ctypes.data, g["pin_in_ptr"], row.size),
+                                   "pm_graph_launch")
+                        graph_rows[s_idx] = g
                         partial_list.append("graph")
                     continue
             host = torch.from_numpy(np.ascontiguousarray(slots, dtype=np.float64))
@@ -673,14 +687,8 @@ class ObjectiveFunction:
                 _dist.allreduce_sum_tensor_(stacked)         # the single data-path collective (NCCL / gloo fallback)
                 host_partials = stacked.cpu().numpy()
             global_host = {i: t.cpu().numpy() for i, t in global_parts.items()}
-            if graph_rows:
-                # the replays were issued on the current stream; the raw-handle comparison keeps a cached Stream object
-                # valid without paying torch.cuda.current_stream() (~15 us) on every call
-                dev_index = states[next(iter(graph_rows))]["ens"].device.index or 0
-                raw = torch._C._cuda_getCurrentRawStream(dev_index)
-                if self._sync_stream is None or self._sync_stream[0] != (dev_index, raw):
-                    self._sync_stream = ((dev_index, raw), torch.cuda.current_stream(dev_index))
-                self._sync_stream[1].synchronize()
+            for g in graph_rows.values():   # one stream wait + read-back per replayed graph, on one GPU as on eight
+                _lib.check(_lib.lib().pm_graph_wait(g["stream_ptr"], g["pin_out_ptr"], NPARTIAL, g["out"].ctypes.data), "pm_graph_wait")
             k = 0
             per_system = []
             for i, p in enumerate(partial_list):
@@ -689,7 +697,7 @@ class ObjectiveFunction:
                 elif isinstance(p, str) and p == "global":
                     per_system.append(global_host[i] * 1.0)
                 elif isinstance(p, str):
-                    per_system.append(graph_rows[i].numpy().copy())
+                    per_system.append(graph_rows[i]["out"].copy())
                 else:
                     per_system.append(host_partials[k] * 1.0)
                     k += 1

@@ -114,6 +114,8 @@ SIGNATURES = {
                                       ctypes.c_int]),
     "pm_has_specialized": (ctypes.c_int, [ctypes.c_void_p]),
     "pm_topology_pairs": (ctypes.c_int, [ctypes.POINTER(PmTopology), ctypes.c_int, c_int_p, c_int_p]),
+    "pm_graph_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]),
+    "pm_graph_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]),
     "pm_measure_fma_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p]),
 }
 

@@ -208,3 +208,22 @@ int pm_spec_grad(pm_handle h, const double *derived_dev, const double *xt, const
     PMS_CUDA(cudaLaunchKernel((const void *)st->kernel_gr, dim3((unsigned)((st->ngp + 127) / 128)), dim3(128), rargs, 0, stream));
     return 0;
 }
+
+// ---- one objective call of a captured single-vector graph ------------------------------------------------------------
+// The host side of ObjectiveFunction.f(x) between "the slots row is known" and "the partial sums are on the host", as two C calls
+// instead of five trips through the Python bindings of the CUDA runtime.  pm_graph_launch copies the row into the graph's pinned
+// staging buffer and launches the instantiated graph (upload, pm_prepare_params, pm_eval_reduce, download); the caller does its
+// host-only work (the regularisation term) while the device runs; pm_graph_wait waits for the stream and copies the sums out.
+extern "C" int pm_graph_launch(void *graph_exec, void *stream, const double *in_host, double *pin_in, long n_in) {
+    if (!graph_exec || !pin_in || (n_in > 0 && !in_host) || n_in < 0) return pm_fail_msg("pm_graph_launch: null argument");
+    if (n_in > 0) memcpy(pin_in, in_host, sizeof(double) * (size_t)n_in);
+    PMS_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int pm_graph_wait(void *stream, const double *pin_out, long n_out, double *out_host) {
+    if (!pin_out || !out_host || n_out < 0) return pm_fail_msg("pm_graph_wait: null argument");
+    PMS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(out_host, pin_out, sizeof(double) * (size_t)n_out);
+    return 0;
+}

@@ -174,38 +174,59 @@ class KernelSource:
             self.emit("const double rbb = pm_rsqrt(bb); const double nb = bb * rbb, ibb = rbb * rbb;")
             if self.wf:
                 self.emit("pm_d3 fj = pm_d3{0.0, 0.0, 0.0}, fk = pm_d3{0.0, 0.0, 0.0};")
+            # Forces of an axis: with A_i = -|d1| / |u_i|^2 * sum_l dE/dphi(i, l) and B_l = |d1| / |w_l|^2 * sum_i dE/dphi(i, l) the
+            # substituents take F_i = A_i u_i, F_l = B_l w_l and the axis atoms F_j = sum_i (g_i - 1) F_i - sum_l h_l F_l,
+            # F_k = sum_l (h_l - 1) F_l - sum_i g_i F_i (ReferenceProperDihedralBond), so a cell only adds its dE/dphi to the two
+            # scalar sums of its substituents and the vector work is done once per substituent instead of once per cell
             for i in subs_i:
                 self.emit("const pm_d3 a%d = pm_sub(%s, xj); const pm_d3 u%d = pm_cross(a%d, d1); const double m%d = pm_dot(u%d, u%d);"
                           " const double s%d = pm_rsqrt(m%d);" % (i, self.X(i), i, i, i, i, i, i, i)
-                          + (" const double g%d = pm_dot(a%d, d1) * ibb; pm_d3 fi%d = pm_d3{0.0, 0.0, 0.0};" % (i, i, i) if self.wf else ""))
+                          + (" double za%d = 0.0;" % i if self.wf else ""))
             for l in subs_l:
                 self.emit("const pm_d3 b%d = pm_sub(xk, %s); const pm_d3 w%d = pm_cross(d1, b%d); const double n%d = pm_dot(w%d, w%d);"
                           " const double t%d = pm_rsqrt(n%d);" % (l, self.X(l), l, l, l, l, l, l, l)
-                          + (" const double h%d = pm_dot(b%d, d1) * ibb; pm_d3 fl%d = pm_d3{0.0, 0.0, 0.0};" % (l, l, l) if self.wf else ""))
+                          + (" double zb%d = 0.0;" % l if self.wf else ""))
             cells = {}
             for (t, i, l) in terms:
                 cells.setdefault((i, l), []).append(t)
             for (i, l), ts in cells.items():
                 ts = sorted(ts, key=lambda t: self.tors_per[t])
                 self.emit("{ const double i12 = s%d * t%d; const double cphi = pm_dot(u%d, w%d) * i12, sphi = nb * pm_dot(a%d, w%d) * i12;" % (i, l, i, l, i, l))
-                self.emit("  double cn = 1.0, sn = 0.0, dd = 0.0;")
-                cur = 0
+                # (cos, sin)(n phi) by the angle-addition recurrence, started at n = 1 (n = 0 only if a term has periodicity 0)
+                if self.tors_per[ts[0]] >= 1:
+                    self.emit("  double cn = cphi, sn = sphi;")
+                    cur = 1
+                else:
+                    self.emit("  double cn = 1.0, sn = 0.0;")
+                    cur = 0
+                if self.wf and len(ts) > 1:
+                    self.emit("  double dd = 0.0;")
                 for t in ts:
                     per = self.tors_per[t]
                     while cur < per:
                         self.emit("  { const double tt = cn * cphi - sn * sphi; sn = fma(sn, cphi, cn * sphi); cn = tt; }")
                         cur += 1
                     o = self.off_tors + 4 * t
-                    self.emit("  e_tors += %s * (1.0 + fma(cn, %s, sn * %s));" % (self.P(o), self.P(o + 2), self.P(o + 3))
-                              + (" dd -= %s * fma(sn, %s, -(cn * %s));" % (self.P(o + 1), self.P(o + 2), self.P(o + 3)) if self.wf else ""))
-                # F_0 = -dd |d1| c1 / n1, F_3 = dd |d1| c2 / n2, F_1 = (ff1-1) F_0 - ff2 F_3, F_2 = (ff2-1) F_3 - ff1 F_0
-                if self.wf:
-                    self.emit("  const double z0 = -dd * nb * (s%d * s%d), z3 = dd * nb * (t%d * t%d);" % (i, i, l, l))
-                    self.emit("  const pm_d3 f0 = pm_d3{z0 * u%d.x, z0 * u%d.y, z0 * u%d.z}, f3 = pm_d3{z3 * w%d.x, z3 * w%d.y, z3 * w%d.z};" % (i, i, i, l, l, l))
-                    self.emit("  pm_axpy(fi%d, 1.0, f0); pm_axpy(fl%d, 1.0, f3);" % (i, l))
-                    self.emit("  pm_axpy(fj, g%d - 1.0, f0); pm_axpy(fj, -h%d, f3); pm_axpy(fk, h%d - 1.0, f3); pm_axpy(fk, -g%d, f0); }" % (i, l, l, i))
-                else:
-                    self.emit("  (void)dd; }")
+                    self.emit("  e_tors += %s * (1.0 + fma(cn, %s, sn * %s));" % (self.P(o), self.P(o + 2), self.P(o + 3)))
+                    if self.wf:
+                        x = "fma(sn, %s, -(cn * %s))" % (self.P(o + 2), self.P(o + 3))   # sin(n phi - delta); dE/dphi = -k n sin(.)
+                        if len(ts) > 1:
+                            self.emit("  dd = fma(-%s, %s, dd);" % (self.P(o + 1), x))
+                        else:
+                            self.emit("  { const double x = %s; za%d = fma(-%s, x, za%d); zb%d = fma(-%s, x, zb%d); }"
+                                      % (x, i, self.P(o + 1), i, l, self.P(o + 1), l))
+                if self.wf and len(ts) > 1:
+                    self.emit("  za%d += dd; zb%d += dd;" % (i, l))
+                self.emit("}")
+            if self.wf:
+                for i in subs_i:
+                    self.emit("const double g%d = pm_dot(a%d, d1) * ibb; const double A%d = -(nb * (s%d * s%d)) * za%d;"
+                              " const pm_d3 fi%d = pm_d3{A%d * u%d.x, A%d * u%d.y, A%d * u%d.z};" % (i, i, i, i, i, i, i, i, i, i, i, i, i))
+                    self.emit("pm_axpy(fj, g%d - 1.0, fi%d); pm_axpy(fk, -g%d, fi%d);" % (i, i, i, i))
+                for l in subs_l:
+                    self.emit("const double h%d = pm_dot(b%d, d1) * ibb; const double B%d = (nb * (t%d * t%d)) * zb%d;"
+                              " const pm_d3 fl%d = pm_d3{B%d * w%d.x, B%d * w%d.y, B%d * w%d.z};" % (l, l, l, l, l, l, l, l, l, l, l, l, l))
+                    self.emit("pm_axpy(fk, h%d - 1.0, fl%d); pm_axpy(fj, -h%d, fl%d);" % (l, l, l, l))
             self.addf(j, "fj")
             self.addf(k, "fk")
             for i in subs_i:
@@ -225,9 +246,10 @@ class KernelSource:
             for (q, j) in lst:
                 o = self.off_pair + 3 * q
                 self.emit("{ const pm_d3 d = pm_sub(xi, %s); const double rinv = pm_rsqrt(pm_dot(d, d)); const double u = rinv * rinv; const double u3 = u * u * u;" % self.X(j))
-                self.emit("  const double a = %s * u3; const double b = a - %s; const double cq = %s * rinv; e_nb = fma(b, u3, e_nb); e_nb += cq;" % (self.P(o), self.P(o + 1), self.P(o + 2)))
+                # b = c12 u^3 - c6 (one fma), E = b u^3 + K / r;  r dE/dr = -(6 u^3 (2 c12 u^3 - c6) + K / r), with 2 c12 u^3 - c6 = c12 u^3 + b
+                self.emit("  const double b = fma(%s, u3, -%s); const double cq = %s * rinv; e_nb = fma(b, u3, e_nb); e_nb += cq;" % (self.P(o), self.P(o + 1), self.P(o + 2)))
                 if self.wf:
-                    self.emit("  const double g = fma(6.0 * u3, a + b, cq) * u; const pm_d3 fv = pm_d3{g * d.x, g * d.y, g * d.z}; pm_axpy(fi, g, d);")
+                    self.emit("  const double g = fma(6.0 * u3, fma(%s, u3, b), cq) * u; const pm_d3 fv = pm_d3{g * d.x, g * d.y, g * d.z}; pm_axpy(fi, g, d);" % self.P(o))
                 self.addf(j, "fv", "-")
                 self.emit("}")
             self.addf(i, "fi")
@@ -777,7 +799,7 @@ def compile_image(source, want_report=False):
     ``__graft_entry__.build()``) travels to the GPU box with the working-tree snapshot and is only loaded there; a molecule first
     seen on a box with nvcc is compiled once on that box.  Safe when several ranks start at once: source, report and image are
     written under per-process names and moved into place with ``os.replace``, so a reader never sees a partial file and
-    concurrent writers produce identical bytes.  With ``want_report`` also returns the ptxas resource report."""
+    concurrent writers produce identical bytes (the source is moved into place before it is compiled).  With ``want_report`` also returns the ptxas resource report."""
     import hashlib
     import os
     import subprocess
@@ -790,18 +812,21 @@ def compile_image(source, want_report=False):
         if nvcc is None:
             raise RuntimeError("nvcc not found: cannot compile the topology-specialised kernel")
         tag = ".tmp%d" % os.getpid()
-        src = os.path.join(cache_dir(), key + tag + ".cu")
+        final_src = os.path.join(cache_dir(), key + ".cu")
+        src = final_src + tag
         with open(src, "w") as fh:
             fh.write(source)
+        # the source goes into place first (atomically; concurrent ranks write identical bytes) and is compiled under its final
+        # name, so that the -lineinfo records of the image point at a file that exists (ncu source view)
+        os.replace(src, final_src)
         tmp = path + tag
         try:
-            res = subprocess.run([nvcc] + NVCC_FLAGS + ["-I", here, src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+            res = subprocess.run([nvcc] + NVCC_FLAGS + ["-I", here, final_src, "-o", tmp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                  universal_newlines=True)
             if res.returncode != 0:
                 raise RuntimeError("nvcc failed on the specialised kernel:\n" + res.stdout[-2000:])
             with open(tmp + ".txt", "w") as fh:
-                fh.write("# %s\n# %s\n" % (_nvcc_identity(nvcc), " ".join(NVCC_FLAGS)) + res.stdout.replace(key + tag, key))
-            os.replace(src, os.path.join(cache_dir(), key + ".cu"))
+                fh.write("# %s\n# %s\n" % (_nvcc_identity(nvcc), " ".join(NVCC_FLAGS)) + res.stdout)
             os.replace(tmp + ".txt", path + ".txt")
             os.replace(tmp, path)
         finally:
