@@ -109,14 +109,13 @@ __device__ __forceinline__ void pm_pair(const pm_d3 xi, const pm_d3 xj, const do
     const double u = rinv * rinv;
     const double u3 = u * u * u;
     const double c12 = pp[0], c6 = pp[1], cq = pp[2];
-    const double a = c12 * u3;
-    const double b = a - c6;
+    const double b = fma(c12, u3, -c6);  // c12 u^3 - c6
     const double ec = cq * rinv;
     e_nb = fma(b, u3, e_nb);
     e_nb += ec;
     if (WITH_F) {
-        // -(dE/dr)/r = (12 c12 u^6 - 6 c6 u^3 + cq rinv) u = (6 (2a - c6) u3 + ec) u
-        const double g = fma(6.0 * u3, a + b, ec) * u;
+        // -(dE/dr)/r = (12 c12 u^6 - 6 c6 u^3 + cq rinv) u = (6 (2 c12 u^3 - c6) u3 + ec) u, with 2 c12 u^3 - c6 = c12 u^3 + b
+        const double g = fma(6.0 * u3, fma(c12, u3, b), ec) * u;
         pm_axpy(fi, g, d);
         pm_axpy(fj, g, d);
     }
@@ -140,13 +139,12 @@ __device__ __forceinline__ void pm_pair_blk(const pm_d3 xi, const pm_d3 xj, cons
     const double u = rinv * rinv;
     const double u3 = u * u * u;
     const double c12 = pp[0], c6 = pp[1], cq = pp[2];
-    const double a = c12 * u3;
-    const double b = a - c6;
+    const double b = fma(c12, u3, -c6);
     const double ec = cq * rinv;
     e_nb = fma(b, u3, e_nb);
     e_nb += ec;
     if (WITH_F) {
-        const double g = fma(6.0 * u3, a + b, ec) * u;
+        const double g = fma(6.0 * u3, fma(c12, u3, b), ec) * u;
         pm_axpy(fi, g, d);
         pm_axpy(fj, g, d);
     }

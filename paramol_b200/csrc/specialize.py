@@ -758,7 +758,8 @@ def choose_warps(n_atoms):
     tile = 3 * n_atoms * 32 * 8
     table = ((257 * 16 + 127) // 128) * 128
     warps = min(MAX_WARPS, int(math.floor((MAX_SMEM - table) / (128 + 2 * tile))))
-    return warps if warps >= MIN_WARPS else None
+    import os
+    return warps if warps >= int(os.environ.get("PM_SPEC_MIN_WARPS", MIN_WARPS)) else None
 
 
 def _nvcc():
@@ -882,22 +883,24 @@ def choose_warps_energy(n_atoms):
 
 F_REG_WARPS = 8       # forces in registers: 255 registers per thread
 F_REG_MIN_WARPS = 6
-F_REG_MAX_ATOMS = 20   # measured on B200 vs the team-mode interpreter: 18 atoms 1.28x, 20 atoms 1.24x, 22 atoms 0.84x, 24 atoms 0.89x (fits only
-                       # with a fence after every block); 28 atoms spill 1 KB at best
+F_REG_MAX_ATOMS = 26   # measured on B200 vs the team-mode interpreter with the round-2 body (scripts/spec_size_sweep.py, 2^18 conformations,
+                       # M conformations/s, generated : interpreter): 20 atoms 727 : 529, 22 atoms 652 : 510, caffeine (24) 426 : 374,
+                       # 26 atoms 390 : 360, 28 atoms 296 : 299, 32 atoms 186 : 314 (the force-tile shape with 4-7 warps never wins there)
 F_REG_MAX_SPILL = 512  # bytes of spill stores tolerated (aniline at fence 6: 204 bytes, still the fastest)
 
 
 def f_reg_fence(n_atoms):
     """Blocks between scheduling fences for the forces-in-registers shape: the more atoms, the fewer registers are left for
-    interleaving (measured on B200: aniline 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms with spills; ptxas
-    reports: 20 atoms fit at 1-2, 24 atoms only at 1, 28 atoms not at all).  15-20 atoms use 2."""
-    return 6 if n_atoms <= 14 else 2
+    interleaving (measured on B200: aniline 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms with spills; 20 atoms 2 -> 727,
+    1 -> 717 M conformations/s; 22 atoms 2 -> 578, 1 -> 652; caffeine 2 -> 409, 1 -> 426; 26 atoms 2 -> 282, 1 -> 390)."""
+    return 6 if n_atoms <= 14 else (2 if n_atoms <= 20 else 1)
 
 
 def choose_warps_f_reg(n_atoms):
     """Warps per CTA of the forces-in-registers shape (coordinate tile only in shared memory; 255 registers cap it at 8)."""
     import math
-    if n_atoms > F_REG_MAX_ATOMS:
+    import os
+    if n_atoms > int(os.environ.get("PM_SPEC_FREG_MAX", F_REG_MAX_ATOMS)):
         return None
     tile = 3 * n_atoms * 32 * 8
     table = ((257 * 16 + 127) // 128) * 128

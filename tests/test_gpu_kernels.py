@@ -403,3 +403,49 @@ def test_warp_team_mode_parity_vs_oracle(golden_dir, name, n_conf, monkeypatch):
     want = ens.reduce(emm, fres, d_shift=1.5).cpu().numpy().copy()
     got = ens.evaluate_reduce(derived, with_forces=True, d_shift=1.5)[0].cpu().numpy()
     assert np.all(np.abs(got - want) <= 1e-12 * np.maximum(np.abs(want), np.abs(want).max() * 1e-4)), (got, want)
+
+
+@pytest.mark.parametrize("name,n_conf,cpw", [("caffeine", 257, 16), ("caffeine", 130, 8), ("aniline", 99, 16), ("lig26", 70, 8), ("lig26", 41, 4)])
+def test_lane_team_mode_parity_vs_oracle(golden_dir, name, n_conf, cpw, monkeypatch):
+    """Teams of 32 / conf_per_tile LANES of one warp per conformation (the interpreter's shapes for molecules that have no generated
+    kernel), forced here on small molecules with the specialisation off: E, F, the energy-only kernel and the residual epilogue
+    against the oracle."""
+    from oracle import oracle as O
+    monkeypatch.setenv("PARAMOL_B200_SPECIALIZE", "0")
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(97)
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    E, F = O.energies_forces(s, X, n_threads=4)
+    Fref = F + rng.normal(0, 50.0, F.shape)
+    metric = np.tile(np.eye(3).ravel(), (s.n_atoms, 1)) * rng.uniform(0.5, 2.0, (s.n_atoms, 1))
+    r = _run(s, X, Fref, E + rng.normal(0, 5, E.shape), metric, conf_per_tile=cpw)
+    assert r["topo"].conf_per_tile == cpw and not r["topo"].specialized
+    assert np.abs(r["emm"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    assert np.abs(r["fmm"][0] - F).max() < 1e-9 * np.abs(F).max()
+    assert np.abs(r["emm_energy_only_kernel"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    d = F - Fref
+    res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
+    assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
+
+
+@pytest.mark.parametrize("name", ["caffeine", "lig26", "lig22", "lig12"])
+def test_generated_kernel_parity_vs_oracle_at_launch_size(golden_dir, name):
+    """The GENERATED E+F and energy-only kernels (installed automatically up to 26 atoms; they serve batches of >= 32768
+    conformations) against the oracle on 32768 + 45 conformations: energies, forces, residuals; ragged last tile."""
+    from oracle import oracle as O
+    s, x0 = _system(golden_dir, name)
+    rng = np.random.default_rng(7)
+    n_conf = 32768 + 45
+    X = x0[None] + rng.normal(0, 0.005, (n_conf,) + x0.shape)
+    E, F = O.energies_forces(s, X, n_threads=8)
+    Fref = F + rng.normal(0, 50.0, F.shape)
+    metric = np.tile(np.eye(3).ravel(), (s.n_atoms, 1)) * rng.uniform(0.5, 2.0, (s.n_atoms, 1))
+    metric[:, 1] += 0.1
+    r = _run(s, X, Fref, E + rng.normal(0, 5, E.shape), metric)
+    assert r["topo"].specialized and r["topo"].conf_per_tile == 32, r["topo"].specialize_status
+    assert np.abs(r["emm"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    assert np.abs(r["fmm"][0] - F).max() < 1e-9 * np.abs(F).max()
+    assert np.abs(r["emm_energy_only_kernel"][0] - E).max() < 1e-9 * max(1.0, np.abs(E).max())
+    d = F - Fref
+    res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
+    assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
