@@ -392,15 +392,17 @@ class DeviceTopology:
                     n_entries=len(entries))
 
     def prepare(self, slots_dev, derived_dev=None):
-        """slots [P, n_slots] CUDA float64 -> derived [P, n_derived]."""
+        """slots [P, n_slots] float64, a CUDA tensor or a PINNED host tensor (read by the kernel over PCIe: the zero-copy input of
+        the single-vector graph; then ``derived_dev`` must be given) -> derived [P, n_derived]."""
         torch = _torch()
-        assert slots_dev.is_cuda and slots_dev.dtype == torch.float64 and slots_dev.is_contiguous()
+        assert slots_dev.dtype == torch.float64 and slots_dev.is_contiguous()
+        assert slots_dev.is_cuda or (slots_dev.is_pinned() and derived_dev is not None)
         assert slots_dev.dim() == 2 and slots_dev.shape[1] == self.n_slots
         n_vec = slots_dev.shape[0]
         if derived_dev is None:
             derived_dev = torch.empty((n_vec, self.n_derived), dtype=torch.float64, device=slots_dev.device)
         _lib.check(self._L.pm_prepare_params(self._h, slots_dev.data_ptr(), n_vec, derived_dev.data_ptr(),
-                                             _stream_ptr(slots_dev.device)), "pm_prepare_params")
+                                             _stream_ptr(derived_dev.device)), "pm_prepare_params")
         return derived_dev
 
 
@@ -529,7 +531,8 @@ class DeviceEnsemble:
                    "pm_reduce_objective")
         return partials
 
-    def evaluate_reduce(self, derived, with_forces=True, d_shift=0.0, weights="own", comm=None, want_emm=False, want_fres=False):
+    def evaluate_reduce(self, derived, with_forces=True, d_shift=0.0, weights="own", comm=None, want_emm=False, want_fres=False,
+                        partials_out=None):
         """
         ``pm_eval_reduce``: evaluation, residual reduction and -- with ``comm`` (:obj:`paramol_b200.Utils.dist.DeviceComm`) --
         the sum over ranks as one pass; no [P, S] arrays are written unless asked for.  Returns (partials [P, 8] CUDA: global
@@ -542,7 +545,9 @@ class DeviceEnsemble:
         need = int(topo._L.pm_eval_reduce_scratch_doubles(topo._h, n_vec, self.n_conf))
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.float64, device=self.device)
-        partials = self._buf("partials", (n_vec, NPARTIAL))
+        # partials_out: a pinned host tensor [P, 8] the row-sum kernel writes directly (zero-copy output of the single-vector graph)
+        partials = self._buf("partials", (n_vec, NPARTIAL)) if partials_out is None else partials_out
+        assert tuple(partials.shape) == (n_vec, NPARTIAL) and partials.dtype == torch.float64 and (partials.is_cuda or partials.is_pinned())
         w = self.weights if isinstance(weights, str) else weights
         use_f = bool(with_forces) and self.fref_tiles is not None
         emm = self._buf("emm", (n_vec, self.n_conf)) if want_emm else None

@@ -158,14 +158,22 @@ class ObjectiveFunction:
         ``property.value`` are set, ``_f_count`` is incremented in ``opt_mode``; NaN becomes 1e16.
         """
         start_time = time.time()
-        self.parameter_space.update_systems(self.systems, parameters_values)
         if opt_mode:
             self._f_count += 1
         if self._fused:
-            slots = [system.engine.current_slots()[None, :] for system in self.systems]
-            objective_function = float(self._evaluate_fused(slots, np.asarray(parameters_values, dtype=np.float64)[None, :],
-                                                           set_values=True)[0])
+            # the slot rows first; the rest of the update (value lists, MM-system arrays, RESP charges) runs while the device
+            # evaluates (``between``), and in any case before this call returns
+            deferred = []
+            try:
+                self.parameter_space.update_systems(self.systems, parameters_values, defer=deferred)
+                slots = self.parameter_space.last_slots
+                objective_function = float(self._evaluate_fused(slots, np.asarray(parameters_values, dtype=np.float64)[None, :],
+                                                               set_values=True, between=deferred)[0])
+            finally:
+                while deferred:
+                    deferred.pop()()
         else:
+            self.parameter_space.update_systems(self.systems, parameters_values)
             fmm, emm, esp = self._run_serial()
             objective_function = self.calculate_objective_function(parameters_values, fmm, emm, esp)
         if np.isnan(objective_function):
@@ -555,6 +563,11 @@ class ObjectiveFunction:
             # allocate the graph's private buffers eagerly (same shapes as the capture will ask for), then capture.  The eager
             # call communicates too (every rank runs it: the sequence numbers of the communicator stay in step).
             comm = st.get("comm")
+            g["global"] = comm is not None or _dist.world_size() == 1    # the sums the graph delivers are already global
+            # zero-copy ends (no copy-engine nodes in the graph): pm_prepare_kernel reads the pinned slots row over PCIe and the
+            # row-sum kernel writes its 8 sums straight into pinned host memory.  Only the NCCL fallback keeps the sums on the
+            # device (they still have to be all-reduced).
+            zero_copy = g["global"] and os.environ.get("PARAMOL_B200_ZERO_COPY", "1") != "0"
             g["slots_dev"].copy_(g["pin_in"])
             topo.prepare(g["slots_dev"], g["derived"])
             ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
@@ -562,10 +575,15 @@ class ObjectiveFunction:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                g["slots_dev"].copy_(g["pin_in"], non_blocking=True)
-                topo.prepare(g["slots_dev"], g["derived"])
-                part, _, _ = ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
-                g["pin_out"].copy_(part, non_blocking=True)
+                if zero_copy:
+                    topo.prepare(g["pin_in"], g["derived"])
+                    part, _, _ = ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm,
+                                                     partials_out=g["pin_out"])
+                else:
+                    g["slots_dev"].copy_(g["pin_in"], non_blocking=True)
+                    topo.prepare(g["slots_dev"], g["derived"])
+                    part, _, _ = ens.evaluate_reduce(g["derived"], with_forces=st["need_f"], d_shift=st["d_shift"], comm=comm)
+                    g["pin_out"].copy_(part, non_blocking=True)
             g["graph"] = graph
             g["part_dev"] = part
             # raw handles for pm_graph_call (one C call per objective evaluation: stage, launch, wait, read back)
@@ -574,12 +592,11 @@ class ObjectiveFunction:
             g["pin_in_ptr"] = ctypes.c_void_p(g["pin_in"].data_ptr())
             g["pin_out_ptr"] = ctypes.c_void_p(g["pin_out"].data_ptr())
             g["out"] = np.zeros((1, NPARTIAL))
-            g["global"] = comm is not None or _dist.world_size() == 1    # the sums in pin_out are already global
         finally:
             ens._buffers, ens._scratch = saved_bufs, saved_scratch
         return g
 
-    def _evaluate_fused(self, slots_per_system, X, set_values):
+    def _evaluate_fused(self, slots_per_system, X, set_values, between=None):
         """
         slots_per_system: list over ``self.systems`` of float64 [P, n_slots]; X [P, P_opt] for the regularisation.
         Returns numpy [P].
@@ -671,7 +688,9 @@ class ObjectiveFunction:
                 partial_list.append(ens.reduce(emm, fres, d_shift=st["d_shift"]))
         live = [p for p in partial_list if p is not None and not isinstance(p, str)]
         values = np.zeros(n_vec)
-        # host-only term first: it overlaps the kernels that are still running
+        # host-only work first: it overlaps the kernels that are still running
+        while between:
+            between.pop()()
         reg = None
         if r_prop is not None:
             if set_values:

@@ -216,10 +216,15 @@ class ParameterSpace:
             return x * self.scaling_constants
         return x
 
-    def update_systems(self, systems, parameters_values, symmetry_constrained=True):
+    def update_systems(self, systems, parameters_values, symmetry_constrained=True, defer=None):
         """
         Pushes ``parameters_values`` (scaled if ``preconditioned``) into every Parameter, force field and engine
         (reference ``:348-399``).  Returns the physical parameter vector.
+
+        ``defer``: a list, or None.  With a list, the part of the update nobody needs before the evaluation starts (the
+        per-system value lists, the MM-system parameter arrays, the RESP engine's charges) is appended to it as ONE callable
+        instead of being executed: ``ObjectiveFunction.f`` runs it while the device evaluates.  ``last_slots`` holds the slot row
+        of every system either way.
         """
         if self.preconditioned:
             self.optimizable_parameters_values_scaled = parameters_values
@@ -228,27 +233,41 @@ class ParameterSpace:
             self.optimizable_parameters_values = parameters_values
         x = np.asarray(self.optimizable_parameters_values, dtype=np.float64)
         plan = self._compile_scatter(systems, symmetry_constrained)
-        system = None
-        by_system = []
+        pending = []
+        last_slots = []
         for system, sc, idx in zip(systems, plan["per_system"], plan["by_system_idx"]):
             ff = system.force_field
             if len(sc["dst"]):
                 ff.store[sc["dst"]] = x[sc["src"]]
             # per-system value list as the reference builds it right after the scatter (parameter_space.py:383-385),
             # gathered from the value store instead of reading 232 Python properties per call
-            by_system.append(ff.store[idx].tolist())
+            values = ff.store[idx]
             engine_plan = system.engine.compile_update_plan(ff)
             if len(engine_plan["abs_idx"]):
                 ff.store[engine_plan["abs_idx"]] = np.abs(ff.store[engine_plan["abs_idx"]])
             slots = system.engine.slots_from_store(ff, ff.store[None, :])
-            system.engine.load_slots(slots[0])
-        self.optimizable_parameters_values_by_system = by_system
-        # as in the reference, only the LAST system's RESP engine is refreshed (:394-395 uses the loop variable)
-        if system is not None and system.resp_engine is not None:
-            if hasattr(system.resp_engine, "set_charges"):
-                system.resp_engine.set_charges(system.force_field.force_field)
-            else:
-                raise NotImplementedError("MM RESP Engine {} is not implemented.".format(type(system.resp_engine)))
+            last_slots.append(slots)
+            pending.append((system, values, slots))
+        self.last_slots = last_slots
+
+        def finish():
+            by_system = []
+            system = None
+            for system, values, slots in pending:
+                by_system.append(values.tolist())
+                system.engine.load_slots(slots[0])
+            self.optimizable_parameters_values_by_system = by_system
+            # as in the reference, only the LAST system's RESP engine is refreshed (:394-395 uses the loop variable)
+            if system is not None and system.resp_engine is not None:
+                if hasattr(system.resp_engine, "set_charges"):
+                    system.resp_engine.set_charges(system.force_field.force_field)
+                else:
+                    raise NotImplementedError("MM RESP Engine {} is not implemented.".format(type(system.resp_engine)))
+
+        if defer is None:
+            finish()
+        else:
+            defer.append(finish)
         return self.optimizable_parameters_values
 
     def gradient_from_store(self, systems, parameters_values, store_gradients, symmetry_constrained=True):
