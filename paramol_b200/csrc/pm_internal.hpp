@@ -81,7 +81,9 @@ int pm_spec_metric_changed(pm_handle h);
 int pm_spec_launch_info(pm_handle h, int with_forces, int *block, int *smem_bytes, int *warps);  // 1 when a specialised kernel serves that mode
 int pm_spec_can_eval(pm_handle h, int with_forces);
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf, double *emm,
-                 double *fres, double *fmm_t, int with_forces, cudaStream_t stream);
+                 double *fres, double *fmm_t, int with_forces, PmRed red, cudaStream_t stream);
+int pm_spec_fused(pm_handle h);                                 // 1 when the generated kernels accumulate the residual sums themselves
+long pm_spec_rows(pm_handle h, int with_forces, long n_conf);   // rows of five they write per vector
 
 // pm_comm.cu
 int pm_comm_max_vec(pm_comm c);

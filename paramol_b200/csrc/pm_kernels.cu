@@ -1356,7 +1356,7 @@ static int pm_eval_core(pm_handle h, const double *derived_dev, int n_vec, const
     PM_CUDA(cudaSetDevice(h->device));
     if (!red.rows && pm_use_spec(h, with_forces, n_vec, n_conf, mode))
         return pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, fmm_tiles_dev,
-                            with_forces ? 1 : 0, (cudaStream_t)stream);
+                            with_forces ? 1 : 0, PmRed{nullptr, nullptr, 0.0, nullptr}, (cudaStream_t)stream);
     const int wf = with_forces ? 1 : 0;
     const long n_tiles = pm_n_tiles(h, n_conf);
     const int warps = h->warps[wf], units = h->team_warps ? warps / h->team_warps : warps;  // tiles in flight per CTA
@@ -1401,8 +1401,11 @@ extern "C" long pm_eval_reduce_scratch_doubles(pm_handle h, int n_vec, long n_co
     const long r0 = pm_red_rows(h, 0, n_conf), r1 = pm_red_rows(h, 1, n_conf);
     long rows = r0 > r1 ? r0 : r1;
     if (rows < PM_RED_BLOCKS) rows = PM_RED_BLOCKS;
-    // generated kernels: per-conformation energies and residuals of the batch are staged behind the rows
-    const long stage = (pm_spec_can_eval(h, 0) || pm_spec_can_eval(h, 1)) ? 2L * n_vec * n_conf : 0L;
+    const long s0 = pm_spec_rows(h, 0, n_conf), s1 = pm_spec_rows(h, 1, n_conf);
+    if (rows < s0) rows = s0;
+    if (rows < s1) rows = s1;
+    // generated kernels without fused sums: per-conformation energies and residuals of the batch are staged behind the rows
+    const long stage = ((pm_spec_can_eval(h, 0) || pm_spec_can_eval(h, 1)) && !pm_spec_fused(h)) ? 2L * n_vec * n_conf : 0L;
     return (long)n_vec * rows * 5 + stage;
 }
 
@@ -1414,11 +1417,22 @@ extern "C" int pm_eval_reduce(pm_handle h, const double *derived_dev, int n_vec,
     if (n_vec < 1 || n_conf < 1) return pm_fail("pm_eval_reduce: empty batch");
     if (!with_forces && (fref_tiles_dev || fres_dev)) return pm_fail("pm_eval_reduce: force inputs/outputs given with with_forces=0");
     if (comm && n_vec > pm_comm_max_vec(comm)) return pm_fail("pm_eval_reduce: more parameter vectors than the communicator was created for");
+    if (pm_use_spec(h, with_forces, n_vec, n_conf, 0) && pm_spec_fused(h)) {
+        // generated kernel with the residual sums in its epilogue: rows of five per warp -> row sum (+ all-reduce)
+        PM_CUDA(cudaSetDevice(h->device));
+        const int rc = pm_spec_eval(h, derived_dev, n_vec, coord_tiles_dev, fref_tiles_dev, n_conf, emm_dev, fres_dev, nullptr,
+                                    with_forces ? 1 : 0, PmRed{eref_dev, weights_dev, d_shift, scratch_dev}, (cudaStream_t)stream);
+        if (rc) return rc;
+        return pm_reduce_rows(scratch_dev, pm_spec_rows(h, with_forces ? 1 : 0, n_conf), n_vec, n_conf, partials_dev, comm, (cudaStream_t)stream);
+    }
     if (pm_use_spec(h, with_forces, n_vec, n_conf, 0)) {
         // generated kernel (round-1 form: energy and residual per conformation) -> stage-1 sums as rows -> row sum (+ all-reduce)
         const long r0 = pm_red_rows(h, 0, n_conf), r1 = pm_red_rows(h, 1, n_conf);
         long rows = r0 > r1 ? r0 : r1;
         if (rows < PM_RED_BLOCKS) rows = PM_RED_BLOCKS;
+        const long s0 = pm_spec_rows(h, 0, n_conf), s1 = pm_spec_rows(h, 1, n_conf);
+        if (rows < s0) rows = s0;
+        if (rows < s1) rows = s1;
         double *stage = scratch_dev + (size_t)n_vec * rows * 5;
         double *e_buf = emm_dev ? emm_dev : stage;
         double *r_buf = fref_tiles_dev ? (fres_dev ? fres_dev : stage + (size_t)n_vec * n_conf) : nullptr;

@@ -29,6 +29,7 @@ struct PmSpecState {
     double *tab_dev;  // __constant__ spec_tab[n_derived + 9 N]: derived table of the vector being evaluated, then the metric
     int warps, warps_e, warps_g;
     int ngp;          // padded number of gradient quantities (rows of the partial array are ngp doubles)
+    int fused;        // the E+F / energy kernels take (eref, weights, d_shift, rows) and accumulate the residual sums themselves
     size_t smem, smem_e, smem_g;
 };
 
@@ -80,8 +81,11 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
             ef_info[0] = 0;
         cudaGetLastError();
     }
+    if (ef_info[1] != 0 && ef_info[1] != 1) ef_info[1] = 0;
+    st->fused = ef_info[1];
+    const size_t red_bytes = st->fused ? (size_t)5 * 32 * sizeof(double) : 0;   // [5][32] running sums per warp
     st->smem = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) +
-               (size_t)warps * (128 + tile * (size_t)(1 + ef_info[0]) + (size_t)3 * n_force_tile_atoms * 32 * sizeof(double));
+               (size_t)warps * (128 + red_bytes + tile * (size_t)(1 + ef_info[0]) + (size_t)3 * n_force_tile_atoms * 32 * sizeof(double));
     if (st->smem > (size_t)h->max_smem ||
         cudaFuncSetAttribute((const void *)st->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem) != cudaSuccess) {
         cudaGetLastError();
@@ -93,7 +97,7 @@ extern "C" int pm_set_specialized(pm_handle h, const void *image, long n_bytes, 
     st->smem_e = 0;
     if (warps_energy > 0 && warps_energy <= 32 && cudaLibraryGetKernel(&st->kernel_e, st->lib, "pm_e_spec_kernel") == cudaSuccess) {
         st->warps_e = warps_energy;
-        st->smem_e = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps_energy * (128 + tile);
+        st->smem_e = (((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127) + (size_t)warps_energy * (128 + red_bytes + tile);
         if (st->smem_e > (size_t)h->max_smem ||
             cudaFuncSetAttribute((const void *)st->kernel_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem_e) != cudaSuccess)
             st->kernel_e = nullptr;
@@ -154,8 +158,28 @@ int pm_spec_can_eval(pm_handle h, int with_forces) {
     return st && (with_forces || st->kernel_e) ? 1 : 0;
 }
 
+int pm_spec_fused(pm_handle h) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    return st && st->fused ? 1 : 0;
+}
+
+// rows of five sums one launch of the generated kernel writes per parameter vector when it reduces (one per warp of the grid)
+long pm_spec_rows(pm_handle h, int with_forces, long n_conf) {
+    PmSpecState *st = (PmSpecState *)h->spec_state;
+    if (!st) return 0;
+    const int warps = with_forces ? st->warps : st->warps_e;
+    if (warps < 1) return 0;
+    const long n_tiles = (n_conf + 31) / 32;
+    long grid = h->n_sm;
+    if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
+    if (grid < 1) grid = 1;
+    return grid * warps;
+}
+
+// red.rows != nullptr (images with fused sums only): the kernel adds the five weighted sums of pm_reduce_objective over the
+// conformations of each warp and writes [P][grid * warps][5]; emm / fres may then be null (nothing per conformation is written)
 int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double *xt, const double *fref_t, long n_conf,
-                 double *emm, double *fres, double *fmm_t, int with_forces, cudaStream_t stream) {
+                 double *emm, double *fres, double *fmm_t, int with_forces, PmRed red, cudaStream_t stream) {
     PmSpecState *st = (PmSpecState *)h->spec_state;
     const cudaKernel_t kernel = with_forces ? st->kernel : st->kernel_e;
     const int warps = with_forces ? st->warps : st->warps_e;
@@ -166,13 +190,20 @@ int pm_spec_eval(pm_handle h, const double *derived_dev, int n_vec, const double
     long grid = h->n_sm;
     if (grid * warps > n_tiles) grid = (n_tiles + warps - 1) / warps;
     if (grid < 1) grid = 1;
+    if (red.rows && !st->fused) return pm_fail_msg("pm_spec_eval: this image has no fused residual sums");
+    if (!red.rows && !emm) return pm_fail_msg("pm_spec_eval: no output requested");
     const double2 *acos_tab = h->d_acos;
+    const long n_rows = grid * warps;
     for (int p = 0; p < n_vec; ++p) {
         // the parameters of this vector become constant-bank operands of the kernel
         PMS_CUDA(cudaMemcpyAsync(st->tab_dev, derived_dev + (size_t)p * h->prog.n_derived, sizeof(double) * nd, cudaMemcpyDeviceToDevice, stream));
-        double *e_p = emm + (size_t)p * n_conf, *r_p = fres ? fres + (size_t)p * n_conf : nullptr;
+        double *e_p = emm ? emm + (size_t)p * n_conf : nullptr, *r_p = fres ? fres + (size_t)p * n_conf : nullptr;
         double *f_p = fmm_t ? fmm_t + (size_t)p * n_tiles * tile_d : nullptr;
-        void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p};
+        const double *eref = red.eref, *wgt = red.w;
+        double d_shift = red.d_shift;
+        double *rows_p = red.rows ? red.rows + (size_t)p * n_rows * 5 : nullptr;
+        void *args[] = {(void *)&acos_tab, (void *)&xt, (void *)&fref_t, (void *)&n_conf, (void *)&n_tiles, (void *)&e_p, (void *)&r_p, (void *)&f_p,
+                        (void *)&eref, (void *)&wgt, (void *)&d_shift, (void *)&rows_p};   // (the last four: fused images only)
         PMS_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)grid), dim3(warps * 32), args, smem, stream));
     }
     return 0;

@@ -44,6 +44,8 @@ class KernelSource:
         # second shared tile per warp: the reference forces of the tile arrive by bulk copy while the body runs, and the next
         # tile's coordinates are requested as soon as the body has read the current ones (set by image_for when it fits)
         self.prefetch = 0
+        # residual sums of pm_eval_reduce accumulated by the kernel itself (no [S] energy / residual round trip, no stage-1 launch)
+        self.fused_sums = bool(int(_os.environ.get("PM_SPEC_FUSED", FUSED_SUMS)))
         self._blocks = 0
         self.name = name
         self.off_bond = 0
@@ -299,11 +301,41 @@ class KernelSource:
         pfr = 1 if (pf and self.prefetch == 2) else 0
         import os as _os
         topsync = 1 if (self.sync_every and int(_os.environ.get("PM_SPEC_TOPSYNC", TOP_SYNC))) else 0
+        red = 1 if self.fused_sums else 0
+        red_params = (", const double *__restrict__ eref, const double *__restrict__ wgt, double d_shift, double *__restrict__ rows"
+                      if red else "")
+        red_init = "for (int q = 0; q < 5; ++q) ra[q * 32 + lane] = 0.0;" if red else ""
+        want_res = ("fres != nullptr || (rows != nullptr && fref_t != nullptr)" if red else "fres != nullptr") if self.wf else "false"
+        # fused residual reduction: the five weighted sums of pm_reduce_objective (d = E_ref - E - shift: sum d, sum w d, sum w d^2,
+        # sum w, sum w res) are kept per lane in shared memory and become one row of five per warp at the end of the kernel
+        red_acc = """if (rows != nullptr) {
+            double d = 0.0, ws = 0.0;
+            if (live && sconf < n_conf) {
+                d = (eref != nullptr ? eref[sconf] : 0.0) - e_total - d_shift;
+                ws = wgt != nullptr ? wgt[sconf] : 1.0;
+            }
+            double *ra_l = ra + lane;
+            ra_l[0] += d;
+            ra_l[32] = fma(ws, d, ra_l[32]);
+            ra_l[64] = fma(ws * d, d, ra_l[64]);
+            ra_l[96] += ws;
+            ra_l[128] = fma(ws, res, ra_l[128]);
+        }""" if red else ""
+        red_out = """if (rows != nullptr) {
+        __syncwarp();
+        double *out = rows + ((size_t)blockIdx.x * n_warps + warp) * 5;
+        for (int q = 0; q < 5; ++q) {
+            double v = ra[q * 32 + lane];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) out[q] = v;
+        }
+    }""" if red else ""
         kernel = _KERNEL.format(name=self.name, W=warps, body=body, f_decl=f_decl, res=res, fout=fout, PF=pf, PFR=pfr, TOPSYNC=topsync,
+                                RED=red, RED_PARAMS=red_params, RED_INIT=red_init, WANT_RES=want_res, RED_ACC=red_acc, RED_OUT=red_out,
                                 f_doubles=0 if (self.f_reg or not self.wf) else 3 * len(self.f_tile_atoms) * 32, x_tile=0 if self.x_reg else 1, x_load=x_load)
         if self.name == "pm_ef_spec_kernel":
             # extra TILE_D buffers per warp of the E+F kernel, read by pm_set_specialized to size the shared memory
-            kernel = "__constant__ int spec_ef_info[2] = {%d, 0};\n" % pfr + kernel
+            kernel = "__constant__ int spec_ef_info[2] = {%d, %d};\n" % (pfr, red) + kernel
         return kernel if not with_header else _HEADER.format(N=N, ND=self.n_derived) + kernel
 
 
@@ -328,20 +360,23 @@ _KERNEL = r'''
 extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     {name}(const double2 *__restrict__ acos_tab, const double *__restrict__ xt,
            const double *__restrict__ fref_t, long n_conf, long n_tiles, double *__restrict__ emm, double *__restrict__ fres,
-           double *__restrict__ fmm_t) {{
+           double *__restrict__ fmm_t{RED_PARAMS}) {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     double2 *s_acos = reinterpret_cast<double2 *>(smem_raw);
     size_t off = ((size_t)(PM_ACOS_N + 1) * sizeof(double2) + 127) & ~(size_t)127;
-    const size_t per_warp = 128 + ((size_t)TILE_D * ({x_tile} + {PFR}) + (size_t){f_doubles}) * sizeof(double);
+    const size_t per_warp = 128 + ((size_t)TILE_D * ({x_tile} + {PFR}) + (size_t){f_doubles} + (size_t){RED} * 160) * sizeof(double);
     unsigned char *wbase = smem_raw + off + per_warp * warp;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
     uint64_t *bar_r = bar + 1;
     double *xs = reinterpret_cast<double *>(wbase + 128);
     double *fs = xs + ({x_tile} ? TILE_D : 0);
     double *rs = fs + {f_doubles};
+    double *ra = rs + ({PFR} ? TILE_D : 0);   // fused residual sums: [5][32] running sums of this warp's lanes
     (void)fs;
     (void)rs;
+    (void)ra;
+    {RED_INIT}
     for (int i = threadIdx.x; i <= PM_ACOS_N; i += blockDim.x) s_acos[i] = acos_tab[i];
     if (lane == 0) {{
         pm_mbar_init(bar, 1);
@@ -350,6 +385,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
     }}
     __syncthreads();
     uint32_t parity = 0, parity_r = 0;
+    const bool want_res = {WANT_RES};
     const long warp_stride = (long)gridDim.x * n_warps;
     // uniform trip count per CTA (the body may contain CTA barriers): a warp without a tile of its own repeats the last tile
     // of the problem and stores nothing
@@ -370,16 +406,16 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
             if ({PF}) {{
                 // reference forces of this tile into the second buffer while the body runs (the buffer was last read in the
                 // previous iteration's epilogue, before its closing __syncwarp)
-                if ({PFR} && fres != nullptr) {{
+                if ({PFR} && want_res) {{
                     pm_fence_proxy_async();
                     pm_mbar_expect_tx(bar_r, (uint32_t)(TILE_D * sizeof(double)));
                     pm_bulk_g2s(rs, fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar_r);
-                }} else if (fres != nullptr) {{
+                }} else if (want_res) {{
                     pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 }}
                 if (tile + warp_stride < n_tiles) {{
                     pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
-                    if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                    if (want_res) pm_bulk_prefetch_l2(fref_t + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 }}
             }} else {{
                 if ({x_tile}) {{
@@ -387,7 +423,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
                     pm_mbar_expect_tx(bar, (uint32_t)(TILE_D * sizeof(double)));
                     pm_bulk_g2s(xs, xt + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)), bar);
                 }}
-                if (fres != nullptr) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
+                if (want_res) pm_bulk_prefetch_l2(fref_t + (size_t)tile * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
                 if (tile + warp_stride < n_tiles) pm_bulk_prefetch_l2(xt + (size_t)(tile + warp_stride) * TILE_D, (uint32_t)(TILE_D * sizeof(double)));
             }}
         }}
@@ -419,7 +455,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
         const long sconf = tile * 32 + lane;
         const double e_total = ((e_bond + e_angle) + e_tors) + e_nb;
         double res = 0.0;
-        if (fres != nullptr) {{
+        if (want_res) {{
             if ({PFR}) {{
                 pm_mbar_wait(bar_r, parity_r);
                 parity_r ^= 1;
@@ -429,7 +465,8 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
                 {res}
             }}
         }}
-        if (live && sconf < n_conf) {{
+        {RED_ACC}
+        if (live && sconf < n_conf && emm != nullptr) {{
             emm[sconf] = e_total;
             if (fres != nullptr) fres[sconf] = res;
         }}
@@ -441,6 +478,7 @@ extern "C" __global__ void __launch_bounds__({W} * 32, 1)
         }}
         __syncwarp();
     }}
+    {RED_OUT}
 }}
 '''
 
@@ -745,6 +783,18 @@ MAX_WARPS = 10
 MAX_WARPS_ENERGY = 16   # 128 registers, no spills
 TOP_SYNC = 0   # CTA barrier at the top of every tile iteration: measured slower (aniline 0.617 -> 0.652 ms: all warps then wait for
                # their coordinate tiles at the same time)
+FUSED_SUMS = 0   # residual sums accumulated by the generated kernel itself (rows of five per warp instead of per-conformation energy and
+                 # residual + pm_reduce_stage1): measured on B200 with the round-2 body, aniline 2^20: kernel 0.449 -> 0.466 ms with the code
+                 # present (register allocation / layout), eval+reduce 0.479 -> 0.497 ms (the reference-energy load at the end of a tile is
+                 # exposed with 2 warps per scheduler); 2^17 conformations: 84.0 vs 84.0 us.  Off.
+
+
+def _red_bytes():
+    """Shared memory per warp of the fused residual sums ([5][32] doubles) when that variant is generated."""
+    import os
+    return 5 * 32 * 8 if int(os.environ.get("PM_SPEC_FUSED", FUSED_SUMS)) else 0
+
+
 PREFETCH = 0   # 0: coordinates requested at the top of the tile loop (L2-prefetched one tile ahead); 1: next tile's coordinates
                # requested right after the body; 2: also the reference forces by bulk copy into a second tile per warp.
                # Measured on B200 (aniline, 2^20): 0 -> 0.619 ms, 1 -> 0.649 ms, 2 -> 0.636 ms: the waits they remove are
@@ -757,7 +807,7 @@ def choose_warps(n_atoms):
     import math
     tile = 3 * n_atoms * 32 * 8
     table = ((257 * 16 + 127) // 128) * 128
-    warps = min(MAX_WARPS, int(math.floor((MAX_SMEM - table) / (128 + 2 * tile))))
+    warps = min(MAX_WARPS, int(math.floor((MAX_SMEM - table) / (128 + _red_bytes() + 2 * tile))))
     import os
     return warps if warps >= int(os.environ.get("PM_SPEC_MIN_WARPS", MIN_WARPS)) else None
 
@@ -867,7 +917,7 @@ def choose_warps_hybrid(n_atoms, n_tile_atoms):
     """Warps per CTA when n_tile_atoms keep their forces in a packed shared tile and the rest in registers (255 registers: 8)."""
     import math
     table = ((257 * 16 + 127) // 128) * 128
-    per_warp = 128 + 3 * (n_atoms + n_tile_atoms) * 32 * 8
+    per_warp = 128 + _red_bytes() + 3 * (n_atoms + n_tile_atoms) * 32 * 8
     warps = min(F_REG_WARPS, int(math.floor((MAX_SMEM - table) / per_warp)))
     return warps if warps >= F_REG_MIN_WARPS else None
 
@@ -877,7 +927,7 @@ def choose_warps_energy(n_atoms):
     import math
     tile = 3 * n_atoms * 32 * 8
     table = ((257 * 16 + 127) // 128) * 128
-    warps = min(MAX_WARPS_ENERGY, int(math.floor((MAX_SMEM - table) / (128 + tile))))
+    warps = min(MAX_WARPS_ENERGY, int(math.floor((MAX_SMEM - table) / (128 + _red_bytes() + tile))))
     return warps if warps >= MIN_WARPS else None
 
 
@@ -904,7 +954,7 @@ def choose_warps_f_reg(n_atoms):
         return None
     tile = 3 * n_atoms * 32 * 8
     table = ((257 * 16 + 127) // 128) * 128
-    warps = min(F_REG_WARPS, int(math.floor((MAX_SMEM - table) / (128 + tile))))
+    warps = min(F_REG_WARPS, int(math.floor((MAX_SMEM - table) / (128 + _red_bytes() + tile))))
     return warps if warps >= F_REG_MIN_WARPS else None
 
 
@@ -941,7 +991,7 @@ def image_for(n_atoms, bonds, angles, torsions, tors_per, pairs):
         tile = 3 * n_atoms * 32 * 8
         table = ((257 * 16 + 127) // 128) * 128
         ks.prefetch = int(os.environ.get("PM_SPEC_PREFETCH", PREFETCH))
-        if ks.prefetch == 2 and table + w * (128 + 2 * tile + 3 * len(ks.f_tile_atoms) * 32 * 8) > MAX_SMEM:
+        if ks.prefetch == 2 and table + w * (128 + _red_bytes() + 2 * tile + 3 * len(ks.f_tile_atoms) * 32 * 8) > MAX_SMEM:
             ks.prefetch = 1
         src = ks.source(w)
         if we:

@@ -449,3 +449,31 @@ def test_generated_kernel_parity_vs_oracle_at_launch_size(golden_dir, name):
     d = F - Fref
     res = np.einsum("sna,nab,snb->s", d, metric.reshape(-1, 3, 3), d)
     assert np.abs(r["fres"][0] - res).max() <= OBJ_RTOL * np.abs(res).max()
+
+
+def test_generated_kernel_fused_sums_variant(monkeypatch):
+    """The measured-and-not-shipped variant of the generated kernels (``PM_SPEC_FUSED=1``: the kernel accumulates the five residual
+    sums itself and writes one row of five per warp; no per-conformation energy / residual, no ``pm_reduce_stage1``): its
+    ``pm_eval_reduce`` equals ``pm_eval`` + ``pm_reduce_objective`` of the same image, with and without forces, weighted, ragged."""
+    import torch
+    from paramol_b200.MM_engines.device import DeviceEnsemble, DeviceTopology
+    from paramol_b200.Utils.synthetic import make_ligand
+    mm, x0 = make_ligand(12)
+    monkeypatch.setenv("PM_SPEC_FUSED", "1")
+    topo = DeviceTopology(mm)
+    assert topo.specialized
+    rng = np.random.default_rng(5)
+    n_conf = 32768 + 77
+    X = x0[None] + rng.normal(0, 0.01, (n_conf,) + x0.shape)
+    F = rng.normal(0, 50.0, X.shape)
+    topo.set_force_metric(np.tile(np.eye(3).ravel(), (12, 1)) * rng.uniform(0.5, 2.0, (12, 1)))
+    ens = DeviceEnsemble(topo, X, F, rng.normal(0, 5.0, n_conf))
+    ens.set_weights(rng.uniform(0.5, 1.5, n_conf))
+    base = topo.slots_from_system(mm)
+    rows = base[None] * (1.0 + 0.02 * rng.uniform(-1, 1, (3, len(base))))
+    der = topo.prepare(torch.from_numpy(rows).cuda())
+    for wf in (True, False):
+        emm, fres, _ = ens.evaluate(der, with_forces=wf, want_fres=wf)
+        want = ens.reduce(emm, fres, d_shift=0.7).cpu().numpy().copy()
+        got = ens.evaluate_reduce(der, with_forces=wf, d_shift=0.7)[0].cpu().numpy()
+        assert np.all(np.abs(got - want) <= 1e-11 * np.maximum(np.abs(want), np.abs(want).max() * 1e-4)), (wf, got, want)
