@@ -193,10 +193,18 @@ __device__ __forceinline__ double pm_axis_cells(const int *__restrict__ cells, c
 
 // Force write-back of one step.  One lane per conformation (L == 1): plain.  Teams of lanes: the records of a step that share a
 // colour touch disjoint atoms (pm_program.hpp), colours are serialised with __syncwarp between them.  Teams of WARPS (WT): the
-// records of a step are disjoint by construction (one colour), the step ends with a barrier of the team.
+// same colours, one ROUND of the team's split barrier per colour (wait until the updates of the previous round are complete,
+// update if the record has this round's colour, arrive) -- the records of a step are all computed concurrently and only their
+// short write-backs are ordered.
 #define PM_ORDERED(n_col, colour, cond, ...)           \
-    if (L == 1 || WT) {                                \
+    if (L == 1) {                                      \
         if (cond) __VA_ARGS__                          \
+    } else if (WT) {                                   \
+        for (int _c = 0; _c < (n_col); ++_c) {         \
+            round_wait();                              \
+            if ((cond) && (colour) == _c) __VA_ARGS__  \
+            round_arrive();                            \
+        }                                              \
     } else {                                           \
         for (int _c = 0; _c < (n_col); ++_c) {         \
             if ((cond) && (colour) == _c) __VA_ARGS__  \
@@ -426,7 +434,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                 }
                 if (WITH_F) {
                     // write-back: records of one colour touch disjoint atoms; colours are serialised
-                    round_wait();
                     PM_ORDERED(n_col, te.y, rec >= 0, {
                         pm_d3 fc{0.0, 0.0, 0.0};
                         _Pragma("unroll") for (int k = 0; k < 4; ++k) {
@@ -440,7 +447,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, center, fc);
                     })
                 }
-                round_arrive();  // the next step's records may touch the atoms this step's members just updated
             }
 
             // ================= axes: every torsion around a rotation axis j-k (trig-free) ================
@@ -494,7 +500,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                     }
                 }
                 pm_d3 Fj{0.0, 0.0, 0.0}, Fk{0.0, 0.0, 0.0};
-                round_wait();  // (the substituent forces are written inside the loop below)
+                double Ai0 = 0.0, Ai1 = 0.0, Ai2 = 0.0;  // teams of warps: the scalars of F_i = A_i c1_i (re-formed at the write-back)
                 const int ni_loop = (L > 1 && !WT) ? (hdr >> 8) : nI;   // (teams of lanes: the longest record of the step)
                 for (int pi = 0; pi < ni_loop; ++pi) {
                     const bool act = L == 1 || WT || (live && pi < nI);
@@ -550,9 +556,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                             fi = pm_d3{A * c1.x, A * c1.y, A * c1.z};
                             pm_axpy(Fj, Ag - A, c1);  // F_j -= A (1 - g1) c1
                             pm_axpy(Fk, -Ag, c1);     // F_k -= g1 A c1
+                            if (WT) {
+                                if (pi == 0)
+                                    Ai0 = A;
+                                else if (pi == 1)
+                                    Ai1 = A;
+                                else
+                                    Ai2 = A;
+                            }
                         }
                     }
-                    if (WITH_F) {
+                    if (WITH_F && !WT) {
                         PM_ORDERED(n_col, te.y, act, { pm_addo<CPW>(fc_base, ai, fi); })
                     }
                 }
@@ -568,6 +582,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         }
                     }
                     PM_ORDERED(n_col, te.y, live, {
+                        if (WT) {
+                            // the i-substituents: F_i = A_i (d0 x d1) with the cross product formed again (9 FP64 operations per
+                            // substituent instead of keeping up to three force vectors alive through the write-back rounds)
+                            const double Ai[3] = {Ai0, Ai1, Ai2};
+                            _Pragma("unroll") for (int q = 0; q < 3; ++q) {
+                                if (q < nI) {
+                                    const int ai = arec[4 + q];
+                                    const pm_d3 c1 = pm_cross(pm_sub(pm_ldo<CPW>(xc_base, ai), xj), d1);
+                                    pm_addo<CPW>(fc_base, ai, pm_d3{Ai[q] * c1.x, Ai[q] * c1.y, Ai[q] * c1.z});
+                                }
+                            }
+                        }
                         _Pragma("unroll") for (int q = 0; q < 3; ++q) {
                             if (q < nL) pm_addo<CPW>(fc_base, La[q], pm_d3{B[q] * c2[q].x, B[q] * c2[q].y, B[q] * c2[q].z});
                         }
@@ -575,7 +601,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
                         pm_addo<CPW>(fc_base, ak, Fk);
                     })
                 }
-                round_arrive();
             }
 
             // ================= nonbonded, teams: 4 x 4 register blocks on disjoint tile pairs ====================
@@ -911,7 +936,8 @@ static pm_ef_fn pm_pick_kernel_w(int cpw, int wf) {
         default: return nullptr;
     }
 }
-#define PM_TEAM_WARPS 8  // members of a team of warps (the one size compiled)
+#define PM_TEAM_WARPS 8  // members of a team of warps (the one size compiled; teams of 16 warps were measured and dropped: the 4 x 4
+                         // pair blocks of a 60-atom molecule fill only 120 of 256 slots -- lig60 68.0 vs 83.8 M conformations/s)
 static pm_ef_fn pm_pick_kernel(int cpw, int wf, int maxw, int rf = 0, int team_warps = 0) {
     if (team_warps > 1) {  // teams of PM_TEAM_WARPS warps: 8 warps per CTA (168 registers) or 16 (128 registers)
         if (maxw <= 12) return wf ? pm_ef_kernel<32, true, 8, false, PM_TEAM_WARPS> : pm_ef_kernel<32, false, 8, false, PM_TEAM_WARPS>;
@@ -1080,13 +1106,16 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
                 if (w >= 9) break;
             }
         }
-        // Large molecules that need teams of lanes anyway: teams of 8 WARPS on tiles of 32 conformations instead, if two such teams
-        // (16 warps) fit -- every branch is uniform and every index a broadcast, as with one lane per conformation, but every step
-        // ends with a barrier of the team.  Measured on B200 (M conformations/s, lanes vs warps): lig50 113 vs 119, lig60 72.6 vs
-        // 73.7 (one team), norfloxacin 164 vs 127, lig33 248 vs 153, caffeine 386 vs 171: the barriers only pay once the pair phase
-        // (balanced 16-pair blocks) dominates, i.e. from about 46 atoms on.
+        // Large molecules that need teams of lanes anyway: teams of 8 WARPS on tiles of 32 conformations instead -- every branch is
+        // uniform and every index a broadcast, as with one lane per conformation; the records of a step are computed concurrently
+        // and their write-backs ordered by colour through the team's split barrier.  Measured on B200 with the coloured rounds
+        // (M conformations/s, lanes vs warps, 2^18 conformations): lig28 297 vs 235, lig33 250 vs 201, lig37 171 vs 167,
+        // norfloxacin (41) 165 vs 150, lig45 141.5 vs 149.5, lig50 113 vs 128.7, lig55 98.2 vs 96.1 (one team per SM),
+        // lig60 75.1 vs 83.8 (one team), lig64 .. vs 87.2.  Rule: from 44 atoms on when two teams (16 warps) fit; with room for one
+        // team only, when the lane-team plan has at most 13 warps (about 58 atoms on).
         const char *et = getenv("PM_TEAM_WARPS_AUTO");
-        if (cpw <= 8 && N >= 46 && !(et && et[0] == '0')) {
+        const int lane_warps = best_w;
+        if (cpw <= 8 && N >= 44 && !(et && et[0] == '0')) {
             PmHostProgram cand;
             if (pm_build_program(N, 32, t->n_bonds, t->bond_idx, t->n_angles, t->angle_idx, t->n_torsions, t->torsion_idx, t->torsion_per, cls,
                                  cand, PM_TEAM_WARPS)) {
@@ -1094,9 +1123,7 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
                 size_t sh, pw;
                 int w;
                 pm_plan((int)cand.blob.size(), n_derived, N, 32, max_smem, 1, &sh, &pw, &w, PM_TEAM_WARPS);
-                // (one team per CTA: lig60 single vector 78.5 vs 72.4 M conformations/s, but batches over 100 000 conformations lose 1.4 %
-                // to the quantisation of 3125 tiles over 148 teams per vector -- two teams required)
-                if (w >= 2 * PM_TEAM_WARPS) {
+                if (w >= 2 * PM_TEAM_WARPS || (w >= PM_TEAM_WARPS && lane_warps <= 13)) {
                     cpw = 32;
                     team_warps = PM_TEAM_WARPS;
                     host = cand;

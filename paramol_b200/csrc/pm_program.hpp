@@ -620,8 +620,13 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
 
     // ------------------------------------------------------------------ tables + blob ---------------------------------
     std::vector<int> star_hdr, axis_hdr;
-    std::vector<int> star_tab = pmh::schedule(star_items, L, &out.n_star_steps, star_hdr, warp_team);
-    std::vector<int> axis_tab = pmh::schedule(axis_items, L, &out.n_axis_steps, axis_hdr, warp_team);
+    // teams of warps: steps of records in several colours, one round of the team's split barrier per colour (default), or
+    // PM_WT_COLOURS=0: strictly disjoint steps of one colour (fewer rounds, but few records find room in a step: lig50's 27 axes
+    // take 8 steps of 8 members instead of 4)
+    const char *wt_col = std::getenv("PM_WT_COLOURS");
+    const bool strict = warp_team && wt_col != nullptr && wt_col[0] == '0';
+    std::vector<int> star_tab = pmh::schedule(star_items, L, &out.n_star_steps, star_hdr, strict);
+    std::vector<int> axis_tab = pmh::schedule(axis_items, L, &out.n_axis_steps, axis_hdr, strict);
     // axis step header: colours | (largest number of i-substituents in the step << 8)
     for (int st = 0; st < out.n_axis_steps; ++st) {
         int max_ni = 0;
@@ -671,7 +676,6 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
     for (int s = 0; s < p.n_star_steps; ++s) {
         std::map<int, std::set<int>> used_by_colour;
         const int n_col = b[p.off_star_hdr + s];
-        if (p.team_warps > 1 && n_col != 1) return 18;  // teams of warps write back concurrently
         for (int l = 0; l < L; ++l) {
             const int rec = b[p.off_star_tab + 2 * (s * L + l)], colour = b[p.off_star_tab + 2 * (s * L + l) + 1];
             if (rec < 0) continue;
@@ -709,7 +713,6 @@ inline int pm_validate_program(const PmHostProgram &p, int N, int n_bonds, const
     for (int s = 0; s < p.n_axis_steps; ++s) {
         std::map<int, std::set<int>> used_by_colour;
         const int n_col = b[p.off_axis_hdr + s] & 0xff, max_ni = b[p.off_axis_hdr + s] >> 8;
-        if (p.team_warps > 1 && n_col != 1) return 28;
         for (int l = 0; l < L; ++l) {
             const int rec = b[p.off_axis_tab + 2 * (s * L + l)], colour = b[p.off_axis_tab + 2 * (s * L + l) + 1];
             if (rec < 0) continue;
