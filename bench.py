@@ -478,7 +478,7 @@ def run_ours(args):
         "config": config_block(args, mm, world, {"conformations_per_gpu": S_rank, "collective": comm_kind}),
         "e2e": {"value": S_total * args.steps / t_e2e, "unit": "conformations/s", "h2d_bytes_per_step": topo.n_slots * 8,
                 "d2h_bytes_per_step": 8 * 8, "ms_per_step": 1e3 * t_e2e / args.steps,
-                "objective_evals_per_s": args.steps / t_e2e, "api": "ObjectiveFunction.f(x) with host x (one CUDA-graph replay per call)",
+                "objective_evals_per_s": args.steps / t_e2e, "api": "ObjectiveFunction.f(x) with host x (one CUDA-graph launch per call through pm_graph_launch / pm_graph_wait; the slots row is read from pinned host memory by pm_prepare_kernel and the 8 sums are written to pinned host memory by the row-sum kernel: those are the h2d / d2h bytes)",
                 "cold_upload": {"seconds": arm.t_upload, "bytes": arm.upload_bytes,
                                 "note": "one-time pinned-host -> HBM staging of the conformation tiles, outside the step"}},
         "gpu_launches": (4 if getattr(topo, "specialized", False) else 3) * args.steps,
