@@ -238,3 +238,37 @@ def test_regularization_batch_matches_rowwise():
         batch = reg.calculate_property(X)
         rows = [reg.calculate_property(X[i]) for i in range(4)]
         assert np.allclose(batch, rows, rtol=0, atol=1e-14)
+
+
+def test_update_systems_deferred_half_gives_the_same_state(kwargs_dict):
+    """``update_systems(..., defer=[])`` (what ``ObjectiveFunction.f`` uses to run the non-critical half of the update while the
+    device evaluates) leaves parameters, value lists, slots and MM-system arrays exactly as the plain call does once the deferred
+    callable has run; before that, ``last_slots`` already holds the new slot rows."""
+    rng = np.random.default_rng(3)
+    states = []
+    for deferred_mode in (False, True):
+        system = _system(kwargs_dict)
+        ps = ParameterSpace()
+        _, x0 = ps.get_optimizable_parameters([system])
+        x0 = np.asarray(x0, dtype=np.float64)
+        for k in range(3):   # consecutive calls: the slots of call k are built on the state call k - 1 left behind
+            x = x0 * (1.0 + 0.05 * np.random.default_rng(10 + k).uniform(-1, 1, len(x0)))
+            if deferred_mode:
+                pending = []
+                ps.update_systems([system], x, defer=pending)
+                assert len(pending) == 1
+                early = [row.copy() for row in ps.last_slots]
+                pending.pop()()
+                assert np.array_equal(early[0], ps.last_slots[0])
+            else:
+                ps.update_systems([system], x)
+        s = system.engine.system
+        states.append(dict(slots=system.engine.current_slots().copy(), last=ps.last_slots[0].copy(), store=system.force_field.store.copy(),
+                           by_system=[list(v) for v in ps.optimizable_parameters_values_by_system],
+                           arrays=[np.array(a, copy=True) for a in (s.bond_par, s.angle_par, s.torsion_par, s.particle_par, s.exception_par)]))
+    a, b = states
+    assert np.array_equal(a["slots"], b["slots"]) and np.array_equal(a["last"], b["last"]) and np.array_equal(a["store"], b["store"])
+    assert a["by_system"] == b["by_system"]
+    for u, v in zip(a["arrays"], b["arrays"]):
+        assert np.array_equal(u, v)
+    assert np.array_equal(a["slots"], a["last"][0])
