@@ -941,9 +941,12 @@ F_REG_MAX_SPILL = 512  # bytes of spill stores tolerated (aniline at fence 6: 20
 
 def f_reg_fence(n_atoms):
     """Blocks between scheduling fences for the forces-in-registers shape: the more atoms, the fewer registers are left for
-    interleaving (measured on B200: aniline 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms with spills; 20 atoms 2 -> 727,
+    interleaving (measured on B200, round-1 body: aniline 4 -> 0.646 ms, 6 -> 0.632 ms, 8 -> 0.659 ms, 10 -> 0.714 ms with spills; final
+    round-2 body, which needs fewer registers (profiles/r3_spec_sweep.txt, barrier every 18 blocks): 4 -> 0.442, 6 -> 0.444, 8 -> 0.437,
+    9 -> 0.453 ms; without the barrier 0.58-0.62 ms: the loose lock step of the warps is what keeps the body in the instruction cache;
+    20 atoms 2 -> 727,
     1 -> 717 M conformations/s; 22 atoms 2 -> 578, 1 -> 652; caffeine 2 -> 409, 1 -> 426; 26 atoms 2 -> 282, 1 -> 390)."""
-    return 6 if n_atoms <= 14 else (2 if n_atoms <= 20 else 1)
+    return 8 if n_atoms <= 14 else (2 if n_atoms <= 20 else 1)
 
 
 def choose_warps_f_reg(n_atoms):
