@@ -13,8 +13,15 @@
 #ifndef PM_MAX_WARPS
 #define PM_MAX_WARPS 16  // warps per CTA (1 persistent CTA per SM)
 #endif
-#define PM_ACOS_N 256    // intervals of the (cos, sin) table behind pm_acos_cs
 #define PM_PI 3.14159265358979323846
+// The table behind pm_acos_cs: tabulated angles theta_e, e = 0 .. PM_ACOS_ENTRIES-1, two double2 per entry: (cos, sin)(theta_e) and
+// (theta_e, 0).  Entries are indexed by round(K cos theta) where |cos theta| <= 1/sqrt(2) (2 NA + 1 of them) and by round(K sin theta)
+// elsewhere (NA + 1 for cos > 0, NA + 1 for cos < 0), so that the nearest entry is found without an inverse trigonometric function
+// and is never further than 1.42 / (2 K) = 0.011 rad away.  PM_ACOS_N + 1 = number of double2 the kernels stage into shared memory.
+#define PM_ACOS_K 64
+#define PM_ACOS_NA 46
+#define PM_ACOS_ENTRIES (4 * PM_ACOS_NA + 3)
+#define PM_ACOS_N (2 * PM_ACOS_ENTRIES - 1)
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
@@ -77,25 +84,49 @@ __device__ __forceinline__ double pm_rsqrt(double x) {
 
 // ---------------------------------------------------------------------------------------------
 // theta in [0, pi] from BOTH c = cos(theta) and s = sin(theta) >= 0 (the angle code has both: the dot product and the
-// norm of the cross product).  An FP32 acosf picks the nearest of PM_ACOS_N+1 tabulated angles theta_q; then
-// sin(theta - theta_q) = s cos(theta_q) - c sin(theta_q) is exact to FP64 rounding and well conditioned for every theta
-// (unlike acos(c) alone near 0 and pi), and theta - theta_q = asin(.) needs a 5-term odd series since |.| < 0.02.
-// 9 FP64 ops + ~15 FP32/integer ops (idle pipes here) instead of ~50 FP64 ops for libm acos.
+// norm of the cross product).  A few FP32 / integer instructions pick a tabulated angle theta_e within 0.011 rad (see
+// PM_ACOS_K above: index by cos in the middle of the range, by sin near 0 and pi, where acos is ill-conditioned in cos); then
+// sin(theta - theta_e) = s cos(theta_e) - c sin(theta_e) is exact to FP64 rounding and well conditioned for every theta, and
+// theta - theta_e = asin(.) needs a 5-term odd series since |.| < 0.02.
+// 10 FP64 ops + ~15 FP32/integer ops (idle pipes here) instead of ~50 FP64 ops for libm acos; no acosf (25 instructions) either.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pm_acos_cs(double c, double s, const double2 *__restrict__ tab) {
-    float cf = __double2float_rn(c);
-    cf = fminf(1.0f, fmaxf(-1.0f, cf));
-    const float th = acosf(cf);
-    int q = __float2int_rn(th * (float)(PM_ACOS_N / PM_PI));
-    q = min(max(q, 0), PM_ACOS_N);
-    const double2 t = tab[q];
+    const float cf = __double2float_rn(c);
+    const float a = fminf(fabsf(cf), 1.0f);
+    float sf;   // ~ sin(theta) for the index only
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(fmaf(-a, a, 1.0f)));
+    const int ia = __float2int_rn(cf * (float)PM_ACOS_K) + PM_ACOS_NA;
+    const int ib = __float2int_rn(sf * (float)PM_ACOS_K) + (cf < 0.0f ? 3 * PM_ACOS_NA + 2 : 2 * PM_ACOS_NA + 1);
+    int e = a <= 0.70710678f ? ia : ib;
+    e = min(max(e, 0), PM_ACOS_ENTRIES - 1);   // (NaN inputs must not index outside the table)
+    const double2 t = tab[2 * e], th = tab[2 * e + 1];
     const double sd = fma(s, t.x, -(c * t.y));
     const double z = sd * sd;
     double p = fma(z, 35.0 / 1152.0, 15.0 / 336.0);
     p = fma(z, p, 3.0 / 40.0);
     p = fma(z, p, 1.0 / 6.0);
     const double delta = fma(sd * z, p, sd);
-    return fma((double)q, PM_PI / PM_ACOS_N, delta);
+    return th.x + delta;
+}
+
+#include <cmath>
+#include <vector>
+// Host side: the table as 2 * (PM_ACOS_N + 1) doubles (pm_create, pm_lls_create).
+static inline std::vector<double> pm_acos_table_host() {
+    std::vector<double> tab(2 * (size_t)(PM_ACOS_N + 1), 0.0);
+    for (int e = 0; e < PM_ACOS_ENTRIES; ++e) {
+        double th;
+        if (e <= 2 * PM_ACOS_NA)
+            th = std::acos((double)(e - PM_ACOS_NA) / PM_ACOS_K);
+        else if (e <= 3 * PM_ACOS_NA + 1)
+            th = std::asin((double)(e - (2 * PM_ACOS_NA + 1)) / PM_ACOS_K);
+        else
+            th = PM_PI - std::asin((double)(e - (3 * PM_ACOS_NA + 2)) / PM_ACOS_K);
+        tab[4 * e] = std::cos(th);
+        tab[4 * e + 1] = std::sin(th);
+        tab[4 * e + 2] = th;
+    }
+    return tab;
 }
 
 struct pm_d3 {

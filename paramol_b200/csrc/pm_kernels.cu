@@ -1230,12 +1230,7 @@ extern "C" int pm_create(const pm_topology *t, int device, int conf_per_tile, pm
     for (int a = 0; a < N; ++a) ident[9 * a] = ident[9 * a + 4] = ident[9 * a + 8] = 1.0;
     PM_CUDA_H(cudaMalloc(&h->d_metric, sizeof(double) * 9 * N));
     PM_CUDA_H(cudaMemcpy(h->d_metric, ident.data(), sizeof(double) * 9 * N, cudaMemcpyHostToDevice));
-    std::vector<double> tab(2 * (PM_ACOS_N + 1));
-    for (int q = 0; q <= PM_ACOS_N; ++q) {
-        const double th = (double)q * (PM_PI / PM_ACOS_N);
-        tab[2 * q] = cos(th);
-        tab[2 * q + 1] = sin(th);
-    }
+    const std::vector<double> tab = pm_acos_table_host();
     PM_CUDA_H(cudaMalloc(&h->d_acos, sizeof(double) * tab.size()));
     PM_CUDA_H(cudaMemcpy(h->d_acos, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     g.ints = h->d_ints;

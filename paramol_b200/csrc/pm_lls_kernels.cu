@@ -638,12 +638,7 @@ extern "C" int pm_lls_create(int device, int n_atoms, int conf_per_tile, int n_t
         p->panels.t0[q] = t0 < t1 ? t0 : 0;
         p->panels.t1[q] = t0 < t1 ? t1 : 0;
     }
-    std::vector<double> tab(2 * (PM_ACOS_N + 1));
-    for (int q = 0; q <= PM_ACOS_N; ++q) {
-        const double th = (double)q * (PM_PI / PM_ACOS_N);
-        tab[2 * q] = cos(th);
-        tab[2 * q + 1] = sin(th);
-    }
+    const std::vector<double> tab = pm_acos_table_host();
     if (cudaMalloc(&p->acos_dev, sizeof(double) * tab.size()) != cudaSuccess ||
         cudaMemcpy(p->acos_dev, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&p->terms_dev, sizeof(LlsTerm) * n_terms) != cudaSuccess ||
