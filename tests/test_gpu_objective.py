@@ -388,3 +388,44 @@ def test_nonbonded_cache_gives_the_same_objective(kwargs_dict, golden_dir):
         assert np.all(np.abs(va - vb) <= 1e-12 * np.abs(va))
         # bonded-only fit: one cache for all calls; with optimizable charges/LJ every vector brings its own
         assert (len(keys) > 1) == expect_refresh
+
+
+@pytest.mark.parametrize("mode", ["zero_copy", "copies", "eager"])
+def test_single_vector_graph_paths_agree_and_keep_the_host_state(kwargs_dict, golden_dir, mode, monkeypatch):
+    """``f(x)`` through the captured graph -- launched and waited for by ``pm_graph_launch`` / ``pm_graph_wait``, with zero-copy ends
+    (default) or with the copy nodes (``PARAMOL_B200_ZERO_COPY=0``) -- and without a graph (``PARAMOL_B200_GRAPHS=0``) gives the same
+    values over a sequence of trial vectors (the graph is captured at the third call, so the sequence crosses the switch), and after
+    every call the host state the deferred half of ``update_systems`` maintains (MM-system arrays, value lists) matches the slots
+    row that was evaluated."""
+    if mode == "copies":
+        monkeypatch.setenv("PARAMOL_B200_ZERO_COPY", "0")
+    if mode == "eager":
+        monkeypatch.setenv("PARAMOL_B200_GRAPHS", "0")
+
+    def run():
+        system = _aniline(kwargs_dict, golden_dir)
+        ps = ParameterSpace()
+        _, x0 = ps.get_optimizable_parameters([system])
+        x0 = np.asarray(x0, dtype=np.float64)
+        ps.calculate_prior_widths("arithmetic")
+        e_prop, f_prop = EnergyProperty([system]), ForceProperty([system], term_type="components")
+        e_prop.calculate_variance()
+        f_prop.calculate_variance()
+        of = ObjectiveFunction(None, ps, [e_prop, f_prop, Regularization(x0.copy(), ps.prior_widths, "L2")], [system],
+                               checkpoint_freq=10 ** 9)
+        values = []
+        for k in range(7):
+            x = x0 * (1.0 + 0.02 * np.random.default_rng(100 + k).uniform(-1, 1, len(x0)))
+            values.append(of.f(x))
+            assert np.array_equal(system.engine.current_slots(), ps.last_slots[0][0])
+            s = system.engine.system
+            flat = np.concatenate([np.ravel(a) for a in (s.bond_par, s.angle_par, s.torsion_par, s.particle_par, s.exception_par)])
+            assert np.array_equal(flat, ps.last_slots[0][0])
+            assert len(ps.optimizable_parameters_values_by_system[0]) == len(x0)
+        return np.asarray(values)
+
+    got = run()
+    monkeypatch.setenv("PARAMOL_B200_GRAPHS", "0")
+    want = run()
+    assert np.all(np.isfinite(got)) and len(set(np.round(got, 12))) == len(got)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-12
