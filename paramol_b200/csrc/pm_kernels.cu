@@ -621,6 +621,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #pragma unroll kBlkUnroll
                     for (int k = 0; k < 4; ++k) {
                         const int io = rec[k];
+                        if (WT && io == tile_d * (int)sizeof(double)) {   // a padding row (tiles of 3 atoms, empty slots): uniform skip
+                            if (k == 0) round_wait();
+                            continue;
+                        }
                         const int2 qq = *reinterpret_cast<const int2 *>(rec + 8 + 2 * k);
                         const unsigned q[4] = {(unsigned)qq.x & 0xffffu, (unsigned)qq.x >> 16, (unsigned)qq.y & 0xffffu, (unsigned)qq.y >> 16};
                         const pm_d3 xi = pm_ldo<CPW>(xc_base, io);

@@ -408,20 +408,31 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
     // from 4 lanes on the blocks win -- norfloxacin 142 -> 150, lig60 63 -> 71)
     const bool use_blocks = L >= 4 && out.n_pairs > 0 && out.n_pairs < 65535 && !(pb_env && pb_env[0] == '0');
     if (use_blocks) {
+        // (measured and dropped for teams of warps: 2 L - 1 = 15 tiles of 3-4 atoms for 45-56 atoms, so that every position of the
+        // tournament is full -- lig50 131.4 vs 134.9 M conformations/s with its 13 tiles of 4: the padding columns cost what the
+        // idle member saves)
         const int T = (N + PMH_IT - 1) / PMH_IT;
         auto tile_atom = [&](int t, int k) {
             const int a = t + k * T;
             return a < N ? a : -1;
         };
+        auto tile_size = [&](int t) {
+            int n = 0;
+            for (int k = 0; k < 4; ++k) n += tile_atom(t, k) >= 0;
+            return n;
+        };
         std::map<std::pair<int, int>, int> pair_index;
         for (int q = 0; q < out.n_pairs; ++q) pair_index[std::make_pair(out.pair_map[3 * q], out.pair_map[3 * q + 1])] = q;
         struct Block {
-            int ti, tj;
+            int ti, tj;   // row tile, column tile
             int idx[16];
         };
         std::vector<Block> blocks;
-        for (int ti = 0; ti < T; ++ti)
-            for (int tj = ti; tj < T; ++tj) {
+        for (int t0 = 0; t0 < T; ++t0)
+            for (int t1 = t0; t1 < T; ++t1) {
+                // rows = the tile with fewer atoms (teams of warps skip padding rows)
+                const bool flip = warp_team && tile_size(t1) < tile_size(t0);
+                const int ti = flip ? t1 : t0, tj = flip ? t0 : t1;
                 Block b;
                 b.ti = ti;
                 b.tj = tj;
@@ -482,6 +493,25 @@ inline bool pm_build_program(int N, int cpw, int n_bonds, const int *bond_idx, i
                 sched.push_back(cur);
             }
             if (best.empty() || sched.size() < best.size()) best = sched;
+        }
+        // teams of warps, odd tile count with (T + 1) / 2 <= L: the round-robin tournament (circle method) -- round r pairs the tiles
+        // r + i and r - i (mod T), i = 1 .. (T - 1) / 2, and gives tile r its diagonal block: T positions, every tile exactly once
+        // per position (lig60: 15 positions instead of the 17 the greedy packing finds)
+        if (warp_team && (T & 1) && (T + 1) / 2 <= L) {
+            std::map<std::pair<int, int>, int> block_of;
+            for (size_t i = 0; i < blocks.size(); ++i)
+                block_of[std::make_pair(std::min(blocks[i].ti, blocks[i].tj), std::max(blocks[i].ti, blocks[i].tj))] = (int)i;
+            std::vector<std::vector<int>> rr;
+            for (int r = 0; r < T; ++r) {
+                std::vector<int> cur;
+                for (int i = 0; i <= (T - 1) / 2; ++i) {
+                    const int a = (r + i) % T, c = ((r - i) % T + T) % T;
+                    auto it = block_of.find(std::make_pair(std::min(a, c), std::max(a, c)));
+                    if (it != block_of.end()) cur.push_back(it->second);
+                }
+                if (!cur.empty()) rr.push_back(cur);
+            }
+            if (rr.size() < best.size()) best = rr;
         }
         const int dummy = N * AO;  // rows of the padding atom behind the tile (zero coordinates, never-read forces)
         for (auto &pos : best)
